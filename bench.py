@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- RUVIII cells/s on the BASELINE.json workload (C3: 11,000 samples x 20,000 genes, 400 PRPS sets x 3,
+1,000 control genes, k = 10), one process per GPU, genes sharded over the ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C1|C4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one complete pass of the hot path over the resident assay:
+residop -> Gram -> allreduce -> eigensolve -> broadcast -> projection -> control-gene products -> allreduce ->
+k x k solve -> rank-k update (K1..K6 of DESIGN.md).  `value` = cells (samples x genes x #k) per second with the
+inputs resident in HBM; `e2e` = the same through `ruviii_normalise` with pinned HOST buffers in and out.
+
+torch is imported only for torch.distributed (gloo rendezvous: NCCL id broadcast, barrier, max over ranks) and
+for pinned host allocations.  Every kernel in the timed region belongs to libruviii_b200.so.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C3", "C4", "tiny"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probes", action="store_true", help="also measure copy / cuBLAS Dgemm / DMMA ceilings")
+    return ap.parse_args()
+
+
+def workload_problem(name):
+    from ruviii_b200.synth import make_config, make_problem
+    if name == "tiny":
+        return make_problem(m1=600, n=4000, groups=40, rep=3, n_ctl=300, k=5, seed=99), [5]
+    p = make_config("C3" if name == "C4" else name)
+    ks = list(range(1, 21)) if name == "C4" else [p.k]
+    return p, ks
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def cpu_reference_run(sample, ks, threads_note=True):
+    """The reference's own algorithm on the host cores: the literal numpy restatement of ruvIII.R:93-146 looped
+    per k as ruvIIIMultipleK.R:75-94 does.  R is not installed, so kind = "port"."""
+    from oracle import ruviii_oracle as O
+    t0 = time.perf_counter()
+    for k in ks:
+        O.ruvIII_literal(sample.assay, sample.sample_names, sample.replicate_data, sample.replicate_names, sample.ctl, k,
+                         apply_log=False)
+    dt = time.perf_counter() - t0
+    cells = sample.meta["m1"] * sample.meta["n"] * len(ks)
+    return cells / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([d.get("num_threads", 1) for d in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_sample(workload):
+    """Bounded sample of the workload for the CPU arm: same generator, same gene count, about a tenth of the
+    samples and PRPS sets.  The literal algorithm costs O(m^3), so cells/s at this size OVERSTATES what the
+    reference would reach at the full size (it flatters the CPU, not us)."""
+    from ruviii_b200.synth import make_config, make_problem
+    if workload == "tiny":
+        return make_problem(m1=300, n=2000, groups=20, rep=3, n_ctl=150, k=5, seed=98), "tiny/2"
+    scale = 1200.0 / 11000.0 if workload in ("C3", "C4") else 1.0
+    p = make_config("C3" if workload == "C4" else workload, scale_rows=scale)
+    return p, "%s generator at %d samples x %d genes, %d PRPS rows (rows scaled x%.3f), literal per-k loop" % (
+        workload, p.meta["m1"], p.meta["n"], p.meta["n_ps"], scale)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample, desc = reference_sample(args.workload)
+        ks = list(range(1, 21)) if args.workload == "C4" else [sample.k]
+        if args.workload == "C4":
+            ks = ks[:2]
+            desc += "; 2 of the 20 k values timed (each k is an independent full ruvIII in the reference)"
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_reference_run(sample, ks)
+        vals, times = [], []
+        for _ in range(args.steps):
+            v, dt = cpu_reference_run(sample, ks)
+            vals.append(v)
+            times.append(dt)
+        v = sample.meta["m1"] * sample.meta["n"] * len(ks) * len(times) / sum(times)
+        line = {"impl": "reference", "metric": "RUVIII cells/s", "value": v, "unit": "cells/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "sample": desc},
+                "cpu_baseline": {"value": v, "unit": "cells/s", "cores": blas_threads(), "kind": "port", "sample": desc,
+                                 "note": "numpy/OpenBLAS literal restatement of ruvIII.R:93-146 (R is not installed); "
+                                         "stock R often links a single-threaded BLAS and would be slower"},
+                "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from ruviii_b200 import _cabi, api
+
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    p, ks = workload_problem(args.workload)
+    m1, n, n_ps = p.meta["m1"], p.meta["n"], p.meta["n_ps"]
+    g0, g1 = n * rank // world, n * (rank + 1) // world
+    n_loc = g1 - g0
+    groups = api.group_codes(list(p.sample_names) + list(p.replicate_names))
+
+    # pinned host buffers holding this rank's gene shard (the R shim would hand over the assay slab)
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    Y_h = pinned((m1, n_loc))
+    PS_h = pinned((n_ps, n_loc))
+    Y_h[...] = p.Y[:, g0:g1]
+    PS_h[...] = p.replicate_data[:, g0:g1]
+    ctl_loc = np.ascontiguousarray(p.ctl[g0:g1])
+    out_h = pinned((len(ks), m1, n_loc))
+
+    if world > 1:
+        ids = [_cabi.Engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng = _cabi.Engine(rank=rank, world=world, device=local_rank, nccl_id=ids[0])
+    else:
+        eng = _cabi.Engine(devices=[local_rank])
+    prm = _cabi.make_params(mode=_cabi.MODE_STACKED, apply_log=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg: plan + upload once, then W + K full passes -------------------------------------
+    eng.plan(prm, m1, n_loc, n_ps, groups, ctl_loc, ks)
+    eng.upload(Y_h, PS_h)
+    for _ in range(args.warmup):
+        eng.run()
+    barrier()
+    torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    stage_ms = {}
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = eng.run()
+        dev_ms += info.ms_total
+        for name, _ in info._fields_:
+            if name.startswith("ms_"):
+                stage_ms[name] = stage_ms.get(name, 0.0) + getattr(info, name)
+    torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    wall_ms = max_over_ranks((t1 - t0) * 1e3 / args.steps)
+    dev_ms = max_over_ranks(dev_ms / args.steps)
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    launches = info.kernel_launches * args.steps
+    cells = float(m1) * n * len(ks)
+    value = cells / (dev_ms * 1e-3)
+
+    # ---- end-to-end leg: ruviii_normalise, pinned host in / pinned host out -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(min(args.warmup, 2)):
+            eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
+        barrier()
+        te0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 5))
+        for _ in range(n_e2e):
+            eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
+        barrier()
+        te = max_over_ranks((time.perf_counter() - te0) / n_e2e)
+        e2e = {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3,
+               "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world,
+               "d2h_bytes_per_step": int(out_h.nbytes) * world, "steps": n_e2e,
+               "api": "ruviii_normalise (C ABI) with pinned host buffers, copies inside the timed region"}
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel of this library ------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    nk = len(ks)
+    upd_bytes = 8.0 * m1 * n_loc * (1 + nk)                          # K6: read Y once, write every requested k
+    res_bytes = 16.0 * info.active_rows * n_loc                      # K1: 16 B per non-singleton cell
+    gram_flops = float(info.active_rows) * (info.active_rows + 1) * n_loc   # K2: symmetric half, FMA = 2 flop
+    kernels = {
+        "update": {"bound": "hbm", "ms": stage_ms["ms_update"], "achieved": upd_bytes / (stage_ms["ms_update"] * 1e-3) / 1e9,
+                   "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": upd_bytes},
+        "residop": {"bound": "hbm", "ms": stage_ms["ms_residop"], "achieved": res_bytes / max(stage_ms["ms_residop"], 1e-6) / 1e6,
+                    "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": res_bytes},
+        "gram": {"bound": "fp64-tensor", "ms": stage_ms["ms_gram"], "achieved": gram_flops / max(stage_ms["ms_gram"], 1e-6) / 1e9,
+                 "peak": 40.0, "unit": "TFLOP/s", "algorithmic_flops": gram_flops,
+                 "peak_note": "nominal B200 FP64 (DMMA) 40 TFLOP/s; MEASURED_PEAKS.json holds no FP64 figure"},
+    }
+    for kinfo in kernels.values():
+        kinfo["frac"] = kinfo["achieved"] / kinfo["peak"]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("update_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    up = kernels["update"]
+    roofline = {"kernel": "update_kernel (K6, ruvIII.R:145)", "bound": "hbm", "achieved": up["achieved"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": up["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": upd_bytes,
+                "share_of_step": stage_ms["ms_update"] / max(stage_ms["ms_total"], 1e-9)}
+
+    probes = None
+    if args.probes:
+        probes = {"copy_gbs": eng.probe(0, 2048), "cublas_dgemm_tflops_8192": eng.probe(1, 8192),
+                  "dmma_issue_tflops": eng.probe(2, 0)}
+        kernels["gram"]["frac_of_cublas_dgemm"] = kernels["gram"]["achieved"] / probes["cublas_dgemm_tflops_8192"]
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        sample, desc = reference_sample(args.workload)
+        ks_cpu = ks if args.workload != "C4" else ks[:2]
+        v, dt = cpu_reference_run(sample, ks_cpu)
+        cpu_baseline = {"value": v, "unit": "cells/s", "cores": blas_threads(), "kind": "port", "sample": desc,
+                        "seconds": dt}
+
+    line = {
+        "metric": "RUVIII cells/s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "ms_per_step_wall": wall_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d samples x %d genes, %d PRPS rows in %d sets, %d control genes, k=%s, ruvIII (stacked) "
+                               "semantics, genes sharded over %d GPU(s)" % (args.workload, m1, n, n_ps, p.meta["groups"],
+                                                                          int(p.ctl.sum()), ks if nk > 1 else ks[0], world),
+                   "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % ((Y_h.nbytes + PS_h.nbytes) / 1e9),
+                   "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next}},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes,
+    }
+    print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,159 @@
+/*
+ * ruviii.h -- C ABI of the B200-native RUV-III normalisation engine (libruviii_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of RMolania/RUVIIIPRPS: the arithmetic of
+ *   ruvIII()          R/ruvIII.R:116-149
+ *   fastruvIII()      R/fastruvIII.R:133-180
+ *   ruvIIIMultipleK() R/ruvIIIMultipleK.R:75-94  (one call computes every k; the reference loops ruvIII per k)
+ * as driven by normalise() (R/normalise.R:143-161).  The reference declares, but never implemented, a
+ * native boundary in R/RcppExports.R:4-26 (`.Call('_RUVIIIPRPS_<fn>', PACKAGE='RUVIIIPRPS', ...)`); the
+ * entry points below are what an `_RUVIIIPRPS_*` .Call shim binds (see INTEGRATION.md and r-shim/).
+ *
+ * Plain C: pointers and sizes only.  No CPU fallback exists: every compute entry point needs a
+ * CUDA device of compute capability 10.0 (sm_100a) and returns RUVIII_ERR_CUDA otherwise.
+ *
+ * Layout conventions (all FP64):
+ *   - An R matrix is column-major.  The assay is genes x samples (n x m1) column-major, which is the same
+ *     bytes as "samples x genes row-major with the genes contiguous".  Every matrix argument below is
+ *     described in that row-major reading, so `Y` IS the assay buffer and `newY_out` IS the buffer of the
+ *     new assay `t(newY[1:m1, ])` (ruvIII.R:158): no transposition on either side.
+ *   - `PS` is `replicate.data` (pseudo-samples x genes, normalise.R:143) in the same row-major reading,
+ *     i.e. R's `t(replicate.data)` buffer -- the genes x pseudo-samples matrix normalise.R:143 starts from.
+ *   - `fullalpha_out` is rows x n row-major (R: t(fullalpha)); `W_out` blocks are m_w x k row-major (R: t(W)).
+ *   - Inputs are read-only, never written, never retained after the call returns.
+ */
+#ifndef RUVIII_B200_H
+#define RUVIII_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUVIII_ABI_VERSION 1
+
+/* status codes */
+#define RUVIII_OK               0
+#define RUVIII_ERR_INVALID      1   /* bad argument / dimension mismatch (len(ctl) != n, group id < 0, k < 0, ...) */
+#define RUVIII_ERR_CUDA         2   /* CUDA runtime failure, or no sm_100 device present                        */
+#define RUVIII_ERR_NCCL         3
+#define RUVIII_ERR_SOLVER       4   /* cuSOLVER failure / eigensolver did not converge                          */
+#define RUVIII_ERR_SINGULAR     5   /* ac %*% t(ac) is not positive definite: R's solve() (ruvIII.R:144) errors  */
+#define RUVIII_ERR_UNSUPPORTED  6
+#define RUVIII_ERR_STATE        7   /* resident API called out of order                                          */
+
+/* which R entry point's semantics to follow (they are NOT interchangeable) */
+#define RUVIII_MODE_STACKED 0  /* ruvIII.R: Y = rbind(samples, PRPS); mu over all m rows; W has m rows            */
+#define RUVIII_MODE_FAST    1  /* fastruvIII.R: Y = samples; M from PRPS rows only; mu over m1 rows; W has m1 rows */
+
+typedef struct ruviii_handle ruviii_handle;
+
+typedef struct ruviii_params {
+    int32_t struct_size;     /* sizeof(ruviii_params), for forward compatibility                              */
+    int32_t mode;            /* RUVIII_MODE_*                                                                  */
+    int32_t apply_log;       /* ruvIII.R:88-92: log2(assay + pseudo_count) on the assay rows (not on PS)       */
+    int32_t average_rep;     /* ruvIII.R:148-149 (apply.average.rep); 0 = off (default)                        */
+    double  pseudo_count;    /* ruvIII.R:42                                                                    */
+    int32_t n_alpha_rows;    /* rows of fullalpha to produce: 0 = max(ks) (all the update needs);              *
+                              * -1 = r = min(m - ncol(M), sum(ctl)) as ruvIII.R:140 keeps (return.info = TRUE)  */
+    int32_t gram_side;       /* 0 = auto (smaller side), 1 = sample side Y0 Y0', 2 = gene side Y0' Y0          */
+    int32_t want_ps_rows;    /* also produce newY for the PRPS rows (STACKED, return.info & !save.se.obj)       */
+    int32_t reserved[7];
+} ruviii_params;
+
+/* what one run did; times are device times (CUDA events on the compute stream of shard 0), in ms */
+typedef struct ruviii_info {
+    int32_t struct_size;
+    int32_t m, m1, n_ps, n;            /* rows of the stacked matrix, samples, pseudo-samples, genes (local)   */
+    int32_t p;                         /* ncol(M): number of replicate groups incl. singletons                  */
+    int32_t active_rows;               /* rows belonging to non-singleton groups (nonzero rows of Y0)           */
+    int32_t r;                         /* min(m - p, sum(ctl))  (ruvIII.R:140)                                  */
+    int32_t n_ctl;                     /* sum(ctl) over all shards                                              */
+    int32_t kmax_eff;                  /* min(max(ks), r)  (ruvIII.R:142)                                       */
+    int32_t no_replicates;             /* 1 when ncol(M) >= m: newY = Y (ruvIII.R:128-129)                      */
+    int32_t gram_side;                 /* 1 sample side, 2 gene side                                            */
+    int32_t n_shards;                  /* GPUs used by this handle (this process)                               */
+    int32_t kernel_launches;           /* kernels of this library launched by the last run                      */
+    float ms_log, ms_residop, ms_gram, ms_gram_reduce, ms_allreduce_gram, ms_eigen, ms_bcast,
+          ms_project, ms_ctl, ms_allreduce_ctl, ms_solve, ms_update, ms_total;
+    float ms_h2d, ms_d2h;              /* host<->device copies (only in ruviii_normalise / upload / download)   */
+    double eig_top, eig_kmax, eig_next;/* lambda_1, lambda_kmax, lambda_kmax+1 (gap that conditions newY)       */
+} ruviii_info;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+
+int  ruviii_abi_version(void);
+
+/* Number of visible sm_100 devices (0 when there is no GPU; never fails). */
+int  ruviii_device_count(void);
+
+/* One process driving `ndev` GPUs (what an R session does): genes are sharded over the devices internally,
+ * NCCL communicators are created with ncclCommInitAll.  devices == NULL means 0..ndev-1. */
+int  ruviii_create(ruviii_handle** out, const int32_t* devices, int32_t ndev);
+
+/* One process per GPU (torchrun-style launch).  Every rank passes the 128-byte id rank 0 obtained from
+ * ruviii_nccl_unique_id().  Each rank then calls the entry points below with ITS gene shard
+ * (n = local genes, ctl/Y/PS/newY restricted to those columns); W and eigenvalues are replicated. */
+int  ruviii_nccl_unique_id(void* out128);
+int  ruviii_create_rank(ruviii_handle** out, int32_t device, int32_t rank, int32_t nranks,
+                        const void* nccl_unique_id128);
+
+void ruviii_destroy(ruviii_handle* h);
+
+/* Message of the last failure on this handle (or of the last failed create when h == NULL). */
+const char* ruviii_last_error(const ruviii_handle* h);
+
+/* ---- one-shot, host buffers in and out: what the R shim calls ------------------------------------------
+ *
+ * Replaces ruvIII.R:116-149 / fastruvIII.R:133-180 and the per-k loop of ruvIIIMultipleK.R:75-94.
+ *   Y            m1 x n   (row stride ldY   >= n)  the assay, see layout note
+ *   PS           n_ps x n (row stride ldPS  >= n)  replicate.data
+ *   group_of_row length m1 + n_ps in STACKED mode (factor codes of row.names(Y), ruvIII.R:101; any ids >= 0,
+ *                need not be dense), length n_ps in FAST mode (row.names(replicate.data), fastruvIII.R:117)
+ *   ctl          length n, nonzero = negative-control gene (tological(), ruvIII.R:80-84,102)
+ *   ks, nk       the k values (ruvIIIMultipleK's vector); k = 0 copies Y (ruvIII.R:134-136)
+ *   newY_out     nk blocks of m1 x n (row stride n), block i = result for ks[i]
+ *   newY_ps_out  NULL, or nk blocks of n_ps x n (STACKED with want_ps_rows)
+ *   fullalpha_out NULL, or rows x n with rows = info->kmax_eff (n_alpha_rows = 0) or info->r (-1)
+ *   W_out        NULL, or nk blocks back to back, block i = m_w x min(ks[i], r) row-major, m_w = m (STACKED) / m1 (FAST)
+ *   info         NULL or filled on return
+ */
+int ruviii_normalise(ruviii_handle* h, const ruviii_params* params,
+                     const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                     const double* PS, int64_t ldPS, int32_t n_ps,
+                     const int32_t* group_of_row, const uint8_t* ctl,
+                     const int32_t* ks, int32_t nk,
+                     double* newY_out, double* newY_ps_out,
+                     double* fullalpha_out, double* W_out, ruviii_info* info);
+
+/* ---- resident API: plan once, keep Y on the device, run many times ------------------------------------- */
+
+int ruviii_plan(ruviii_handle* h, const ruviii_params* params, int32_t m1, int32_t n, int32_t n_ps,
+                const int32_t* group_of_row, const uint8_t* ctl, const int32_t* ks, int32_t nk);
+int ruviii_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS);
+int ruviii_run(ruviii_handle* h, ruviii_info* info);
+int ruviii_download(ruviii_handle* h, double* newY_out, double* newY_ps_out,
+                    double* fullalpha_out, double* W_out);
+/* Small replicated results of the last run: eigenvalues (descending, `count` of them are written). */
+int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count);
+
+/* Skip residop/Gram/eigensolve and start from a previously returned fullalpha (ruvIII.R:138, the reference's
+ * only reuse mechanism).  rows x n row-major; must be called after ruviii_plan and before ruviii_run. */
+int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows);
+
+/* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
+ * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
+ * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */
+int ruviii_fast_residop(ruviii_handle* h, const double* A_rowmajor_rows_x_n, int32_t rows, int32_t n,
+                        const int32_t* group_of_row, double* out);
+
+/* ---- micro-benchmarks used by bench.py to state practical ceilings beside the roofline ----------------- */
+/* which: 0 = device copy GB/s (bytes read+written), 1 = cuBLAS Dgemm TFLOP/s at size^3, 2 = DMMA issue peak TFLOP/s */
+int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUVIII_B200_H */

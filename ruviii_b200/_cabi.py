@@ -1,0 +1,279 @@
+"""ctypes binding of include/ruviii.h (libruviii_b200.so).
+
+The shared library is the product; this module only marshals numpy buffers into its C ABI.  There is no
+fallback of any kind: if the library is missing or no sm_100 GPU is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libruviii_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_SOLVER, ERR_SINGULAR, ERR_UNSUPPORTED, ERR_STATE = range(8)
+MODE_STACKED, MODE_FAST = 0, 1
+
+# every symbol include/ruviii.h declares (tests/test_cabi.py checks the header against this list and the .so)
+SYMBOLS = [
+    "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
+    "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
+    "ruviii_download", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("apply_log", C.c_int32),
+                ("average_rep", C.c_int32), ("pseudo_count", C.c_double), ("n_alpha_rows", C.c_int32),
+                ("gram_side", C.c_int32), ("want_ps_rows", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class Info(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("m", C.c_int32), ("m1", C.c_int32), ("n_ps", C.c_int32),
+                ("n", C.c_int32), ("p", C.c_int32), ("active_rows", C.c_int32), ("r", C.c_int32),
+                ("n_ctl", C.c_int32), ("kmax_eff", C.c_int32), ("no_replicates", C.c_int32),
+                ("gram_side", C.c_int32), ("n_shards", C.c_int32), ("kernel_launches", C.c_int32),
+                ("ms_log", C.c_float), ("ms_residop", C.c_float), ("ms_gram", C.c_float),
+                ("ms_gram_reduce", C.c_float), ("ms_allreduce_gram", C.c_float), ("ms_eigen", C.c_float),
+                ("ms_bcast", C.c_float), ("ms_project", C.c_float), ("ms_ctl", C.c_float),
+                ("ms_allreduce_ctl", C.c_float), ("ms_solve", C.c_float), ("ms_update", C.c_float),
+                ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("eig_top", C.c_double), ("eig_kmax", C.c_double), ("eig_next", C.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class RuviiiError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("ruviii error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libruviii_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C ruviii_b200/csrc`. There is no CPU or PyTorch fallback for the RUV-III hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL if False else C.RTLD_LOCAL)
+    dp, ip, bp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_void_p
+    H = C.c_void_p
+    lib.ruviii_abi_version.restype = C.c_int
+    lib.ruviii_device_count.restype = C.c_int
+    lib.ruviii_create.argtypes = [C.POINTER(H), ip, C.c_int32]
+    lib.ruviii_nccl_unique_id.argtypes = [vp]
+    lib.ruviii_create_rank.argtypes = [C.POINTER(H), C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.ruviii_destroy.argtypes = [H]
+    lib.ruviii_destroy.restype = None
+    lib.ruviii_last_error.argtypes = [H]
+    lib.ruviii_last_error.restype = C.c_char_p
+    lib.ruviii_normalise.argtypes = [H, C.POINTER(Params), vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int64,
+                                     C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.POINTER(Info)]
+    lib.ruviii_plan.argtypes = [H, C.POINTER(Params), C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32]
+    lib.ruviii_upload.argtypes = [H, vp, C.c_int64, vp, C.c_int64]
+    lib.ruviii_run.argtypes = [H, C.POINTER(Info)]
+    lib.ruviii_download.argtypes = [H, vp, vp, vp, vp]
+    lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
+    lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
+    lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
+    lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("ruviii_destroy", "ruviii_last_error"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _rowmajor(a, name):
+    """A C-contiguous float64 2-D view; an F-ordered genes x samples assay must be passed as ``assay.T``."""
+    a = np.asarray(a)
+    if a.dtype != np.float64 or a.ndim != 2:
+        raise TypeError("%s must be a 2-D float64 array" % name)
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def make_params(mode=MODE_STACKED, apply_log=False, pseudo_count=1.0, average_rep=False, n_alpha_rows=0,
+                want_ps_rows=False, gram_side=0):
+    p = Params()
+    p.struct_size = C.sizeof(Params)
+    p.mode = mode
+    p.apply_log = int(bool(apply_log))
+    p.pseudo_count = float(pseudo_count)
+    p.average_rep = int(bool(average_rep))
+    p.n_alpha_rows = int(n_alpha_rows)
+    p.want_ps_rows = int(bool(want_ps_rows))
+    p.gram_side = int(gram_side)
+    return p
+
+
+class Engine:
+    """Owns one ``ruviii_handle`` (device buffers, NCCL communicators, cuSOLVER handle)."""
+
+    def __init__(self, devices=None, *, rank=None, world=None, device=None, nccl_id=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if rank is None:
+            devices = [0] if devices is None else list(devices)
+            arr = (C.c_int32 * len(devices))(*devices)
+            rc = self._lib.ruviii_create(C.byref(self._h), arr, len(devices))
+        else:
+            buf = None if nccl_id is None else C.create_string_buffer(bytes(nccl_id), 128)
+            rc = self._lib.ruviii_create_rank(C.byref(self._h), int(device), int(rank), int(world), buf)
+        if rc != OK:
+            raise RuviiiError(rc, self._lib.ruviii_last_error(None).decode())
+        self._plan = None
+
+    @staticmethod
+    def nccl_unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.ruviii_nccl_unique_id(buf)
+        if rc != OK:
+            raise RuviiiError(rc, lib.ruviii_last_error(None).decode())
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.ruviii_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != OK:
+            raise RuviiiError(rc, self._lib.ruviii_last_error(self._h).decode())
+
+    # ---- resident API -----------------------------------------------------------------------------------
+    def plan(self, params, m1, n, n_ps, group_of_row, ctl, ks):
+        group_of_row = np.ascontiguousarray(group_of_row, dtype=np.int32)
+        ctl = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        if ctl.shape[0] != n:
+            raise RuviiiError(ERR_INVALID, "len(ctl) != n")
+        need = n_ps if params.mode == MODE_FAST else m1 + n_ps
+        if group_of_row.shape[0] != need:
+            raise RuviiiError(ERR_INVALID, "group_of_row has %d entries, expected %d" % (group_of_row.shape[0], need))
+        self._check(self._lib.ruviii_plan(self._h, C.byref(params), m1, n, n_ps, _ptr(group_of_row), _ptr(ctl),
+                                          _ptr(ks), ks.shape[0]))
+        self._plan = dict(params=params, m1=m1, n=n, n_ps=n_ps, ks=[int(k) for k in ks])
+
+    def upload(self, Y, PS):
+        Y = _rowmajor(Y, "Y")
+        PS = _rowmajor(PS, "PS")
+        self._check(self._lib.ruviii_upload(self._h, _ptr(Y), Y.strides[0] // 8, _ptr(PS), PS.strides[0] // 8))
+
+    def run(self):
+        info = Info()
+        self._check(self._lib.ruviii_run(self._h, C.byref(info)))
+        self._info = info
+        return info
+
+    def set_fullalpha(self, fullalpha):
+        fa = _rowmajor(fullalpha, "fullalpha")
+        self._check(self._lib.ruviii_set_fullalpha(self._h, _ptr(fa), fa.shape[0]))
+
+    def eigenvalues(self, count):
+        out = np.empty(count, dtype=np.float64)
+        self._check(self._lib.ruviii_eigenvalues(self._h, _ptr(out), count))
+        return out
+
+    def download(self, want_fullalpha=False, want_W=False, want_ps=False, out=None):
+        pl, info = self._plan, self._info
+        nk = len(pl["ks"])
+        newY = out if out is not None else np.empty((nk, pl["m1"], pl["n"]), dtype=np.float64)
+        skip = info.no_replicates or info.kmax_eff == 0
+        newY_ps = np.empty((nk, pl["n_ps"], pl["n"]), dtype=np.float64) if want_ps else None
+        fa = W = None
+        if want_fullalpha and not skip:
+            rows = info.r if pl["params"].n_alpha_rows < 0 else max(info.kmax_eff, min(info.r, pl["params"].n_alpha_rows))
+            fa = np.empty((rows, pl["n"]), dtype=np.float64)
+        k_eff = [0 if skip else min(k, info.r) for k in pl["ks"]]
+        rows_w = pl["m1"] if pl["params"].mode == MODE_FAST else pl["m1"] + pl["n_ps"]
+        if want_W and not skip:
+            W = np.empty(sum(rows_w * k for k in k_eff), dtype=np.float64)
+        self._check(self._lib.ruviii_download(self._h, _ptr(newY), _ptr(newY_ps), _ptr(fa), _ptr(W)))
+        Ws = None
+        if W is not None:
+            Ws, off = [], 0
+            for k in k_eff:
+                Ws.append(W[off:off + rows_w * k].reshape(rows_w, k))
+                off += rows_w * k
+        return dict(newY=newY, newY_ps=newY_ps, fullalpha=fa, W=Ws, info=info)
+
+    # ---- one shot ---------------------------------------------------------------------------------------
+    def normalise(self, params, Y, PS, group_of_row, ctl, ks, want_fullalpha=False, want_W=False, want_ps=False,
+                  out=None):
+        """Host buffers in, host buffers out, through ``ruviii_normalise`` (what the R shim calls)."""
+        Y = _rowmajor(Y, "Y")
+        PS = _rowmajor(PS, "PS") if PS is not None and np.size(PS) else np.zeros((0, Y.shape[1]))
+        m1, n = Y.shape
+        n_ps = PS.shape[0]
+        if n_ps and PS.shape[1] != n:
+            raise RuviiiError(ERR_INVALID, "replicate.data has %d columns, the assay has %d genes" % (PS.shape[1], n))
+        group_of_row = np.ascontiguousarray(group_of_row, dtype=np.int32)
+        ctl_u8 = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
+        if ctl_u8.shape[0] != n:
+            raise RuviiiError(ERR_INVALID, "len(ctl) != n")
+        need = n_ps if params.mode == MODE_FAST else m1 + n_ps
+        if group_of_row.shape[0] != need:
+            raise RuviiiError(ERR_INVALID, "group_of_row has %d entries, expected %d" % (group_of_row.shape[0], need))
+        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        nk = ks_arr.shape[0]
+        # output sizes depend on r, which the plan computes: plan first, then size the optional outputs
+        self.plan(params, m1, n, n_ps, group_of_row, ctl_u8, ks_arr)
+        self.upload(Y, PS)
+        self.run()
+        return self.download(want_fullalpha=want_fullalpha, want_W=want_W, want_ps=want_ps, out=out)
+
+    def normalise_oneshot(self, params, Y, PS, group_of_row, ctl, ks, out):
+        """The literal one-call C entry point (newY only); used by bench.py's end-to-end leg."""
+        Y = _rowmajor(Y, "Y")
+        PS = _rowmajor(PS, "PS")
+        group_of_row = np.ascontiguousarray(group_of_row, dtype=np.int32)
+        ctl_u8 = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
+        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        info = Info()
+        self._check(self._lib.ruviii_normalise(
+            self._h, C.byref(params), _ptr(Y), Y.strides[0] // 8, Y.shape[0], Y.shape[1], _ptr(PS),
+            PS.strides[0] // 8, PS.shape[0], _ptr(group_of_row), _ptr(ctl_u8), _ptr(ks_arr), ks_arr.shape[0],
+            _ptr(out), None, None, None, C.byref(info)))
+        self._info = info
+        return info
+
+    def fast_residop(self, A, group_of_row):
+        A = _rowmajor(A, "A")
+        g = np.ascontiguousarray(group_of_row, dtype=np.int32)
+        out = np.empty_like(A)
+        self._check(self._lib.ruviii_fast_residop(self._h, _ptr(A), A.shape[0], A.shape[1], _ptr(g), _ptr(out)))
+        return out
+
+    def probe(self, which, size=0):
+        v = C.c_double()
+        self._check(self._lib.ruviii_probe(self._h, which, size, C.byref(v)))
+        return v.value

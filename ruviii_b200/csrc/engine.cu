@@ -1,0 +1,950 @@
+// Engine: handle, plan, gene-sharded pipeline, NCCL exchange steps, C ABI (include/ruviii.h).
+//
+// Pipeline.  Every GPU ("shard") owns a contiguous gene range of Y, PS, ctl and of
+// every output; the only exchanges are two small allreduces and one broadcast:
+//   K1 residop -> K2 partial Gram -> allreduce(G) -> K3 eigensolve on global rank 0 -> bcast(U)
+//   -> K4 projection -> K5 control-gene products -> allreduce([A | Gm]) -> Cholesky -> K6 update.
+// One process may drive several shards (an R session: ruviii_create) or exactly one (torchrun:
+// ruviii_create_rank); the code below is the same loop over `shards_` in both cases.
+#include "../../include/ruviii.h"
+#include "kernels.cuh"
+
+#include <cublas_v2.h>
+#include <cuda.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace ruviii {
+
+int launch_gram_tma_prepare(const GramPlan& gp, const double* Y0, int64_t ldY0, void* desc_out);  // gram_tma.cu
+
+#define RUVIII_NCCL_CHECK(expr)                                                                         \
+    do {                                                                                                \
+        ncclResult_t _r = (expr);                                                                       \
+        if (_r != ncclSuccess)                                                                          \
+            throw ::ruviii::Error(RUVIII_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(_r)); \
+    } while (0)
+#define RUVIII_SOLVER_CHECK(expr)                                                                        \
+    do {                                                                                                 \
+        cusolverStatus_t _r = (expr);                                                                    \
+        if (_r != CUSOLVER_STATUS_SUCCESS)                                                               \
+            throw ::ruviii::Error(RUVIII_ERR_SOLVER, std::string(#expr) + ": cusolver status " +         \
+                                                         std::to_string((int)_r));                       \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    void alloc(size_t n, bool zero = true) {
+        if (n <= count && p) {
+            if (zero) RUVIII_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+            return;
+        }
+        release();
+        if (n == 0) return;
+        RUVIII_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+        count = n;
+        if (zero) RUVIII_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+};
+
+struct Shard {
+    int device = 0;
+    int g0 = 0, n = 0;            // first gene (in the caller's matrix) and gene count of this shard
+    int64_t ld = 0;               // device row pitch (doubles) of every genes-contiguous matrix
+    int n_ctl = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    ncclComm_t comm = nullptr;
+    std::vector<cudaEvent_t> ev;
+    DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
+        evals_asc, falpha;
+    DevBuf<int2> tile_map;
+    DevBuf<int> ctl_idx, grp_start, grp_rows, status;
+    DevBuf<unsigned char> tma_desc;
+    GramPlan gp;
+    int rsplit = 1;
+};
+
+enum Ev { E_START, E_LOG, E_RESIDOP, E_GRAM, E_AR1, E_EIG, E_BCAST, E_PROJECT, E_CTL, E_AR2, E_SOLVE, E_UPDATE, E_COUNT };
+
+}  // namespace ruviii
+
+using namespace ruviii;
+
+struct ruviii_handle {
+    std::vector<Shard> shards;
+    int rank0 = 0, world = 1;           // global rank of shards[0], total shards over all processes
+    bool multi_process = false;
+    std::string err;
+    int n_sms = 148;
+
+    // solver state lives on the device of shards[0] (used only when rank0 == 0)
+    cusolverDnHandle_t solver = nullptr;
+    cublasHandle_t blas = nullptr;
+    DevBuf<double> solver_work;
+    DevBuf<int> solver_info;
+    int* h_flags = nullptr;             // pinned: [0] cusolver devInfo, [1..] cholesky status per shard
+
+    // plan
+    bool planned = false, uploaded = false, ran = false, logged = false, have_user_alpha = false;
+    ruviii_params prm{};
+    int m1 = 0, n_ps = 0, m = 0, n_local_total = 0;
+    int p = 0, R = 0, r = 0, n_groups_active = 0, max_group = 0;
+    int64_t n_ctl_global = 0;
+    std::vector<int> ks, k_eff;
+    int kmax = 0, kk = 0, kp = 4;       // kk = min(kmax, r); kp = padded register extent
+    int n_alpha_rows = 0, n_keep = 0;   // rows of fullalpha produced / eigenvectors kept
+    int rows_w = 0, mu_rows = 0;
+    bool no_replicates = false;
+    uint64_t kmask = 0;
+    int slot_of_k[kMaxK + 1];
+    std::vector<std::pair<int, int>> dup_slots;   // (dst slot, src slot) for k values with the same effective k
+    int launches = 0;
+    ruviii_info info{};
+    int gram_impl = 1, eig_impl = 0;
+
+    ~ruviii_handle();
+};
+
+static thread_local std::string g_create_error;
+
+ruviii_handle::~ruviii_handle() {
+    for (auto& s : shards) {
+        cudaSetDevice(s.device);
+        cudaDeviceSynchronize();
+        if (s.comm) ncclCommDestroy(s.comm);
+        for (auto e : s.ev) cudaEventDestroy(e);
+        DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
+                                  &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
+                                  &s.falpha};
+        for (auto b : bufs) b->release();
+        s.tile_map.release();
+        s.ctl_idx.release();
+        s.grp_start.release();
+        s.grp_rows.release();
+        s.status.release();
+        s.tma_desc.release();
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+    }
+    if (!shards.empty()) cudaSetDevice(shards[0].device);
+    solver_work.release();
+    solver_info.release();
+    if (solver) cusolverDnDestroy(solver);
+    if (blas) cublasDestroy(blas);
+    if (h_flags) cudaFreeHost(h_flags);
+}
+
+namespace {
+
+void check_device(int dev) {
+    cudaDeviceProp prop;
+    RUVIII_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        throw Error(RUVIII_ERR_CUDA, "device " + std::to_string(dev) + " (" + prop.name + ", sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor) +
+                                         ") is not a Blackwell sm_100 GPU; this library has no other code path");
+}
+
+void init_shard(ruviii_handle* h, Shard& s, int device) {
+    s.device = device;
+    check_device(device);
+    RUVIII_CUDA_CHECK(cudaSetDevice(device));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    s.ev.resize(E_COUNT);
+    for (auto& e : s.ev) RUVIII_CUDA_CHECK(cudaEventCreate(&e));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->n_sms = sms;
+}
+
+void finish_create(ruviii_handle* h) {
+    RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+    RUVIII_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flags, 64 * sizeof(int), cudaHostAllocDefault));
+    std::memset(h->h_flags, 0, 64 * sizeof(int));
+    h->gram_impl = env_int("RUVIII_GRAM_IMPL", 1);
+    h->eig_impl = env_int("RUVIII_EIG_IMPL", 0);
+}
+
+// ---- collectives over all shards of all processes ------------------------------------------------------
+void allreduce_sum(ruviii_handle* h, std::vector<double*> bufs, size_t count) {
+    if (h->world == 1) return;
+    RUVIII_NCCL_CHECK(ncclGroupStart());
+    for (size_t i = 0; i < h->shards.size(); ++i)
+        RUVIII_NCCL_CHECK(ncclAllReduce(bufs[i], bufs[i], count, ncclDouble, ncclSum, h->shards[i].comm,
+                                        h->shards[i].stream));
+    RUVIII_NCCL_CHECK(ncclGroupEnd());
+}
+void broadcast0(ruviii_handle* h, std::vector<double*> bufs, size_t count) {
+    if (h->world == 1) return;
+    RUVIII_NCCL_CHECK(ncclGroupStart());
+    for (size_t i = 0; i < h->shards.size(); ++i)
+        RUVIII_NCCL_CHECK(ncclBroadcast(bufs[i], bufs[i], count, ncclDouble, 0, h->shards[i].comm, h->shards[i].stream));
+    RUVIII_NCCL_CHECK(ncclGroupEnd());
+}
+
+void sync_all(ruviii_handle* h) {
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.copy_stream));
+    }
+}
+
+// ---- plan ----------------------------------------------------------------------------------------------
+void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps, const int32_t* group_of_row,
+             const uint8_t* ctl, const int32_t* ks, int nk) {
+    if (!prm || m1 < 0 || n <= 0 || n_ps < 0 || nk <= 0 || !ks || !ctl)
+        throw Error(RUVIII_ERR_INVALID, "ruviii_plan: null or non-positive argument");
+    if (prm->mode != RUVIII_MODE_STACKED && prm->mode != RUVIII_MODE_FAST)
+        throw Error(RUVIII_ERR_INVALID, "ruviii_plan: unknown mode");
+    if (prm->average_rep)
+        throw Error(RUVIII_ERR_UNSUPPORTED, "apply.average.rep (ruvIII.R:148-149) is not implemented yet");
+    if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
+    h->prm = *prm;
+    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = false;
+    h->m1 = m1;
+    h->n_ps = n_ps;
+    h->m = m1 + n_ps;
+    const bool fast = prm->mode == RUVIII_MODE_FAST;
+    // rows that carry replicate structure: all m rows (ruvIII.R:101) or the PRPS rows only (fastruvIII.R:117-118)
+    const int n_grp_rows = fast ? n_ps : h->m;
+    const int row_offset = fast ? m1 : 0;          // stacked row index of group_of_row[0]
+    const int m_for_M = fast ? n_ps : h->m;         // the `m` of `ncol(M) >= m` (fastruvIII.R:112,146)
+    if (n_grp_rows > 0 && !group_of_row) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: group_of_row is NULL");
+
+    // ---- replicate structure: CSR of non-singleton groups (host, O(m log m)) ----
+    std::map<int32_t, std::vector<int>> groups;
+    for (int i = 0; i < n_grp_rows; ++i) {
+        if (group_of_row[i] < 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: negative group id");
+        groups[group_of_row[i]].push_back(i + row_offset);
+    }
+    h->p = (int)groups.size();
+    std::vector<int> grp_start{0}, grp_rows;
+    h->max_group = 0;
+    for (auto& kv : groups) {
+        if (kv.second.size() < 2) continue;
+        for (int r : kv.second) grp_rows.push_back(r);
+        grp_start.push_back((int)grp_rows.size());
+        h->max_group = std::max(h->max_group, (int)kv.second.size());
+    }
+    h->n_groups_active = (int)grp_start.size() - 1;
+    h->R = (int)grp_rows.size();
+    h->no_replicates = h->p >= m_for_M;             // ruvIII.R:128-129
+
+    // ---- k values ----
+    h->ks.assign(ks, ks + nk);
+    h->kmax = 0;
+    for (int k : h->ks) {
+        if (k < 0) throw Error(RUVIII_ERR_INVALID, "k must be >= 0");
+        h->kmax = std::max(h->kmax, k);
+    }
+
+    // ---- gene shards ----
+    const int nsh = (int)h->shards.size();
+    int64_t local_ctl = 0;
+    for (int g = 0; g < n; ++g) local_ctl += ctl[g] != 0;
+    h->n_local_total = n;
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        s.g0 = (int)((int64_t)n * i / nsh);
+        s.n = (int)((int64_t)n * (i + 1) / nsh) - s.g0;
+        s.ld = round_up(std::max(s.n, 1), kRowAlign);
+    }
+    // total number of control genes over all processes (r depends on it, ruvIII.R:140)
+    h->n_ctl_global = local_ctl;
+    if (h->multi_process) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        s.AG.alloc(16);
+        double v = (double)local_ctl;
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.AG.p, &v, 8, cudaMemcpyHostToDevice, s.stream));
+        RUVIII_NCCL_CHECK(ncclAllReduce(s.AG.p, s.AG.p, 1, ncclDouble, ncclSum, s.comm, s.stream));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&v, s.AG.p, 8, cudaMemcpyDeviceToHost, s.stream));
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h->n_ctl_global = (int64_t)(v + 0.5);
+    }
+    // r = min(m - ncol(M), sum(ctl))  (ruvIII.R:140); fastruvIII keeps k vectors of the n_ps x n residual
+    const int rank_bound = m_for_M - h->p;
+    h->r = (int)std::max<int64_t>(0, std::min<int64_t>(rank_bound, fast ? (int64_t)rank_bound : h->n_ctl_global));
+    h->kk = std::min(h->kmax, h->r);
+    if (h->kk > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "k > 32 is not supported by the fused update");
+    h->kp = pad_k(std::max(h->kk, 1));
+    const bool skip = h->no_replicates || h->kk == 0;
+    h->n_alpha_rows = skip ? 0 : (prm->n_alpha_rows < 0 ? h->r : std::min(h->r, std::max(h->kk, prm->n_alpha_rows)));
+    h->n_keep = skip ? 0 : std::min(h->R, std::max(h->n_alpha_rows, h->kk + 1));   // one extra: the gap lambda_kk+1
+    h->rows_w = fast ? m1 : h->m;
+    h->mu_rows = fast ? m1 : h->m;                  // ruvIII.R:118 vs fastruvIII.R:136
+    if (!skip && h->R > 0 && prm->gram_side == 2)
+        throw Error(RUVIII_ERR_UNSUPPORTED, "gene-side Gram is not implemented yet");
+
+    // ---- output slots ----
+    h->k_eff.resize(nk);
+    h->kmask = 0;
+    h->dup_slots.clear();
+    for (int i = 0; i <= kMaxK; ++i) h->slot_of_k[i] = -1;
+    for (int i = 0; i < nk; ++i) {
+        const int ke = skip ? 0 : std::min(h->ks[i], h->r);
+        h->k_eff[i] = ke;
+        if (h->slot_of_k[ke] < 0) {
+            h->slot_of_k[ke] = i;
+            h->kmask |= 1ull << ke;
+        } else {
+            h->dup_slots.emplace_back(i, h->slot_of_k[ke]);
+        }
+    }
+    for (int i = 0; i <= kMaxK; ++i)
+        if (h->slot_of_k[i] < 0) h->slot_of_k[i] = 0;
+
+    // ---- device buffers ----
+    const int kp = h->kp, R = h->R;
+    const bool want_ps = prm->want_ps_rows && !fast && n_ps > 0;
+    size_t w_total = 0;
+    for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        std::vector<int> cidx;
+        for (int g = 0; g < s.n; ++g)
+            if (ctl[s.g0 + g]) cidx.push_back(g);
+        s.n_ctl = (int)cidx.size();
+        s.Y.alloc((size_t)std::max(m1, 1) * s.ld);
+        s.PS.alloc((size_t)std::max(n_ps, 1) * s.ld);
+        s.out.alloc((size_t)nk * std::max(m1, 1) * s.ld, false);
+        if (want_ps) s.out_ps.alloc((size_t)nk * n_ps * s.ld, false);
+        s.status.alloc(4);
+        if (!skip) {
+            s.ctl_idx.alloc(std::max<size_t>(cidx.size(), 1));
+            if (!cidx.empty())
+                RUVIII_CUDA_CHECK(cudaMemcpy(s.ctl_idx.p, cidx.data(), cidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+            s.grp_start.alloc(grp_start.size());
+            s.grp_rows.alloc(std::max<size_t>(grp_rows.size(), 1));
+            RUVIII_CUDA_CHECK(cudaMemcpy(s.grp_start.p, grp_start.data(), grp_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (!grp_rows.empty())
+                RUVIII_CUDA_CHECK(cudaMemcpy(s.grp_rows.p, grp_rows.data(), grp_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+            s.Y0.alloc((size_t)R * s.ld);
+            s.gp = plan_gram(R, (int)s.ld, h->n_sms, h->gram_impl);
+            s.gram_ws.alloc(s.gp.workspace_bytes / sizeof(double), false);
+            std::vector<int2> tm(s.gp.n_tiles);
+            fill_gram_tile_map(s.gp, tm.data());
+            s.tile_map.alloc(tm.size());
+            RUVIII_CUDA_CHECK(cudaMemcpy(s.tile_map.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            s.G.alloc((size_t)R * R);
+            s.evals_asc.alloc(R);
+            s.evals.alloc(std::max(h->n_keep, kp) + 2);
+            s.U.alloc((size_t)R * kp);
+            if (h->n_alpha_rows > h->kk) s.Vd.alloc((size_t)R * h->n_keep);
+            s.rsplit = project_rsplit(R, s.n, h->n_sms);
+            s.part.alloc((size_t)s.rsplit * kp * s.ld);
+            s.alpha.alloc((size_t)kp * s.ld);
+            s.at.alloc((size_t)kp * s.ld);
+            s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
+            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp);
+            s.At.alloc((size_t)h->rows_w * kp);
+            s.Linv.alloc((size_t)kp * kp);
+            s.colmean.alloc(kp);
+            if (h->n_alpha_rows > h->kk) s.falpha.alloc((size_t)h->n_alpha_rows * s.ld);
+            s.W.alloc(std::max<size_t>(w_total, 1));
+            if (s.gp.impl == 2) {
+                s.tma_desc.alloc(128);
+                launch_gram_tma_prepare(s.gp, s.Y0.p, s.ld, s.tma_desc.p);
+            }
+        }
+    }
+    // ---- solver (global rank 0 only) ----
+    if (!skip && h->rank0 == 0 && R > 0) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        if (!h->solver) {
+            RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
+            RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
+        }
+        int lwork = 0, meig = 0;
+        if (h->eig_impl == 1 || h->n_keep >= R) {
+            RUVIII_SOLVER_CHECK(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, R,
+                                                            s.G.p, R, s.evals_asc.p, &lwork));
+        } else {
+            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                                             CUBLAS_FILL_MODE_UPPER, R, s.G.p, R, 0.0, 0.0,
+                                                             R - h->n_keep + 1, R, &meig, s.evals_asc.p, &lwork));
+        }
+        h->solver_work.alloc((size_t)lwork, false);
+        h->solver_info.alloc(4);
+    }
+    h->planned = true;
+}
+
+void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS) {
+    if (!h->planned) throw Error(RUVIII_ERR_STATE, "ruviii_upload before ruviii_plan");
+    if ((h->m1 > 0 && (!Y || ldY < h->n_local_total)) || (h->n_ps > 0 && (!PS || ldPS < h->n_local_total)))
+        throw Error(RUVIII_ERR_INVALID, "ruviii_upload: NULL matrix or row stride < n");
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        if (h->n_ps > 0)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
+                                                cudaMemcpyHostToDevice, s.stream));
+        if (h->m1 > 0)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p, s.ld * 8, Y + s.g0, ldY * 8, (size_t)s.n * 8, h->m1,
+                                                cudaMemcpyHostToDevice, s.stream));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+    }
+    sync_all(h);
+    float ms = 0.f;
+    RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+    cudaEventElapsedTime(&ms, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
+    h->info.ms_h2d = ms;
+    h->uploaded = true;
+    h->logged = false;
+    h->ran = false;
+}
+
+void eigensolve(ruviii_handle* h) {
+    Shard& s = h->shards[0];
+    const int R = h->R;
+    RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+    int n_found = R;
+    if (h->eig_impl == 1 || h->n_keep >= R) {
+        RUVIII_SOLVER_CHECK(cusolverDnDsyevd(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, R, s.G.p, R,
+                                             s.evals_asc.p, h->solver_work.p, (int)h->solver_work.count,
+                                             h->solver_info.p));
+    } else {
+        int meig = 0;
+        RUVIII_SOLVER_CHECK(cusolverDnDsyevdx(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                              CUBLAS_FILL_MODE_UPPER, R, s.G.p, R, 0.0, 0.0, R - h->n_keep + 1, R, &meig,
+                                              s.evals_asc.p, h->solver_work.p, (int)h->solver_work.count,
+                                              h->solver_info.p));
+        n_found = meig;
+        if (meig != h->n_keep) throw Error(RUVIII_ERR_SOLVER, "syevdx returned an unexpected number of eigenpairs");
+    }
+    RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[0], h->solver_info.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    launch_pick_top(s.G.p, R, s.evals_asc.p, n_found, R, h->n_keep, h->kk, h->kp, h->n_alpha_rows > h->kk ? s.Vd.p : nullptr,
+                    s.U.p, s.evals.p, s.stream);
+    h->launches += 1;
+}
+
+void do_run(ruviii_handle* h, ruviii_info* info_out) {
+    if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_run needs ruviii_plan and ruviii_upload first");
+    const bool fast = h->prm.mode == RUVIII_MODE_FAST;
+    const bool skip = h->no_replicates || h->kk == 0;
+    const int kp = h->kp, kk = h->kk, R = h->R, nk = (int)h->ks.size();
+    const bool want_ps = h->prm.want_ps_rows && !fast && h->n_ps > 0;
+    h->launches = 0;
+    auto rec = [&](int e) {
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[e], s.stream));
+        }
+    };
+    auto for_shards = [&](auto&& fn) {
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            fn(s);
+        }
+    };
+    rec(E_START);
+    if (h->prm.apply_log && !h->logged) {             // ruvIII.R:88-89, once per upload
+        for_shards([&](Shard& s) { launch_log2_inplace(s.Y.p, s.ld, h->m1, s.n, h->prm.pseudo_count, s.stream); });
+        h->logged = true;
+        h->launches += 1;
+    }
+    rec(E_LOG);
+    if (skip) {
+        // ncol(M) >= m (ruvIII.R:128-129) or k == 0 (:134-136): newY = Y
+        for_shards([&](Shard& s) {
+            for (int i = 0; i < nk; ++i) {
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.out.p + (size_t)i * h->m1 * s.ld, s.Y.p, (size_t)h->m1 * s.ld * 8,
+                                                  cudaMemcpyDeviceToDevice, s.stream));
+                if (want_ps)
+                    RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.out_ps.p + (size_t)i * h->n_ps * s.ld, s.PS.p,
+                                                      (size_t)h->n_ps * s.ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+            }
+        });
+        for (int e = E_RESIDOP; e < E_COUNT; ++e) rec(e);
+    } else {
+        if (!h->have_user_alpha) {
+            for_shards([&](Shard& s) {
+                RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+                launch_residop(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld,
+                               s.stream);
+            });
+            h->launches += 1;
+            rec(E_RESIDOP);
+            for_shards([&](Shard& s) {
+                launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tma_desc.p, s.stream);
+            });
+            h->launches += 2;
+            rec(E_GRAM);
+            {
+                std::vector<double*> b;
+                for (auto& s : h->shards) b.push_back(s.G.p);
+                allreduce_sum(h, b, (size_t)R * R);
+            }
+            rec(E_AR1);
+            if (h->rank0 == 0) eigensolve(h);
+            rec(E_EIG);
+            {
+                std::vector<double*> b;
+                for (auto& s : h->shards) b.push_back(s.U.p);
+                broadcast0(h, b, (size_t)R * kp);
+                b.clear();
+                for (auto& s : h->shards) b.push_back(s.evals.p);
+                broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
+                if (h->n_alpha_rows > kk) {
+                    b.clear();
+                    for (auto& s : h->shards) b.push_back(s.Vd.p);
+                    broadcast0(h, b, (size_t)R * h->n_keep);
+                }
+            }
+            rec(E_BCAST);
+            for_shards([&](Shard& s) {
+                launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
+                launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+            });
+            h->launches += 3;
+            if (h->n_alpha_rows > kk) {
+                // rows kk.. of fullalpha (return.info = TRUE, ruvIII.R:187-188): a plain library GEMM off the hot path
+                if (!h->blas) {
+                    RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+                    if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) throw Error(RUVIII_ERR_CUDA, "cublasCreate failed");
+                }
+                if (h->shards.size() != 1)
+                    throw Error(RUVIII_ERR_UNSUPPORTED, "n_alpha_rows = -1 needs one GPU per process");
+                Shard& s = h->shards[0];
+                const double one = 1.0, zero = 0.0;
+                cublasSetStream(h->blas, s.stream);
+                if (cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)s.ld, h->n_alpha_rows, R, &one, s.Y0.p, (int)s.ld, s.Vd.p,
+                                R, &zero, s.falpha.p, (int)s.ld) != CUBLAS_STATUS_SUCCESS)
+                    throw Error(RUVIII_ERR_CUDA, "cublasDgemm (fullalpha) failed");
+            }
+        } else {
+            for (int e = E_RESIDOP; e <= E_BCAST; ++e) rec(e);
+            for_shards([&](Shard& s) {
+                launch_alpha_finalize(s.alpha.p, 1, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+            });
+            h->launches += 2;
+        }
+        rec(E_PROJECT);
+        for_shards([&](Shard& s) {
+            RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+            launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
+                                s.stream);
+        });
+        h->launches += 2;
+        rec(E_CTL);
+        {
+            std::vector<double*> b;
+            for (auto& s : h->shards) b.push_back(s.AG.p);
+            allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
+        }
+        rec(E_AR2);
+        for_shards([&](Shard& s) {
+            const double* A = s.AG.p;
+            const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
+            launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
+            launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
+            launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
+        });
+        h->launches += 3;
+        rec(E_SOLVE);
+        for_shards([&](Shard& s) {
+            const int64_t stride = (int64_t)h->m1 * s.ld;
+            launch_update(s.Y.p, s.ld, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
+                          stride, s.stream);
+            if (want_ps)
+                launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At.p + (size_t)h->m1 * kp, kp, s.at.p, s.ld, kk, h->kmask,
+                              h->slot_of_k, s.out_ps.p, s.ld, (int64_t)h->n_ps * s.ld, s.stream);
+            for (auto& d : h->dup_slots) {
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.out.p + (size_t)d.first * stride, s.out.p + (size_t)d.second * stride,
+                                                  (size_t)stride * 8, cudaMemcpyDeviceToDevice, s.stream));
+                if (want_ps)
+                    RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.out_ps.p + (size_t)d.first * h->n_ps * s.ld,
+                                                      s.out_ps.p + (size_t)d.second * h->n_ps * s.ld,
+                                                      (size_t)h->n_ps * s.ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+            }
+            size_t off = 0;
+            for (int i = 0; i < nk; ++i) {
+                launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
+                off += (size_t)h->rows_w * h->k_eff[i];
+            }
+        });
+        h->launches += 1 + (want_ps ? 1 : 0) + nk;
+        rec(E_UPDATE);
+        for (size_t i = 0; i < h->shards.size(); ++i) {
+            Shard& s = h->shards[i];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[1 + i], s.status.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    sync_all(h);
+    if (!skip) {
+        if (h->rank0 == 0 && !h->have_user_alpha && h->h_flags[0] != 0)
+            throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
+        for (size_t i = 0; i < h->shards.size(); ++i)
+            if (h->h_flags[1 + i] != 0)
+                throw Error(RUVIII_ERR_SINGULAR,
+                            "ac %*% t(ac) is not positive definite at pivot " + std::to_string(h->h_flags[1 + i]) +
+                                " (solve() in ruvIII.R:144 would fail)");
+    }
+    // ---- info ----
+    ruviii_info& I = h->info;
+    const float keep_h2d = I.ms_h2d, keep_d2h = I.ms_d2h;
+    std::memset(&I, 0, sizeof(I));
+    I.struct_size = sizeof(ruviii_info);
+    I.ms_h2d = keep_h2d;
+    I.ms_d2h = keep_d2h;
+    I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->R; I.r = h->r;
+    I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = 1;
+    I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
+    {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
+        I.ms_log = el(E_START, E_LOG);
+        I.ms_residop = el(E_LOG, E_RESIDOP);
+        I.ms_gram = el(E_RESIDOP, E_GRAM);
+        I.ms_allreduce_gram = el(E_GRAM, E_AR1);
+        I.ms_eigen = el(E_AR1, E_EIG);
+        I.ms_bcast = el(E_EIG, E_BCAST);
+        I.ms_project = el(E_BCAST, E_PROJECT);
+        I.ms_ctl = el(E_PROJECT, E_CTL);
+        I.ms_allreduce_ctl = el(E_CTL, E_AR2);
+        I.ms_solve = el(E_AR2, E_SOLVE);
+        I.ms_update = el(E_SOLVE, E_UPDATE);
+        I.ms_total = el(E_START, E_UPDATE);
+        if (!skip && !h->have_user_alpha) {
+            std::vector<double> ev(h->kk + 1, 0.0);
+            const int have = std::min(h->kk + 1, h->n_keep);
+            RUVIII_CUDA_CHECK(cudaMemcpy(ev.data(), s.evals.p, have * sizeof(double), cudaMemcpyDeviceToHost));
+            I.eig_top = ev[0];
+            I.eig_kmax = ev[h->kk - 1];
+            I.eig_next = have > h->kk ? ev[h->kk] : 0.0;
+        }
+    }
+    h->ran = true;
+    if (info_out) *info_out = I;
+}
+
+void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W) {
+    if (!h->ran) throw Error(RUVIII_ERR_STATE, "ruviii_download before ruviii_run");
+    const bool fast = h->prm.mode == RUVIII_MODE_FAST;
+    const bool skip = h->no_replicates || h->kk == 0;
+    const int nk = (int)h->ks.size();
+    const int64_t n = h->n_local_total;
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        if (newY && h->m1 > 0)
+            for (int i = 0; i < nk; ++i)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY + (size_t)i * h->m1 * n + s.g0, n * 8,
+                                                    s.out.p + (size_t)i * h->m1 * s.ld, s.ld * 8, (size_t)s.n * 8, h->m1,
+                                                    cudaMemcpyDeviceToHost, s.stream));
+        if (newY_ps) {
+            if (fast || !h->prm.want_ps_rows) throw Error(RUVIII_ERR_INVALID, "newY_ps_out needs STACKED mode with want_ps_rows");
+            for (int i = 0; i < nk; ++i)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY_ps + (size_t)i * h->n_ps * n + s.g0, n * 8,
+                                                    s.out_ps.p + (size_t)i * h->n_ps * s.ld, s.ld * 8, (size_t)s.n * 8,
+                                                    h->n_ps, cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (fullalpha && !skip) {
+            const double* src = (!h->have_user_alpha && h->n_alpha_rows > h->kk) ? s.falpha.p : s.alpha.p;
+            const int rows = h->have_user_alpha ? h->kk : h->n_alpha_rows;
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(fullalpha + s.g0, n * 8, src, s.ld * 8, (size_t)s.n * 8, rows,
+                                                cudaMemcpyDeviceToHost, s.stream));
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+    }
+    if (W && !skip) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        size_t w_total = 0;
+        for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(W, s.W.p, w_total * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    sync_all(h);
+    float ms = 0.f;
+    RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+    cudaEventElapsedTime(&ms, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
+    h->info.ms_d2h = ms;
+}
+
+template <class F>
+int guarded(ruviii_handle* h, F&& fn) {
+    try {
+        fn();
+        return RUVIII_OK;
+    } catch (const Error& e) {
+        if (h) h->err = e.what(); else g_create_error = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception& e) {
+        if (h) h->err = e.what(); else g_create_error = e.what();
+        return RUVIII_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// ======================================== C ABI ==========================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int ruviii_abi_version(void) { return RUVIII_ABI_VERSION; }
+
+int ruviii_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int ruviii_create(ruviii_handle** out, const int32_t* devices, int32_t ndev) {
+    if (!out || ndev <= 0) { g_create_error = "ruviii_create: bad arguments"; return RUVIII_ERR_INVALID; }
+    *out = nullptr;
+    auto h = std::make_unique<ruviii_handle>();
+    int rc = guarded(nullptr, [&] {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw Error(RUVIII_ERR_CUDA, "no CUDA device: the RUV-III engine has no CPU fallback");
+        h->shards.resize(ndev);
+        std::vector<int> devs(ndev);
+        for (int i = 0; i < ndev; ++i) {
+            devs[i] = devices ? devices[i] : i;
+            if (devs[i] < 0 || devs[i] >= count) throw Error(RUVIII_ERR_INVALID, "device index out of range");
+            init_shard(h.get(), h->shards[i], devs[i]);
+        }
+        h->world = ndev;
+        h->rank0 = 0;
+        if (ndev > 1) {
+            std::vector<ncclComm_t> comms(ndev);
+            RUVIII_NCCL_CHECK(ncclCommInitAll(comms.data(), ndev, devs.data()));
+            for (int i = 0; i < ndev; ++i) h->shards[i].comm = comms[i];
+        }
+        finish_create(h.get());
+    });
+    if (rc == RUVIII_OK) *out = h.release();
+    return rc;
+}
+
+int ruviii_nccl_unique_id(void* out128) {
+    if (!out128) return RUVIII_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return RUVIII_ERR_NCCL; }
+    std::memcpy(out128, &id, sizeof(id));
+    return RUVIII_OK;
+}
+
+int ruviii_create_rank(ruviii_handle** out, int32_t device, int32_t rank, int32_t nranks, const void* id128) {
+    if (!out || nranks <= 0 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) {
+        g_create_error = "ruviii_create_rank: bad arguments";
+        return RUVIII_ERR_INVALID;
+    }
+    *out = nullptr;
+    auto h = std::make_unique<ruviii_handle>();
+    int rc = guarded(nullptr, [&] {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw Error(RUVIII_ERR_CUDA, "no CUDA device: the RUV-III engine has no CPU fallback");
+        if (device < 0 || device >= count) throw Error(RUVIII_ERR_INVALID, "device index out of range");
+        h->shards.resize(1);
+        init_shard(h.get(), h->shards[0], device);
+        h->world = nranks;
+        h->rank0 = rank;
+        h->multi_process = nranks > 1;
+        if (nranks > 1) {
+            ncclUniqueId id;
+            std::memcpy(&id, id128, sizeof(id));
+            RUVIII_NCCL_CHECK(ncclCommInitRank(&h->shards[0].comm, nranks, id, rank));
+        }
+        finish_create(h.get());
+    });
+    if (rc == RUVIII_OK) *out = h.release();
+    return rc;
+}
+
+void ruviii_destroy(ruviii_handle* h) { delete h; }
+
+const char* ruviii_last_error(const ruviii_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ruviii_plan(ruviii_handle* h, const ruviii_params* params, int32_t m1, int32_t n, int32_t n_ps,
+                const int32_t* group_of_row, const uint8_t* ctl, const int32_t* ks, int32_t nk) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk); });
+}
+
+int ruviii_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_upload(h, Y, ldY, PS, ldPS); });
+}
+
+int ruviii_run(ruviii_handle* h, ruviii_info* info) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_run(h, info); });
+}
+
+int ruviii_download(ruviii_handle* h, double* newY_out, double* newY_ps_out, double* fullalpha_out, double* W_out) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out); });
+}
+
+int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count) {
+    if (!h || !out) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->ran || h->no_replicates || h->kk == 0 || h->have_user_alpha)
+            throw Error(RUVIII_ERR_STATE, "no eigenvalues: run did not decompose anything");
+        if (count < 0 || count > h->n_keep) throw Error(RUVIII_ERR_INVALID, "count exceeds the eigenvalues kept");
+        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+        RUVIII_CUDA_CHECK(cudaMemcpy(out, h->shards[0].evals.p, count * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->planned) throw Error(RUVIII_ERR_STATE, "ruviii_set_fullalpha before ruviii_plan");
+        if (!fullalpha || rows <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_fullalpha: bad arguments");
+        if (h->no_replicates || h->kmax == 0) return;
+        // alpha <- fullalpha[1:min(k, nrow(fullalpha)), ]  (ruvIII.R:142)
+        const int kk = std::min(h->kmax, (int)rows);
+        if (kk > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "k > 32");
+        if (kk > h->kk)
+            throw Error(RUVIII_ERR_INVALID, "fullalpha has more usable rows than the plan allows (min(k, r))");
+        h->kk = kk;
+        const int64_t n = h->n_local_total;
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            RUVIII_CUDA_CHECK(cudaMemsetAsync(s.alpha.p, 0, (size_t)h->kp * s.ld * 8, s.stream));
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.alpha.p, s.ld * 8, fullalpha + s.g0, n * 8, (size_t)s.n * 8, kk,
+                                                cudaMemcpyHostToDevice, s.stream));
+            RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        }
+        // effective k of every request shrinks accordingly
+        const int nk = (int)h->ks.size();
+        h->kmask = 0;
+        h->dup_slots.clear();
+        for (int i = 0; i <= kMaxK; ++i) h->slot_of_k[i] = -1;
+        for (int i = 0; i < nk; ++i) {
+            const int ke = std::min(h->ks[i], kk);
+            h->k_eff[i] = ke;
+            if (h->slot_of_k[ke] < 0) { h->slot_of_k[ke] = i; h->kmask |= 1ull << ke; }
+            else h->dup_slots.emplace_back(i, h->slot_of_k[ke]);
+        }
+        for (int i = 0; i <= kMaxK; ++i) if (h->slot_of_k[i] < 0) h->slot_of_k[i] = 0;
+        h->have_user_alpha = true;
+    });
+}
+
+int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                     const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
+                     const int32_t* ks, int32_t nk, double* newY_out, double* newY_ps_out, double* fullalpha_out,
+                     double* W_out, ruviii_info* info) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!newY_out) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
+        do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk);
+        do_upload(h, Y, ldY, PS, ldPS);
+        do_run(h, nullptr);
+        do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out);
+        if (info) *info = h->info;
+    });
+}
+
+int ruviii_fast_residop(ruviii_handle* h, const double* A, int32_t rows, int32_t n, const int32_t* group_of_row,
+                        double* out) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!A || !out || !group_of_row || rows <= 0 || n <= 0) throw Error(RUVIII_ERR_INVALID, "fast_residop: bad arguments");
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        std::map<int32_t, std::vector<int>> groups;
+        for (int i = 0; i < rows; ++i) groups[group_of_row[i]].push_back(i);
+        std::vector<int> gs{0}, gr;
+        for (auto& kv : groups) {           // singletons included here: their residual rows are written as zeros
+            for (int r : kv.second) gr.push_back(r);
+            gs.push_back((int)gr.size());
+        }
+        const int64_t ld = round_up(n, kRowAlign);
+        DevBuf<double> dA, dO;
+        DevBuf<int> dgs, dgr;
+        dA.alloc((size_t)rows * ld);
+        dO.alloc((size_t)rows * ld);
+        dgs.alloc(gs.size());
+        dgr.alloc(gr.size());
+        RUVIII_CUDA_CHECK(cudaMemcpy(dgs.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice));
+        RUVIII_CUDA_CHECK(cudaMemcpy(dgr.p, gr.data(), gr.size() * 4, cudaMemcpyHostToDevice));
+        RUVIII_CUDA_CHECK(cudaMemcpy2D(dA.p, ld * 8, A, (size_t)n * 8, (size_t)n * 8, rows, cudaMemcpyHostToDevice));
+        RowSrc src{dA.p, ld, dA.p, ld, rows};
+        launch_residop(src, dgs.p, dgr.p, (int)gs.size() - 1, 0, n, dO.p, ld, s.stream);
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        // compact row t of the kernel output is the residual of input row gr[t]
+        std::vector<double> tmp((size_t)rows * n);
+        RUVIII_CUDA_CHECK(cudaMemcpy2D(tmp.data(), (size_t)n * 8, dO.p, ld * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < rows; ++t) std::memcpy(out + (size_t)gr[t] * n, tmp.data() + (size_t)t * n, (size_t)n * 8);
+        dA.release(); dO.release(); dgs.release(); dgr.release();
+    });
+}
+
+int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_out) {
+    if (!h || !value_out) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        if (which == 0) {
+            *value_out = probe_copy_gbs((size_t)std::max(size, 64) << 20, s.stream);
+        } else if (which == 2) {
+            *value_out = probe_dmma_tflops(h->n_sms, s.stream);
+        } else if (which == 1) {
+            if (!h->blas && cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) throw Error(RUVIII_ERR_CUDA, "cublasCreate failed");
+            cublasSetStream(h->blas, s.stream);
+            const int N = std::max(size, 256);
+            DevBuf<double> a, b, c;
+            a.alloc((size_t)N * N); b.alloc((size_t)N * N); c.alloc((size_t)N * N);
+            const double one = 1.0, zero = 0.0;
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            float best = 1e30f;
+            for (int it = 0; it < 4; ++it) {
+                cudaEventRecord(e0, s.stream);
+                cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, N, N, N, &one, a.p, N, b.p, N, &zero, c.p, N);
+                cudaEventRecord(e1, s.stream);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (it >= 1) best = std::min(best, ms);
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            a.release(); b.release(); c.release();
+            *value_out = 2.0 * N * (double)N * N / (best * 1e-3) / 1e12;
+        } else {
+            throw Error(RUVIII_ERR_INVALID, "unknown probe");
+        }
+    });
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

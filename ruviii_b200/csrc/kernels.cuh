@@ -1,0 +1,90 @@
+// Launchers of the hand-written sm_100a kernels of the RUV-III hot path.  Each one cites the R
+// statement it replaces; DESIGN.md gives the roofline and algorithmic bytes of each.
+#pragma once
+#include "common.cuh"
+
+namespace ruviii {
+
+// Rows of the stacked matrix Y = rbind(t(expr.data), replicate.data) (ruvIII.R:93) are never stacked
+// physically: rows [0, m1) live in the assay buffer, rows [m1, m) in the replicate.data buffer.
+struct RowSrc {
+    const double* Y;
+    int64_t ldY;
+    const double* PS;
+    int64_t ldPS;
+    int m1;
+    __host__ __device__ const double* row(int i) const {
+        return i < m1 ? Y + (int64_t)i * ldY : PS + (int64_t)(i - m1) * ldPS;
+    }
+};
+
+// K8  ruvIII.R:89  log2(assay + pseudo.count), in place on the device copy of the assay.
+void launch_log2_inplace(double* Y, int64_t ld, int rows, int n, double pseudo_count, cudaStream_t s);
+
+// K1  ruvIII.R:139 residop(Y, M) / fastruvIII.R:88-95.  M is one-hot, so Y0 = Y - group mean; rows of
+// singleton groups are exactly zero and are not produced.  grp_start/grp_rows: CSR of the non-singleton
+// groups; compact row (grp position) t of Y0 is the residual of stacked row grp_rows[t].
+void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int max_group,
+                    int n, double* Y0, int64_t ldY0, cudaStream_t s);
+
+// K2  ruvIII.R:140  Y0 %*% t(Y0): symmetric FP64 Gram on DMMA, split over the contraction (genes).
+struct GramPlan {
+    int R = 0, K = 0;            // order of the Gram, contraction length (padded to kRowAlign)
+    int tiles_1d = 0, n_tiles = 0, splits = 1, kchunk = 0;
+    size_t workspace_bytes = 0;  // splits x n_tiles x 128 x 128 doubles
+    int impl = 1;                // 0 = plain DFMA reference kernel, 1 = cp.async + DMMA, 2 = TMA + DMMA
+};
+GramPlan plan_gram(int R, int K, int n_sms, int impl);
+// G (R x R, ld = R) = sum over this shard's genes; both triangles written, bitwise symmetric.
+// tile_map: device array of n_tiles int2 (ti, tj) with ti <= tj, filled by fill_gram_tile_map.
+void fill_gram_tile_map(const GramPlan& gp, int2* host_map);
+int launch_gram(const GramPlan& gp, const double* Y0, int64_t ldY0, const int2* tile_map, double* workspace,
+                double* G, const void* tma_desc, cudaStream_t s);   // returns kernels launched
+
+// K3 post-processing: cuSOLVER returns ascending eigenpairs; keep the top `n_keep` in descending order with
+// a deterministic sign (largest-|component| positive): Vd column-major R x n_keep (optional, may be NULL),
+// U row-major R x kp holding the first kk components (zero padded) for the projection kernel.
+void launch_pick_top(const double* evec_colmajor, int64_t ldv, const double* eval_asc, int n_found, int R,
+                     int n_keep, int kk, int kp, double* Vd_colmajor, double* U_rowmajor, double* eval_desc,
+                     cudaStream_t s);
+
+// K4  ruvIII.R:140  fullalpha = t(U) %*% Y  (rows 1..kk; = t(U) %*% Y0 because U is orthogonal to col(M)).
+// part: rsplit x kp x ld partial sums over row chunks of Y0 (summed by launch_alpha_finalize).
+int  project_rsplit(int R, int n, int n_sms);
+void launch_project(const double* Y0, int64_t ldY0, int R, int n, const double* U_rowmajor, int kp,
+                    int rsplit, double* part, int64_t ld, cudaStream_t s);
+// alpha[j][g] = sum_split part; acT[c][j] = alpha[j][ctl_idx[c]]   (ruvIII.R:142-143)
+void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_t ld, double* alpha,
+                           const int* ctl_idx, int n_ctl, double* acT, cudaStream_t s);
+
+// K5  ruvIII.R:144  A = Y[, ctl] %*% t(ac)  (rows_w x kp, row-major) and Gm = ac %*% t(ac) (kp x kp).
+// The centring Y.stand = Y - 1 mu' (ruvIII.R:118-120) is applied later as A - 1 colMeans(A) (exact algebra).
+void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
+                         double* A, double* Gm, cudaStream_t s);
+
+// K5c ruvIII.R:144  solve(ac %*% t(ac)) via Cholesky Gm[:kk,:kk] = L L'.  Produces Linv (kp x kp, lower), the
+// column means of A over the first mu_rows rows, and a status word (nonzero = not positive definite).
+void launch_chol_solve(const double* A, int rows_w, int mu_rows, const double* Gm, int kk, int kp,
+                       double* Linv, double* colmean, int* status, cudaStream_t s);
+// At[i][q] = sum_{j<=q} (A[i][j] - colmean[j]) Linv[q][j]    (A~ = A_c L^-T)
+void launch_atilde(const double* A, int rows_w, const double* colmean, const double* Linv, int kk, int kp,
+                   double* At, cudaStream_t s);
+// at[q][g] = sum_{j<=q} Linv[q][j] alpha[j][g]               (a~ = L^-1 alpha)
+void launch_alpha_tilde(const double* alpha, const double* Linv, int kk, int kp, int n, int64_t ld,
+                        double* at, cudaStream_t s);
+// W_k = A~[:, :k] Linv[:k, :k]  (rows_w x k, row-major, dense)  -- the W of ruvIII.R:144 for one k
+void launch_w_from_atilde(const double* At, int rows_w, const double* Linv, int k, int kp, double* W,
+                          cudaStream_t s);
+
+// K6  ruvIII.R:145  newY = Y - W %*% alpha, for every requested k in one read of Y:
+// newY_k = Y - sum_{q<k} A~[:, q] (x) a~[q, :]   (nested Cholesky form).
+// kmask bit (k) set (k = 0..kk) => block out_index(k) of `out` receives newY_k; blocks are out_stride apart.
+void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const double* At_rows, int kp,
+                   const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k,
+                   double* out, int64_t ldout, int64_t out_stride, cudaStream_t s);
+
+// micro-benchmarks (ceilings quoted beside the roofline)
+float probe_copy_gbs(size_t bytes, cudaStream_t s);
+float probe_dmma_tflops(int n_sms, cudaStream_t s);
+
+}  // namespace ruviii

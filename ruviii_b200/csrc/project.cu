@@ -1,0 +1,356 @@
+// K3 post-processing, K4 (projection), K5 (control-gene products, k x k solve).
+//
+// Reference statements (ruvIII.R):
+//   :140  fullalpha <- t(svd(Y0 %*% t(Y0))$u[, 1:r]) %*% Y
+//   :142  alpha <- fullalpha[1:min(k, nrow(fullalpha)), ]
+//   :143  ac <- alpha[, ctl]
+//   :144  W <- Y.stand[, ctl] %*% t(ac) %*% solve(ac %*% t(ac))
+// All of these are skinny (k <= 32 rows), so they are bandwidth problems, not tensor problems.
+#include "kernels.cuh"
+
+namespace ruviii {
+
+namespace {
+
+// ---- K3 post: top eigenvectors, descending, deterministic sign -------------------------------------------
+// Block j handles component j (0 = largest eigenvalue): Vd[:, j] (column-major, optional) for j < n_keep,
+// U[:, j] (row-major R x kp, what the projection kernel stages) for j < kk, zero padding for kk <= j < kp.
+__global__ void __launch_bounds__(256)
+pick_top_kernel(const double* __restrict__ V, int64_t ldv, const double* __restrict__ w_asc, int n_found,
+                int R, int n_keep, int kk, int kp, double* __restrict__ Vd, double* __restrict__ U,
+                double* __restrict__ w_desc) {
+    const int j = blockIdx.x;
+    __shared__ double s_abs[256];
+    __shared__ double s_val[256];
+    if (j >= n_keep) {
+        if (j < kp)
+            for (int r = threadIdx.x; r < R; r += blockDim.x) U[(int64_t)r * kp + j] = 0.0;
+        return;
+    }
+    const double* v = V + (int64_t)(n_found - 1 - j) * ldv;
+    double best_abs = -1.0, best_val = 0.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const double x = v[r], a = fabs(x);
+        if (a > best_abs) { best_abs = a; best_val = x; }
+    }
+    s_abs[threadIdx.x] = best_abs;
+    s_val[threadIdx.x] = best_val;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && s_abs[threadIdx.x + o] > s_abs[threadIdx.x]) {
+            s_abs[threadIdx.x] = s_abs[threadIdx.x + o];
+            s_val[threadIdx.x] = s_val[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const double sgn = s_val[0] < 0.0 ? -1.0 : 1.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const double x = sgn * v[r];
+        if (Vd) Vd[(int64_t)j * R + r] = x;
+        if (j < kp) U[(int64_t)r * kp + j] = (j < kk) ? x : 0.0;
+    }
+    if (threadIdx.x == 0) w_desc[j] = w_asc[n_found - 1 - j];
+}
+
+// ---- K4: part[split][j][g] = sum_{r in chunk} U[r][j] * Y0[r][g] -----------------------------------------
+// One thread owns two adjacent genes; a CTA owns 256 genes x one chunk of rows.  U rows are staged through
+// shared memory and read as warp-wide broadcasts.
+constexpr int kProjThreads = 128;
+constexpr int kProjRows = 32;                      // rows staged per step
+
+template <int KP>
+__global__ void __launch_bounds__(kProjThreads)
+project_kernel(const double* __restrict__ Y0, int64_t ldY0, int R, int n_pairs, const double* __restrict__ U,
+               int rows_per_split, double* __restrict__ part, int64_t ld) {
+    __shared__ double sU[kProjRows][KP];
+    const int pair = blockIdx.x * kProjThreads + threadIdx.x;
+    const bool active = pair < n_pairs;
+    const int64_t col = 2 * (int64_t)pair;
+    const int r0 = blockIdx.y * rows_per_split;
+    const int r1 = min(r0 + rows_per_split, R);
+    double2 acc[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int rb = r0; rb < r1; rb += kProjRows) {
+        const int nr = min(kProjRows, r1 - rb);
+        __syncthreads();
+        for (int e = threadIdx.x; e < kProjRows * KP; e += kProjThreads) {
+            const int rr = e / KP, j = e - rr * KP;
+            sU[rr][j] = rr < nr ? U[(int64_t)(rb + rr) * KP + j] : 0.0;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int rr = 0; rr < kProjRows; rr += 4) {
+                double2 y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    y[u] = (rr + u < nr) ? ld_stream(Y0 + (int64_t)(rb + rr + u) * ldY0 + col)
+                                         : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) {
+                        const double w = sU[rr + u][j];
+                        acc[j].x = fma(w, y[u].x, acc[j].x);
+                        acc[j].y = fma(w, y[u].y, acc[j].y);
+                    }
+            }
+        }
+    }
+    if (active) {
+        double* out = part + (int64_t)blockIdx.y * KP * ld + col;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) *reinterpret_cast<double2*>(out + (int64_t)j * ld) = acc[j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+alpha_finalize_kernel(const double* __restrict__ part, int rsplit, int kp, int64_t ld,
+                      double* __restrict__ alpha) {
+    // grid.y = j, threads over the padded pitch (pad columns are sums of zeros)
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (g >= ld) return;
+    double s = 0.0;
+    for (int sp = 0; sp < rsplit; ++sp) s += part[((int64_t)sp * kp + j) * ld + g];
+    alpha[(int64_t)j * ld + g] = s;
+}
+
+__global__ void __launch_bounds__(256)
+gather_ac_kernel(const double* __restrict__ alpha, int64_t ld, int kp, const int* __restrict__ ctl_idx,
+                 int n_ctl, double* __restrict__ acT) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ctl * kp) return;
+    const int c = e / kp, j = e - c * kp;
+    acT[e] = alpha[(int64_t)j * ld + ctl_idx[c]];
+}
+
+// ---- K5: A[i][j] = sum_c Y[i][ctl_idx[c]] * acT[c][j] ; one warp per 4 rows, lanes stride the control genes
+constexpr int kCtlWarps = 8;
+__host__ __device__ constexpr int ctl_rows_per_warp(int kp) { return kp <= 16 ? 4 : 2; }   // 64 accumulators/thread
+
+template <int KP>
+__global__ void __launch_bounds__(kCtlWarps * 32)
+ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl,
+                    const double* __restrict__ acT, double* __restrict__ A) {
+    constexpr int kCtlRowsPerWarp = ctl_rows_per_warp(KP);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = (blockIdx.x * kCtlWarps + warp) * kCtlRowsPerWarp;
+    if (row0 >= rows_w) return;
+    const double* rp[kCtlRowsPerWarp];
+#pragma unroll
+    for (int u = 0; u < kCtlRowsPerWarp; ++u) rp[u] = src.row(min(row0 + u, rows_w - 1));
+    double acc[kCtlRowsPerWarp][KP];
+#pragma unroll
+    for (int u = 0; u < kCtlRowsPerWarp; ++u)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) acc[u][j] = 0.0;
+    for (int c = lane; c < n_ctl; c += 32) {
+        const int g = ctl_idx[c];
+        double y[kCtlRowsPerWarp];
+#pragma unroll
+        for (int u = 0; u < kCtlRowsPerWarp; ++u) y[u] = rp[u][g];
+        const double* a = acT + (int64_t)c * KP;
+#pragma unroll
+        for (int j = 0; j < KP; j += 2) {
+            const double2 w = *reinterpret_cast<const double2*>(a + j);
+#pragma unroll
+            for (int u = 0; u < kCtlRowsPerWarp; ++u) {
+                acc[u][j] = fma(y[u], w.x, acc[u][j]);
+                acc[u][j + 1] = fma(y[u], w.y, acc[u][j + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kCtlRowsPerWarp; ++u)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const double v = warp_sum(acc[u][j]);
+            if (lane == 0 && row0 + u < rows_w) A[(int64_t)(row0 + u) * KP + j] = v;
+        }
+}
+
+// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp, one CTA, fixed summation order)
+__global__ void __launch_bounds__(1024)
+ac_gram_kernel(const double* __restrict__ acT, int n_ctl, int kp, double* __restrict__ Gm) {
+    const int e = threadIdx.x;
+    if (e >= kp * kp) return;
+    const int a = e / kp, b = e - a * kp;
+    double s = 0.0;
+    for (int c = 0; c < n_ctl; ++c) s = fma(acT[(int64_t)c * kp + a], acT[(int64_t)c * kp + b], s);
+    Gm[e] = s;
+}
+
+// ---- K5c: column means of A, Cholesky of Gm[:kk,:kk], inverse of the factor -------------------------------
+__global__ void __launch_bounds__(1024)
+chol_solve_kernel(const double* __restrict__ A, int rows_w, int mu_rows, const double* __restrict__ Gm, int kk,
+                  int kp, double* __restrict__ Linv, double* __restrict__ colmean, int* __restrict__ status) {
+    __shared__ double L[kMaxK][kMaxK + 1];
+    __shared__ double Li[kMaxK][kMaxK + 1];
+    __shared__ double red[1024];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    // column means over the rows that define mu (ruvIII.R:118: all m rows; fastruvIII.R:136: the m1 samples)
+    {
+        const int j = tid % kp, lane_row = tid / kp, stride = 1024 / kp;
+        double s = 0.0;
+        if (lane_row < stride)
+            for (int i = lane_row; i < mu_rows; i += stride) s += A[(int64_t)i * kp + j];
+        red[tid] = (lane_row < stride) ? s : 0.0;
+        __syncthreads();
+        if (tid < kp) {
+            double t = 0.0;
+            for (int q = 0; q < stride; ++q) t += red[q * kp + tid];
+            colmean[tid] = t / (double)mu_rows;
+        }
+    }
+    const int r = tid / kMaxK, c = tid % kMaxK;       // 32 x 32 threads, one per matrix element
+    if (tid == 0) bad = 0;
+    L[r][c] = (r < kk && c < kk) ? Gm[r * kp + c] : (r == c ? 1.0 : 0.0);
+    Li[r][c] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < kk; ++j) {                    // right-looking Cholesky
+        if (tid == 0) {
+            const double d = L[j][j];
+            if (!(d > 0.0)) { bad = j + 1; L[j][j] = 1.0; } else L[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        if (c == j && r > j && r < kk) L[r][j] /= L[j][j];
+        __syncthreads();
+        if (r > j && c > j && c <= r && r < kk) L[r][c] -= L[r][j] * L[c][j];
+        __syncthreads();
+    }
+    // inverse of the lower-triangular factor, one thread per column, forward substitution
+    if (tid < kk) {
+        const int col = tid;
+        for (int i = col; i < kk; ++i) {
+            double s = (i == col) ? 1.0 : 0.0;
+            for (int q = col; q < i; ++q) s -= L[i][q] * Li[q][col];
+            Li[i][col] = s / L[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < kp * kp; e += 1024) {
+        const int i = e / kp, j = e - i * kp;
+        Linv[e] = (i < kk && j <= i) ? Li[i][j] : 0.0;
+    }
+    if (tid == 0) *status = bad;
+}
+
+__global__ void __launch_bounds__(256)
+atilde_kernel(const double* __restrict__ A, int rows_w, const double* __restrict__ colmean,
+              const double* __restrict__ Linv, int kk, int kp, double* __restrict__ At) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows_w * kp) return;
+    const int i = e / kp, q = e - i * kp;
+    double s = 0.0;
+    if (q < kk)
+        for (int j = 0; j <= q; ++j) s = fma(A[(int64_t)i * kp + j] - colmean[j], Linv[q * kp + j], s);
+    At[e] = s;
+}
+
+__global__ void __launch_bounds__(256)
+alpha_tilde_kernel(const double* __restrict__ alpha, const double* __restrict__ Linv, int kk, int kp, int64_t ld,
+                   double* __restrict__ at) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (g >= ld) return;
+    double s = 0.0;
+    if (q < kk)
+        for (int j = 0; j <= q; ++j) s = fma(Linv[q * kp + j], alpha[(int64_t)j * ld + g], s);
+    at[(int64_t)q * ld + g] = s;
+}
+
+__global__ void __launch_bounds__(256)
+w_kernel(const double* __restrict__ At, int rows_w, const double* __restrict__ Linv, int k, int kp,
+         double* __restrict__ W) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows_w * k) return;
+    const int i = e / k, j = e - i * k;
+    double s = 0.0;
+    for (int q = j; q < k; ++q) s = fma(At[(int64_t)i * kp + q], Linv[q * kp + j], s);
+    W[e] = s;
+}
+
+}  // namespace
+
+void launch_pick_top(const double* V, int64_t ldv, const double* w_asc, int n_found, int R, int n_keep, int kk,
+                     int kp, double* Vd, double* U, double* w_desc, cudaStream_t s) {
+    pick_top_kernel<<<std::max(n_keep, kp), 256, 0, s>>>(V, ldv, w_asc, n_found, R, n_keep, kk, kp, Vd, U, w_desc);
+    RUVIII_LAUNCH_CHECK();
+}
+
+int project_rsplit(int R, int n, int n_sms) {
+    const int tiles = ceil_div((n + 1) / 2, kProjThreads);
+    int rs = ceil_div(4 * n_sms, tiles);
+    rs = std::max(1, std::min(rs, ceil_div(R, kProjRows)));
+    return rs;
+}
+
+void launch_project(const double* Y0, int64_t ldY0, int R, int n, const double* U, int kp, int rsplit,
+                    double* part, int64_t ld, cudaStream_t s) {
+    const int n_pairs = (n + 1) / 2;
+    const int rows_per_split = (int)round_up(ceil_div(R, rsplit), kProjRows);
+    dim3 grid(ceil_div(n_pairs, kProjThreads), rsplit);
+    switch (kp) {
+        case 4: project_kernel<4><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
+        case 8: project_kernel<8><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
+        case 16: project_kernel<16><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
+        default: project_kernel<32><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
+    }
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_t ld, double* alpha,
+                           const int* ctl_idx, int n_ctl, double* acT, cudaStream_t s) {
+    dim3 grid(ceil_div(ld, 256), kp);
+    alpha_finalize_kernel<<<grid, 256, 0, s>>>(part, rsplit, kp, ld, alpha);
+    RUVIII_LAUNCH_CHECK();
+    if (n_ctl > 0) {
+        gather_ac_kernel<<<ceil_div((int64_t)n_ctl * kp, 256), 256, 0, s>>>(alpha, ld, kp, ctl_idx, n_ctl, acT);
+        RUVIII_LAUNCH_CHECK();
+    }
+}
+
+void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
+                         double* A, double* Gm, cudaStream_t s) {
+    const int blocks = ceil_div(rows_w, kCtlWarps * ctl_rows_per_warp(kp));
+    switch (kp) {
+        case 4: ctl_products_kernel<4><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
+        case 8: ctl_products_kernel<8><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
+        case 16: ctl_products_kernel<16><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
+        default: ctl_products_kernel<32><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
+    }
+    RUVIII_LAUNCH_CHECK();
+    ac_gram_kernel<<<1, 1024, 0, s>>>(acT, n_ctl, kp, Gm);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_chol_solve(const double* A, int rows_w, int mu_rows, const double* Gm, int kk, int kp, double* Linv,
+                       double* colmean, int* status, cudaStream_t s) {
+    chol_solve_kernel<<<1, 1024, 0, s>>>(A, rows_w, mu_rows, Gm, kk, kp, Linv, colmean, status);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_atilde(const double* A, int rows_w, const double* colmean, const double* Linv, int kk, int kp,
+                   double* At, cudaStream_t s) {
+    atilde_kernel<<<ceil_div((int64_t)rows_w * kp, 256), 256, 0, s>>>(A, rows_w, colmean, Linv, kk, kp, At);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_alpha_tilde(const double* alpha, const double* Linv, int kk, int kp, int n, int64_t ld, double* at,
+                        cudaStream_t s) {
+    dim3 grid(ceil_div(ld, 256), kp);
+    alpha_tilde_kernel<<<grid, 256, 0, s>>>(alpha, Linv, kk, kp, ld, at);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_w_from_atilde(const double* At, int rows_w, const double* Linv, int k, int kp, double* W,
+                          cudaStream_t s) {
+    if (k <= 0) return;
+    w_kernel<<<ceil_div((int64_t)rows_w * k, 256), 256, 0, s>>>(At, rows_w, Linv, k, kp, W);
+    RUVIII_LAUNCH_CHECK();
+}
+
+}  // namespace ruviii

@@ -1,0 +1,94 @@
+// K1: segmented replicate-group mean subtraction (residop) and K8: log2 transform.
+//
+// Reference: ruvIII.R:139 `Y0 = residop(Y, M)`, in-tree statement fastruvIII.R:88-95
+//   A - B solve(B'B) B'A  with B = M the one-hot replicate matrix (ruvIII.R:101).
+// B'B = diag(group sizes), so row i of the result is Y[i,] - mean_{j in g(i)} Y[j,].  Rows of singleton
+// groups are exactly 0 and are never produced: Y0 is stored compactly, one row per member of a
+// non-singleton group, members of one group adjacent.
+//
+// HBM-bound: 16 B per produced cell (8 read + 8 written).  One thread owns two adjacent genes (16-byte
+// accesses, a warp covers 512 contiguous bytes of a row); group members stay in registers between the
+// summation and the subtraction so every input byte is read once.
+#include "kernels.cuh"
+
+namespace ruviii {
+
+namespace {
+
+constexpr int kResidopThreads = 128;
+constexpr int kRegGroup = 8;     // members held in registers; larger groups take the two-pass path
+
+__global__ void __launch_bounds__(kResidopThreads)
+residop_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restrict__ grp_rows,
+               int n_groups, int n_pairs, double* __restrict__ Y0, int64_t ldY0) {
+    const int pair = blockIdx.x * kResidopThreads + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const int64_t col = 2 * (int64_t)pair;
+    for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        const int s = grp_start[g];
+        const int sz = grp_start[g + 1] - s;
+        const double inv = 1.0 / (double)sz;           // (B'B)^-1 = diag(1/size), fastruvIII.R:90
+        if (sz <= kRegGroup) {
+            double2 v[kRegGroup];
+            double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int t = 0; t < kRegGroup; ++t) {
+                if (t < sz) {
+                    v[t] = ld_stream(src.row(grp_rows[s + t]) + col);
+                    sum.x += v[t].x;
+                    sum.y += v[t].y;
+                }
+            }
+            const double2 mean = make_double2(sum.x * inv, sum.y * inv);
+#pragma unroll
+            for (int t = 0; t < kRegGroup; ++t) {
+                if (t < sz)
+                    st_stream(Y0 + (int64_t)(s + t) * ldY0 + col, make_double2(v[t].x - mean.x, v[t].y - mean.y));
+            }
+        } else {
+            double2 sum = make_double2(0.0, 0.0);
+            for (int t = 0; t < sz; ++t) {
+                const double2 v = *reinterpret_cast<const double2*>(src.row(grp_rows[s + t]) + col);
+                sum.x += v.x;
+                sum.y += v.y;
+            }
+            const double2 mean = make_double2(sum.x * inv, sum.y * inv);
+            for (int t = 0; t < sz; ++t) {
+                const double2 v = *reinterpret_cast<const double2*>(src.row(grp_rows[s + t]) + col);
+                st_stream(Y0 + (int64_t)(s + t) * ldY0 + col, make_double2(v.x - mean.x, v.y - mean.y));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+log2_kernel(double* __restrict__ Y, int64_t ld, int rows, int n, double pc) {
+    const int64_t total = (int64_t)rows * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n, c = i - r * n;
+        double* p = Y + r * ld + c;
+        *p = log2(*p + pc);
+    }
+}
+
+}  // namespace
+
+void launch_log2_inplace(double* Y, int64_t ld, int rows, int n, double pc, cudaStream_t s) {
+    if (rows <= 0 || n <= 0) return;
+    const int64_t total = (int64_t)rows * n;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    log2_kernel<<<blocks, 256, 0, s>>>(Y, ld, rows, n, pc);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int /*max_group*/,
+                    int n, double* Y0, int64_t ldY0, cudaStream_t s) {
+    if (n_groups <= 0 || n <= 0) return;
+    const int n_pairs = (n + 1) / 2;          // pitches are even and zero padded, so the odd tail pair is safe
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    residop_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Y0, ldY0);
+    RUVIII_LAUNCH_CHECK();
+}
+
+}  // namespace ruviii

@@ -1,0 +1,202 @@
+// K6: streaming rank-k update  newY = Y - W %*% alpha  (ruvIII.R:145, fastruvIII.R:176), all requested k in
+// one read of Y (replaces the per-k loop of ruvIIIMultipleK.R:75-94).
+//
+// With Gm = ac ac' = L L', A~ = (Y_c - 1 mu_c') ac' L^-T and a~ = L^-1 alpha the correction for k is the
+// sum of the first k outer products A~[:, q] (x) a~[q, :], so
+//     newY_k = newY_{k-1} - A~[:, k] (x) a~[k, :]
+// and every requested k is a snapshot of one running accumulator.
+//
+// HBM-bound: 8 B read + 8 B written per cell and per requested k.  One thread owns two adjacent genes
+// (16-byte accesses; a warp covers 512 contiguous bytes of a row) and keeps its 2 x kk entries of a~ in
+// registers; the A~ rows of the CTA's row block are broadcast from shared memory.  Four rows are in flight
+// per thread.  Y and newY are touched exactly once, so they bypass L1 allocation.
+#include "kernels.cuh"
+
+namespace ruviii {
+
+namespace {
+
+constexpr int kUpdThreads = 128;
+constexpr int kUpdRows = 64;       // rows per CTA
+constexpr int kUpdUnroll = 4;      // rows in flight per thread
+
+struct KSlots { signed char slot[kMaxK + 1]; };
+
+__device__ __forceinline__ double2 lds_v2(const double* p) {
+    double2 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kUpdThreads, KP <= 8 ? 6 : KP <= 16 ? 4 : 2)
+update_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, const double* __restrict__ At,
+              const double* __restrict__ at, int64_t ldat, int kk, uint64_t kmask, KSlots slots,
+              double* __restrict__ out, int64_t ldout, int64_t out_stride) {
+    __shared__ __align__(16) double sAt[kUpdRows][KP];
+    const int pair = blockIdx.x * kUpdThreads + threadIdx.x;
+    const bool active = pair < n_pairs;
+    const int64_t col = 2 * (int64_t)pair;
+    const int row0 = blockIdx.y * kUpdRows;
+    const int nrows = min(kUpdRows, rows - row0);
+    for (int e = threadIdx.x; e < kUpdRows * KP; e += kUpdThreads) {
+        const int r = e / KP;
+        sAt[r][e - r * KP] = r < nrows ? At[(int64_t)(row0 + r) * KP + (e - r * KP)] : 0.0;
+    }
+    double2 a[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q)
+        a[q] = (active && q < kk) ? *reinterpret_cast<const double2*>(at + (int64_t)q * ldat + col)
+                                  : make_double2(0.0, 0.0);
+    __syncthreads();
+    if (!active) return;
+    const bool want0 = kmask & 1ull;
+    for (int rb = 0; rb < nrows; rb += kUpdUnroll) {
+        double2 y[kUpdUnroll];
+#pragma unroll
+        for (int u = 0; u < kUpdUnroll; ++u)
+            y[u] = (rb + u < nrows) ? ld_stream(Y + (int64_t)(row0 + rb + u) * ldY + col) : make_double2(0.0, 0.0);
+        if (want0) {
+            double* o = out + (int64_t)slots.slot[0] * out_stride + col;
+#pragma unroll
+            for (int u = 0; u < kUpdUnroll; ++u)
+                if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+        }
+#pragma unroll
+        for (int q = 0; q < KP; q += 2) {
+            if (q < kk) {
+                // volatile shared loads pin the A~ reads next to their use: without them the compiler hoists all
+                // KP x 4 broadcasts to the top of the row step and the kernel needs > 200 registers
+                double2 w[kUpdUnroll];
+#pragma unroll
+                for (int u = 0; u < kUpdUnroll; ++u) w[u] = lds_v2(&sAt[rb + u][q]);   // rb + u < kUpdRows always
+#pragma unroll
+                for (int u = 0; u < kUpdUnroll; ++u) {
+                    y[u].x = fma(-w[u].x, a[q].x, y[u].x);
+                    y[u].y = fma(-w[u].x, a[q].y, y[u].y);
+                }
+                if ((kmask >> (q + 1)) & 1ull) {
+                    double* o = out + (int64_t)slots.slot[q + 1] * out_stride + col;
+#pragma unroll
+                    for (int u = 0; u < kUpdUnroll; ++u)
+                        if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+                }
+                if (q + 1 < kk) {
+#pragma unroll
+                    for (int u = 0; u < kUpdUnroll; ++u) {
+                        y[u].x = fma(-w[u].y, a[q + 1].x, y[u].x);
+                        y[u].y = fma(-w[u].y, a[q + 1].y, y[u].y);
+                    }
+                    if ((kmask >> (q + 2)) & 1ull) {
+                        double* o = out + (int64_t)slots.slot[q + 2] * out_stride + col;
+#pragma unroll
+                        for (int u = 0; u < kUpdUnroll; ++u)
+                            if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- micro-benchmarks -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ a, double2* __restrict__ b, size_t n2) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+        b[i] = a[i];
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace
+
+void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const double* At_rows, int kp,
+                   const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k, double* out,
+                   int64_t ldout, int64_t out_stride, cudaStream_t s) {
+    if (rows <= 0 || n <= 0) return;
+    KSlots slots;
+    for (int i = 0; i <= kMaxK; ++i) slots.slot[i] = (signed char)out_slot_of_k[i];
+    const int n_pairs = (n + 1) / 2;
+    dim3 grid(ceil_div(n_pairs, kUpdThreads), ceil_div(rows, kUpdRows));
+#define RUVIII_UPD(KP)                                                                                         \
+    update_kernel<KP><<<grid, kUpdThreads, 0, s>>>(Yrows, ldY, rows, n_pairs, At_rows, at, ldat, kk, kmask,    \
+                                                   slots, out, ldout, out_stride)
+    switch (kp) {
+        case 4: RUVIII_UPD(4); break;
+        case 8: RUVIII_UPD(8); break;
+        case 16: RUVIII_UPD(16); break;
+        default: RUVIII_UPD(32); break;
+    }
+#undef RUVIII_UPD
+    RUVIII_LAUNCH_CHECK();
+}
+
+float probe_copy_gbs(size_t bytes, cudaStream_t s) {
+    double2 *a = nullptr, *b = nullptr;
+    const size_t n2 = bytes / sizeof(double2);
+    RUVIII_CUDA_CHECK(cudaMalloc(&a, n2 * sizeof(double2)));
+    RUVIII_CUDA_CHECK(cudaMalloc(&b, n2 * sizeof(double2)));
+    RUVIII_CUDA_CHECK(cudaMemsetAsync(a, 0, n2 * sizeof(double2), s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < 8; ++it) {
+        cudaEventRecord(e0, s);
+        copy_kernel<<<148 * 16, 256, 0, s>>>(a, b, n2);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 2) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    RUVIII_LAUNCH_CHECK();
+    return (float)(2.0 * n2 * sizeof(double2) / (best * 1e-3) / 1e9);
+}
+
+float probe_dmma_tflops(int n_sms, cudaStream_t s) {
+    double* out = nullptr;
+    RUVIII_CUDA_CHECK(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, blocks = n_sms * 4;
+    float best = 1e30f;
+    for (int it = 0; it < 5; ++it) {
+        cudaEventRecord(e0, s);
+        dmma_peak_kernel<<<blocks, 256, 0, s>>>(out, iters);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 1) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    RUVIII_LAUNCH_CHECK();
+    const double flops = 2.0 * 256.0 * 16.0 * iters * (double)blocks * 8.0;   // 8 warps x 16 DMMA x 256 FMA
+    return (float)(flops / (best * 1e-3) / 1e12);
+}
+
+}  // namespace ruviii

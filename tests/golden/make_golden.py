@@ -1,0 +1,88 @@
+"""Generates the golden fixtures in this directory from the CPU oracle (oracle/ruviii_oracle.py, literal flavour).
+
+    python tests/golden/make_golden.py
+
+PARITY UNPINNED: the reference ships no golden vectors and R is not installed in the build container, so
+these files pin the *restatement*, not an R session.  Every matrix is stored exactly as R would hold it --
+raw little-endian float64, column-major -- next to a JSON sidecar with dim/dimnames, so a real R session can
+replay the same bytes later:
+
+    con <- file("mid.assay.bin", "rb"); x <- matrix(readBin(con, "double", n = prod(dim), endian = "little"), dim[1], dim[2])
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from oracle import ruviii_oracle as O          # noqa: E402
+from ruviii_b200.synth import make_problem     # noqa: E402
+
+
+def put(case, name, a):
+    a = np.asarray(a, dtype="<f8")
+    a.T.ravel().tofile(os.path.join(HERE, "%s.%s.bin" % (case, name)))     # column-major bytes
+    return list(a.shape)
+
+
+def tiny():
+    # hand-checkable: 4 samples, 2 PRPS sets x 2 pseudo-samples, 6 genes, 3 control genes, k = 1
+    assay = np.array([[5.0, 6.0, 7.0, 8.0],
+                      [4.0, 4.5, 6.0, 6.5],
+                      [9.0, 8.0, 7.0, 6.0],
+                      [3.0, 3.5, 3.0, 3.5],
+                      [7.0, 7.0, 8.0, 8.0],
+                      [2.0, 4.0, 6.0, 8.5]])
+    PS = np.array([[5.5, 4.2, 8.5, 3.2, 7.0, 3.0],
+                   [7.5, 6.3, 6.5, 3.3, 8.1, 7.2],
+                   [5.0, 4.0, 9.1, 3.0, 7.2, 2.1],
+                   [8.1, 6.4, 6.1, 3.6, 7.9, 8.4]])
+    return dict(assay=assay, sample_names=["s1", "s2", "s3", "s4"], replicate_data=PS,
+                replicate_names=["A", "A", "B", "B"], ctl=np.array([True, False, True, False, True, False]), k=1)
+
+
+def mid():
+    p = make_problem(m1=60, n=300, groups=7, rep=3, n_ctl=40, k=4, seed=20261019 + 100)
+    return dict(assay=np.array(p.assay), sample_names=p.sample_names, replicate_data=p.replicate_data,
+                replicate_names=p.replicate_names, ctl=p.ctl, k=4)
+
+
+def main():
+    for case, c in (("tiny", tiny()), ("mid", mid())):
+        meta = dict(case=case, k=int(c["k"]), ks_multi=[1, 2, c["k"]] if case == "mid" else [1],
+                    sample_names=list(c["sample_names"]), replicate_names=list(c["replicate_names"]),
+                    ctl_index_0based=[int(i) for i in np.nonzero(c["ctl"])[0]], apply_log=False,
+                    layout="raw little-endian float64, column-major (R)", dims={})
+        meta["dims"]["assay"] = put(case, "assay", c["assay"])
+        meta["dims"]["replicate_data"] = put(case, "replicate_data", c["replicate_data"])
+        L = O.ruvIII_literal(c["assay"], c["sample_names"], c["replicate_data"], c["replicate_names"], c["ctl"],
+                             c["k"], apply_log=False)
+        meta["dims"]["ruvIII.newY"] = put(case, "ruvIII.newY", L["newY"])
+        meta["dims"]["ruvIII.fullalpha"] = put(case, "ruvIII.fullalpha", L["fullalpha"])
+        meta["dims"]["ruvIII.W"] = put(case, "ruvIII.W", L["W"])
+        F = O.fastruvIII_literal(c["assay"], c["replicate_data"], c["replicate_names"], c["ctl"], c["k"],
+                                 apply_log=False)
+        meta["dims"]["fastruvIII.newY"] = put(case, "fastruvIII.newY", F["newY"])
+        meta["dims"]["fastruvIII.fullalpha"] = put(case, "fastruvIII.fullalpha", F["fullalpha"])
+        meta["dims"]["fastruvIII.W"] = put(case, "fastruvIII.W", F["W"])
+        for k in meta["ks_multi"]:
+            Lk = O.ruvIII_literal(c["assay"], c["sample_names"], c["replicate_data"], c["replicate_names"],
+                                  c["ctl"], k, apply_log=False)
+            meta["dims"]["ruvIIIMultipleK.k%d.newY" % k] = put(case, "ruvIIIMultipleK.k%d.newY" % k, Lk["newY"])
+        # apply.log = TRUE on counts (ruvIII.R:88-89) for the mid case
+        if case == "mid":
+            counts = np.round(np.exp2(c["assay"]) - 1.0).clip(min=0.0)
+            meta["dims"]["counts"] = put(case, "counts", counts)
+            Lc = O.ruvIII_literal(counts, c["sample_names"], c["replicate_data"], c["replicate_names"], c["ctl"],
+                                  c["k"], apply_log=True, pseudo_count=1.0)
+            meta["dims"]["ruvIII.log.newY"] = put(case, "ruvIII.log.newY", Lc["newY"])
+        with open(os.path.join(HERE, "%s.json" % case), "w") as f:
+            json.dump(meta, f, indent=1)
+        print(case, {k: v for k, v in meta["dims"].items()})
+
+
+if __name__ == "__main__":
+    main()
