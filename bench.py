@@ -125,7 +125,7 @@ def reference_sample(workload):
     from ruviii_b200.synth import make_config, make_problem
     if workload == "tiny":
         return make_problem(m1=300, n=2000, groups=20, rep=3, n_ctl=150, k=5, seed=98), "tiny/2"
-    scale = 1200.0 / 11000.0 if workload in ("C3", "C4") else 1.0
+    scale = 3000.0 / 11000.0 if workload in ("C3", "C4") else 1.0     # ~10-20 s of literal CPU work per k
     p = make_config("C3" if workload == "C4" else workload, scale_rows=scale)
     return p, "%s generator at %d samples x %d genes, %d PRPS rows (rows scaled x%.3f), literal per-k loop" % (
         workload, p.meta["m1"], p.meta["n"], p.meta["n_ps"], scale)
@@ -313,7 +313,10 @@ def main():
                                "semantics, genes sharded over %d GPU(s)" % (args.workload, m1, n, n_ps, p.meta["groups"],
                                                                           int(p.ctl.sum()), ks if nk > 1 else ks[0], world),
                    "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % ((Y_h.nbytes + PS_h.nbytes) / 1e9),
-                   "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next}},
+                   "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next},
+                   "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(
+                       info.eig_solver, "none"), "eig_iterations": info.eig_iterations,
+                   "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes,
     }

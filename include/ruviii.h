@@ -80,6 +80,8 @@ typedef struct ruviii_info {
           ms_project, ms_ctl, ms_allreduce_ctl, ms_solve, ms_update, ms_total;
     float ms_h2d, ms_d2h;              /* host<->device copies (only in ruviii_normalise / upload / download)   */
     double eig_top, eig_kmax, eig_next;/* lambda_1, lambda_kmax, lambda_kmax+1 (gap that conditions newY)       */
+    int32_t eig_solver;                /* 0 none, 1 cuSOLVER syevd, 2 cuSOLVER syevdx, 3 block subspace iteration   */
+    int32_t eig_iterations;            /* subspace-iteration passes (solver 3); 0 otherwise                        */
 } ruviii_info;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */

@@ -1,0 +1,127 @@
+/*
+ * .Call shim between the RUVIIIPRPS R package and libruviii_b200.so (include/ruviii.h).
+ *
+ * COMPILE-UNTESTED: the build container has no R (no Rinternals.h, no libR.so), so this file has never been
+ * compiled.  It is deliberately free of logic: argument unpacking, one C-ABI call, result packing.
+ *
+ * Naming follows the package's own (dangling) Rcpp boundary, R/RcppExports.R:4-26:
+ *     .Call('_RUVIIIPRPS_<fn>', PACKAGE = 'RUVIIIPRPS', ...)
+ * Build:  R CMD SHLIB shim.c -I<repo>/include -L<repo>/ruviii_b200/lib -lruviii_b200  (-> RUVIIIPRPS.so)
+ * NAMESPACE gains:  useDynLib(RUVIIIPRPS, .registration = TRUE)
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+#include "ruviii.h"
+
+static ruviii_handle* g_handle = NULL;           /* one engine per R session, created on first use */
+
+static ruviii_handle* engine(void) {
+    if (!g_handle) {
+        int ndev = ruviii_device_count();
+        const char* env = getenv("RUVIII_NUM_GPUS");
+        if (env && atoi(env) > 0 && atoi(env) < ndev) ndev = atoi(env);
+        if (ndev < 1) Rf_error("RUVIIIPRPS: no sm_100 GPU visible; the CUDA engine has no CPU fallback");
+        if (ruviii_create(&g_handle, NULL, ndev) != RUVIII_OK) Rf_error("RUVIIIPRPS: %s", ruviii_last_error(NULL));
+    }
+    return g_handle;
+}
+
+/* _RUVIIIPRPS_ruvIIICore(assay, tReplicate, groupId, ctl, k, mode, applyLog, pseudoCount, returnInfo)
+ *   assay       numeric n x m1 (genes x samples): assay(se.obj, assay.name)           -- ruvIII.R:88-92
+ *   tReplicate  numeric n x n_ps: t(replicate.data)                                   -- ruvIII.R:93
+ *   groupId     integer, as.integer(factor(row.names(Y))) (STACKED: m1 + n_ps; FAST: n_ps) -- ruvIII.R:101
+ *   ctl         logical n (after tological())                                         -- ruvIII.R:102
+ *   k           integer vector (ruvIIIMultipleK's k)
+ * returns list(newY = list of n x m1 matrices (one per k; exactly the new assay t(newY[1:m1, ])),
+ *              fullalpha = n x r (R side applies t()), W = list of k x m_w (R side applies t()), info) */
+SEXP _RUVIIIPRPS_ruvIIICore(SEXP assay, SEXP tRep, SEXP groupId, SEXP ctl, SEXP k, SEXP mode, SEXP applyLog,
+                            SEXP pseudoCount, SEXP returnInfo) {
+    const int n = Rf_nrows(assay), m1 = Rf_ncols(assay), n_ps = Rf_ncols(tRep), nk = LENGTH(k);
+    const int info_wanted = Rf_asLogical(returnInfo);
+    ruviii_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.struct_size = sizeof(prm);
+    prm.mode = Rf_asInteger(mode);
+    prm.apply_log = Rf_asLogical(applyLog);
+    prm.pseudo_count = Rf_asReal(pseudoCount);
+    prm.n_alpha_rows = (info_wanted && prm.mode == RUVIII_MODE_STACKED) ? -1 : 0;
+    unsigned char* ctl8 = (unsigned char*)R_alloc(n, 1);
+    for (int i = 0; i < n; ++i) ctl8[i] = LOGICAL(ctl)[i] == TRUE;
+    int* gid = (int*)R_alloc(LENGTH(groupId), sizeof(int));
+    for (int i = 0; i < LENGTH(groupId); ++i) gid[i] = INTEGER(groupId)[i] - 1;
+
+    ruviii_handle* h = engine();
+    if (ruviii_plan(h, &prm, m1, n, n_ps, gid, ctl8, INTEGER(k), nk) != RUVIII_OK ||
+        ruviii_upload(h, REAL(assay), n, REAL(tRep), n) != RUVIII_OK)
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    ruviii_info info;
+    if (ruviii_run(h, &info) != RUVIII_OK) Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+
+    /* outputs are allocated by R and filled in place; the engine writes nk blocks back to back, so the
+       download goes through one contiguous REALSXP that is then split without copying the first block */
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SEXP big = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nk * n * m1));
+    const int m_w = prm.mode == RUVIII_MODE_FAST ? m1 : m1 + n_ps;
+    R_xlen_t w_len = 0;
+    for (int i = 0; i < nk; ++i) w_len += (R_xlen_t)m_w * (INTEGER(k)[i] < info.r ? INTEGER(k)[i] : info.r);
+    const int fa_rows = prm.n_alpha_rows < 0 ? info.r : info.kmax_eff;
+    SEXP fa = PROTECT(Rf_allocMatrix(REALSXP, n, (info_wanted && !info.no_replicates) ? fa_rows : 0));
+    SEXP W = PROTECT(Rf_allocVector(REALSXP, (info_wanted && !info.no_replicates) ? w_len : 0));
+    if (ruviii_download(h, REAL(big), NULL, LENGTH(fa) ? REAL(fa) : NULL, LENGTH(W) ? REAL(W) : NULL) != RUVIII_OK) {
+        UNPROTECT(4);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    }
+    SEXP newY = PROTECT(Rf_allocVector(VECSXP, nk));
+    for (int i = 0; i < nk; ++i) {
+        SEXP mat = PROTECT(Rf_allocMatrix(REALSXP, n, m1));
+        memcpy(REAL(mat), REAL(big) + (R_xlen_t)i * n * m1, sizeof(double) * (size_t)n * m1);
+        SET_VECTOR_ELT(newY, i, mat);
+        UNPROTECT(1);
+    }
+    SET_VECTOR_ELT(out, 0, newY);
+    SET_VECTOR_ELT(out, 1, fa);
+    SET_VECTOR_ELT(out, 2, W);
+    SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(info.r));
+    UNPROTECT(5);
+    return out;
+}
+
+/* RcppExports.R:4-6  fastResidop(A, B): B is a replicate (0/1) matrix; its column index per row is the group */
+SEXP _RUVIIIPRPS_fastResidop(SEXP A, SEXP B) {
+    const int rows = Rf_nrows(A), n = Rf_ncols(A), p = Rf_ncols(B);
+    int* gid = (int*)R_alloc(rows, sizeof(int));
+    for (int i = 0; i < rows; ++i) {
+        gid[i] = 0;
+        for (int j = 0; j < p; ++j) if (REAL(B)[i + (R_xlen_t)j * rows] != 0.0) { gid[i] = j; break; }
+    }
+    /* the engine works on rows with the genes contiguous: hand it t(A) and transpose back */
+    SEXP tA = PROTECT(Rf_allocMatrix(REALSXP, n, rows));
+    for (int i = 0; i < rows; ++i) for (int j = 0; j < n; ++j) REAL(tA)[j + (R_xlen_t)i * n] = REAL(A)[i + (R_xlen_t)j * rows];
+    SEXP tO = PROTECT(Rf_allocMatrix(REALSXP, n, rows));
+    if (ruviii_fast_residop(engine(), REAL(tA), rows, n, gid, REAL(tO)) != RUVIII_OK) {
+        UNPROTECT(2);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(g_handle));
+    }
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, rows, n));
+    for (int i = 0; i < rows; ++i) for (int j = 0; j < n; ++j) REAL(out)[i + (R_xlen_t)j * rows] = REAL(tO)[j + (R_xlen_t)i * n];
+    UNPROTECT(3);
+    return out;
+}
+SEXP _RUVIIIPRPS_fastResidop2(SEXP A, SEXP B) { return _RUVIIIPRPS_fastResidop(A, B); }
+
+static const R_CallMethodDef call_methods[] = {
+    {"_RUVIIIPRPS_ruvIIICore", (DL_FUNC)&_RUVIIIPRPS_ruvIIICore, 9},
+    {"_RUVIIIPRPS_fastResidop", (DL_FUNC)&_RUVIIIPRPS_fastResidop, 2},
+    {"_RUVIIIPRPS_fastResidop2", (DL_FUNC)&_RUVIIIPRPS_fastResidop2, 2},
+    {NULL, NULL, 0}};
+
+void R_init_RUVIIIPRPS(DllInfo* dll) {
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
+void R_unload_RUVIIIPRPS(DllInfo* dll) {
+    (void)dll;
+    if (g_handle) { ruviii_destroy(g_handle); g_handle = NULL; }
+}

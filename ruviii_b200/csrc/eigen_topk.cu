@@ -1,0 +1,468 @@
+// K3: top-k eigenvectors of the small symmetric Gram by block subspace iteration with Rayleigh-Ritz.
+//
+// Reference: ruvIII.R:140 `svd(Y0 %*% t(Y0))$u[, 1:r]` computes ALL singular vectors with LAPACK dgesdd; the
+// update (ruvIII.R:142-145) only ever uses the first k <= 32 of them.  A dense tridiagonalisation (cuSOLVER
+// syevd/syevdx, ~1200 tiny latency-bound kernels at R = 1200) costs ~15 ms on a B200 -- 6x everything else in the
+// pass -- so when only the leading rows of fullalpha are wanted the engine runs this solver instead and keeps
+// cuSOLVER as the fallback (non-convergence, tiny problems, or return.info's full r rows).
+//
+// Algorithm (block width B = 32 or 64 >= k + oversampling, G is R x R, all FP64):
+//     Q0 = orthonormalised pseudo-random block
+//     repeat:  Z = G Q                                   (DMMA, split over the contraction, fixed-order partial sums)
+//              every 3rd pass: H = Q'Z, H = V diag(theta) V' (parallel cyclic Jacobi in one CTA),
+//                              X = Q V (Ritz vectors), Z = Z V, stop when ||Z_j - theta_j X_j|| <= tol * theta_1, j < k
+//              Q = orth(Z) by column-scaled Cholesky QR  (S = Z'Z, S = L L', Q = Z L^-T)
+// Convergence of Ritz vector j is linear with ratio lambda_{B+1} / lambda_j; eigenvalues of a Gram are squared
+// singular values, so the ratio is the square of the singular-value ratio.  Everything is deterministic: fixed
+// start block, fixed summation orders, no atomics.
+#include "kernels.cuh"
+
+namespace ruviii {
+
+namespace {
+
+constexpr int kRowsPerCta = 32;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// ---- start block: a fixed hash of (row, column), uniform in (-1, 1) ------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) ek_init_kernel(double* __restrict__ Z, int R, int* __restrict__ state) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e == 0) { state[0] = 0; state[1] = 0; state[2] = 0; }
+    if (e >= R * B) return;
+    uint64_t x = (uint64_t)e * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    Z[e] = (double)(int64_t)(x >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+
+// ---- Zp[split] = G[:, k0:k1] Q[k0:k1, :]  -------------------------------------------------------------------
+// 4 warps per CTA, each owns 8 rows x B columns (B/8 DMMA tiles); fragments come straight from L2 (G is read
+// exactly once per pass, Q is 8 R B bytes and stays L2 resident).
+template <int B>
+__global__ void __launch_bounds__(128)
+ek_gemm_kernel(const double* __restrict__ G, const double* __restrict__ Q, int R, int kchunk,
+               double* __restrict__ Zp, const int* __restrict__ state) {
+    if (state[0]) return;
+    constexpr int NT = B / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, kq = lane & 3;
+    const int row = blockIdx.x * kRowsPerCta + warp * 8 + g;
+    const int k0 = blockIdx.y * kchunk, k1 = min(k0 + kchunk, R);
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const double* grow = G + (int64_t)min(row, R - 1) * R;
+    const bool row_ok = row < R;
+#pragma unroll 2
+    for (int k = k0; k < k1; k += 8) {
+        double a[2], b[2][NT];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int kk = k + u * 4 + kq;
+            const bool ok = kk < k1;
+            a[u] = (ok && row_ok) ? grow[kk] : 0.0;
+            const double* qrow = Q + (int64_t)min(kk, R - 1) * B + g;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) b[u][t] = ok ? qrow[t * 8] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) dmma884(acc[t][0], acc[t][1], a[u], b[u][t]);
+    }
+    if (row_ok) {
+        double* out = Zp + ((int64_t)blockIdx.y * R + row) * B + kq * 2;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) *reinterpret_cast<double2*>(out + t * 8) = make_double2(acc[t][0], acc[t][1]);
+    }
+}
+
+// ---- Z = sum_s Zp[s];  Sp[cta] = Z_blk' Z_blk;  Hp[cta] = Q_blk' Z_blk (optional) ---------------------------
+template <int B>
+__global__ void __launch_bounds__(256)
+ek_ztz_kernel(const double* __restrict__ Zp, int nsplit, const double* __restrict__ Q, int R, double* __restrict__ Z,
+              double* __restrict__ Sp, double* __restrict__ Hp, const int* __restrict__ state) {
+    if (state[0]) return;
+    __shared__ double sZ[kRowsPerCta][B + 1];
+    __shared__ double sQ[kRowsPerCta][B + 1];
+    const int r0 = blockIdx.x * kRowsPerCta;
+    for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
+        const int r = e / B, c = e - r * B;
+        double z = 0.0, q = 0.0;
+        if (r0 + r < R) {
+            for (int s = 0; s < nsplit; ++s) z += Zp[((int64_t)s * R + r0 + r) * B + c];
+            if (Z) Z[(int64_t)(r0 + r) * B + c] = z;
+            if (Hp) q = Q[(int64_t)(r0 + r) * B + c];
+        }
+        sZ[r][c] = z;
+        sQ[r][c] = q;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < B * B; e += 256) {
+        const int a = e / B, b = e - a * B;
+        double s = 0.0, h = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < kRowsPerCta; ++r) {
+            s = fma(sZ[r][a], sZ[r][b], s);
+            h = fma(sQ[r][a], sZ[r][b], h);
+        }
+        Sp[(int64_t)blockIdx.x * B * B + e] = s;
+        if (Hp) Hp[(int64_t)blockIdx.x * B * B + e] = h;
+    }
+}
+
+// ---- one-CTA small dense work ----------------------------------------------------------------------------------
+// mode 0 (ORTHO): S = sum Sp, scale to unit diagonal, Cholesky, M = D L^-T          -> Q = Z M is orthonormal
+// mode 1 (RR):    H = sym(sum Hp), Jacobi  H = V diag(theta) V', theta descending    -> V, theta
+// mode 2 (CHECK): residual norms from Rp, converged flag, then ORTHO on the rotated block
+template <int B>
+__global__ void __launch_bounds__(1024)
+ek_small_kernel(int mode, const double* __restrict__ Sp, const double* __restrict__ Hp, const double* __restrict__ Rp,
+                int n_part, int kk, double tol, int iter, double* __restrict__ M, double* __restrict__ V,
+                double* __restrict__ theta, double* __restrict__ resid, int* __restrict__ state) {
+    if (state[0]) return;
+    __shared__ double A[B][B + 1];
+    __shared__ double W[B][B + 1];
+    __shared__ double cs[B / 2][2];
+    __shared__ double dscale[B];
+    __shared__ int pr[B / 2][2];
+    __shared__ int flag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    if (mode == 2) {
+        // ||Z_j - theta_j X_j||, j < kk, against tol * theta_0
+        if (tid < B) {
+            double s = 0.0;
+            for (int p = 0; p < n_part; ++p) s += Rp[(int64_t)p * B + tid];
+            resid[tid] = sqrt(s);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            bool ok = true;
+            const double lim = tol * fabs(theta[0]);
+            for (int j = 0; j < kk; ++j) ok = ok && (resid[j] <= lim);
+            state[1] = iter;
+            if (ok) state[0] = 1;
+            flag = ok;
+        }
+        __syncthreads();
+        if (flag) return;
+    }
+
+    if (mode == 1) {
+        for (int e = tid; e < B * B; e += nt) {
+            double s = 0.0;
+            for (int p = 0; p < n_part; ++p) s += Hp[(int64_t)p * B * B + e];
+            W[e / B][e % B] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < B * B; e += nt) {
+            const int i = e / B, j = e % B;
+            A[i][j] = 0.5 * (W[i][j] + W[j][i]);
+        }
+        __syncthreads();
+        for (int e = tid; e < B * B; e += nt) W[e / B][e % B] = (e / B == e % B) ? 1.0 : 0.0;   // W = V
+        __syncthreads();
+        // parallel cyclic Jacobi, round-robin pairing: B/2 disjoint rotations per round, B-1 rounds per sweep
+        for (int sweep = 0; sweep < 16; ++sweep) {
+            if (tid == 0) flag = 0;
+            __syncthreads();
+            for (int round = 0; round < B - 1; ++round) {
+                if (tid < B / 2) {
+                    int p, q;
+                    if (tid == 0) { p = B - 1; q = round; }
+                    else { p = (round + tid) % (B - 1); q = (round - tid + (B - 1)) % (B - 1); }
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+                    double c = 1.0, s = 0.0;
+                    if (fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                        flag = 1;
+                    }
+                    cs[tid][0] = c; cs[tid][1] = s;
+                    pr[tid][0] = p; pr[tid][1] = q;
+                }
+                __syncthreads();
+                for (int e = tid; e < (B / 2) * B; e += nt) {         // rows p, q:  A <- J' A
+                    const int i = e / B, j = e % B;
+                    const int p = pr[i][0], q = pr[i][1];
+                    const double c = cs[i][0], s = cs[i][1];
+                    const double x = A[p][j], y = A[q][j];
+                    A[p][j] = c * x - s * y;
+                    A[q][j] = s * x + c * y;
+                }
+                __syncthreads();
+                for (int e = tid; e < (B / 2) * B; e += nt) {         // columns p, q:  A <- A J,  V <- V J
+                    const int i = e / B, j = e % B;
+                    const int p = pr[i][0], q = pr[i][1];
+                    const double c = cs[i][0], s = cs[i][1];
+                    const double x = A[j][p], y = A[j][q];
+                    A[j][p] = c * x - s * y;
+                    A[j][q] = s * x + c * y;
+                    const double vx = W[j][p], vy = W[j][q];
+                    W[j][p] = c * vx - s * vy;
+                    W[j][q] = s * vx + c * vy;
+                }
+                __syncthreads();
+            }
+            if (!flag) break;
+            __syncthreads();
+        }
+        // sort descending (rank sort), write V with permuted columns
+        if (tid < B) {
+            const double t = A[tid][tid];
+            int rank = 0;
+            for (int i = 0; i < B; ++i) {
+                const double u = A[i][i];
+                rank += (u > t) || (u == t && i < tid);
+            }
+            pr[tid % (B / 2)][tid / (B / 2)] = rank;      // reuse: rank of column tid
+            theta[rank] = t;
+        }
+        __syncthreads();
+        for (int e = tid; e < B * B; e += nt) {
+            const int i = e / B, j = e % B;
+            V[i * B + pr[j % (B / 2)][j / (B / 2)]] = W[i][j];
+        }
+        return;
+    }
+
+    // ---- ORTHO ----
+    for (int e = tid; e < B * B; e += nt) {
+        double s = 0.0;
+        for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];
+        W[e / B][e % B] = s;
+    }
+    __syncthreads();
+    if (tid < B) dscale[tid] = W[tid][tid] > 0.0 ? rsqrt(W[tid][tid]) : 1.0;
+    __syncthreads();
+    for (int e = tid; e < B * B; e += nt) {
+        const int i = e / B, j = e % B;
+        A[i][j] = 0.5 * (W[i][j] + W[j][i]) * dscale[i] * dscale[j];
+    }
+    __syncthreads();
+    for (int j = 0; j < B; ++j) {                                  // right-looking Cholesky, lower triangle of A
+        if (tid == 0) {
+            const double d = A[j][j];
+            if (!(d > 1e-30)) { state[2] = j + 1; A[j][j] = 1.0; } else A[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        if (tid > j && tid < B) A[tid][j] /= A[j][j];
+        __syncthreads();
+        for (int e = tid; e < B * B; e += nt) {
+            const int r = e / B, c = e % B;
+            if (r > j && c > j && c <= r) A[r][c] -= A[r][j] * A[c][j];
+        }
+        __syncthreads();
+    }
+    if (tid < B) {                                                 // W = L^-1, one column per thread
+        const int col = tid;
+        for (int i = 0; i < B; ++i) W[i][col] = 0.0;
+        for (int i = col; i < B; ++i) {
+            double s = (i == col) ? 1.0 : 0.0;
+            for (int q = col; q < i; ++q) s -= A[i][q] * W[q][col];
+            W[i][col] = s / A[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += nt) {                        // M[a][b] = D[a] Linv[b][a]
+        const int a = e / B, b = e % B;
+        M[e] = (a <= b) ? dscale[a] * W[b][a] : 0.0;
+    }
+}
+
+// ---- out = in M  (R x B by B x B), rows blocked through shared memory ---------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256)
+ek_apply_kernel(const double* __restrict__ in, const double* __restrict__ M, int R, double* __restrict__ out,
+                const int* __restrict__ state) {
+    if (state[0]) return;
+    __shared__ double sM[B][B + 1];
+    __shared__ double sI[kRowsPerCta][B + 1];
+    const int r0 = blockIdx.x * kRowsPerCta;
+    for (int e = threadIdx.x; e < B * B; e += 256) sM[e / B][e % B] = M[e];
+    for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
+        const int r = e / B, c = e % B;
+        sI[r][c] = (r0 + r < R) ? in[(int64_t)(r0 + r) * B + c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
+        const int r = e / B, c = e % B;
+        double s = 0.0;
+#pragma unroll 8
+        for (int a = 0; a < B; ++a) s = fma(sI[r][a], sM[a][c], s);
+        if (r0 + r < R) out[(int64_t)(r0 + r) * B + c] = s;
+    }
+}
+
+// ---- X = Q V, Z <- Z V, Rp[cta][j] = sum_rows (Z_j - theta_j X_j)^2 ----------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256)
+ek_rotate_kernel(const double* __restrict__ Q, double* __restrict__ Z, const double* __restrict__ V,
+                 const double* __restrict__ theta, int R, double* __restrict__ X, double* __restrict__ Rp,
+                 const int* __restrict__ state) {
+    if (state[0]) return;
+    __shared__ double sV[B][B + 1];
+    __shared__ double sQ[kRowsPerCta][B + 1];
+    __shared__ double sZ[kRowsPerCta][B + 1];
+    __shared__ double sR[kRowsPerCta][B + 1];
+    const int r0 = blockIdx.x * kRowsPerCta;
+    for (int e = threadIdx.x; e < B * B; e += 256) sV[e / B][e % B] = V[e];
+    for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
+        const int r = e / B, c = e % B;
+        const bool ok = r0 + r < R;
+        sQ[r][c] = ok ? Q[(int64_t)(r0 + r) * B + c] : 0.0;
+        sZ[r][c] = ok ? Z[(int64_t)(r0 + r) * B + c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
+        const int r = e / B, c = e % B;
+        double x = 0.0, z = 0.0;
+#pragma unroll 8
+        for (int a = 0; a < B; ++a) {
+            x = fma(sQ[r][a], sV[a][c], x);
+            z = fma(sZ[r][a], sV[a][c], z);
+        }
+        if (r0 + r < R) {
+            X[(int64_t)(r0 + r) * B + c] = x;
+            Z[(int64_t)(r0 + r) * B + c] = z;
+        }
+        const double d = z - theta[c] * x;
+        sR[r][c] = d * d;
+    }
+    __syncthreads();
+    if (threadIdx.x < B) {
+        double s = 0.0;
+        for (int r = 0; r < kRowsPerCta; ++r) s += sR[r][threadIdx.x];
+        Rp[(int64_t)blockIdx.x * B + threadIdx.x] = s;
+    }
+}
+
+// ---- Ritz vectors -> U (row-major R x kp, sign fixed), eigenvalues descending ----------------------------------
+template <int B>
+__global__ void __launch_bounds__(256)
+ek_finalize_kernel(const double* __restrict__ X, const double* __restrict__ theta, int R, int n_keep, int kk, int kp,
+                   double* __restrict__ U, double* __restrict__ evals) {
+    const int j = blockIdx.x;
+    __shared__ double s_abs[256];
+    __shared__ double s_val[256];
+    if (j >= kk) {
+        if (j < kp)
+            for (int r = threadIdx.x; r < R; r += 256) U[(int64_t)r * kp + j] = 0.0;
+        if (threadIdx.x == 0 && j < n_keep) evals[j] = theta[j];
+        return;
+    }
+    double best_abs = -1.0, best_val = 0.0;
+    for (int r = threadIdx.x; r < R; r += 256) {
+        const double x = X[(int64_t)r * B + j], a = fabs(x);
+        if (a > best_abs) { best_abs = a; best_val = x; }
+    }
+    s_abs[threadIdx.x] = best_abs;
+    s_val[threadIdx.x] = best_val;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && s_abs[threadIdx.x + o] > s_abs[threadIdx.x]) {
+            s_abs[threadIdx.x] = s_abs[threadIdx.x + o];
+            s_val[threadIdx.x] = s_val[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const double sgn = s_val[0] < 0.0 ? -1.0 : 1.0;
+    for (int r = threadIdx.x; r < R; r += 256) U[(int64_t)r * kp + j] = sgn * X[(int64_t)r * B + j];
+    if (threadIdx.x == 0) evals[j] = theta[j];
+}
+
+template <int B>
+TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork& w, double* U, double* evals, double tol,
+                    int max_iter, int n_sms, int* h_state, cudaStream_t s) {
+    const int n_rb = ceil_div(R, kRowsPerCta);
+    int splits = std::max(1, std::min(16, ceil_div(2 * n_sms, n_rb)));
+    const int kchunk = (int)round_up(ceil_div(R, splits), 8);
+    splits = ceil_div(R, kchunk);
+    const int T = 3;
+    int launches = 0;
+    ek_init_kernel<B><<<ceil_div((int64_t)R * B, 256), 256, 0, s>>>(w.Zp, R, w.state);
+    ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, 1, nullptr, R, w.Z, w.Sp, nullptr, w.state);
+    ek_small_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, nullptr, n_rb, kk, tol, 0, w.M, w.V, w.theta, w.resid, w.state);
+    ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+    launches += 4;
+    TopkResult res;
+    int it = 0;
+    while (it < max_iter) {
+        const int batch_end = std::min(max_iter, it == 0 ? 2 * T : it + T);
+        for (; it < batch_end;) {
+            ++it;
+            ek_gemm_kernel<B><<<dim3(n_rb, splits), 128, 0, s>>>(G, w.Q, R, kchunk, w.Zp, w.state);
+            ++launches;
+            if (it % T == 0) {
+                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, w.Q, R, w.Z, w.Sp, w.Hp, w.state);
+                ek_small_kernel<B><<<1, 1024, 0, s>>>(1, w.Sp, w.Hp, nullptr, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_rotate_kernel<B><<<n_rb, 256, 0, s>>>(w.Q, w.Z, w.V, w.theta, R, w.X, w.Rp, w.state);
+                // CHECK sets the flag; the ORTHO half of mode 2 needs S of the rotated block, so it is recomputed first
+                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, 1, nullptr, R, nullptr, w.Sp, nullptr, w.state);
+                ek_small_kernel<B><<<1, 1024, 0, s>>>(2, w.Sp, nullptr, w.Rp, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+                launches += 6;
+            } else {
+                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, nullptr, R, w.Z, w.Sp, nullptr, w.state);
+                ek_small_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, nullptr, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+                launches += 3;
+            }
+        }
+        RUVIII_LAUNCH_CHECK();
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (h_state[0]) break;
+    }
+    res.converged = h_state[0] != 0;
+    res.iterations = h_state[1];
+    res.launches = launches;
+    if (res.converged) {
+        ek_finalize_kernel<B><<<std::max(std::max(n_keep, kp), kk), 256, 0, s>>>(w.X, w.theta, R, n_keep, kk, kp, U, evals);
+        RUVIII_LAUNCH_CHECK();
+        res.launches += 1;
+    }
+    return res;
+}
+
+}  // namespace
+
+size_t topk_work_doubles(int R, int B) {
+    const int n_rb = ceil_div(R, kRowsPerCta);
+    // Q, X, Z, Zp (16 splits), Sp, Hp, Rp, M, V, theta, resid
+    return (size_t)R * B * (3 + 16) + (size_t)n_rb * B * B * 2 + (size_t)n_rb * B + (size_t)B * B * 2 + 4 * B;
+}
+
+void topk_bind(TopkWork& w, double* base, int* state, int R, int B) {
+    const int n_rb = ceil_div(R, kRowsPerCta);
+    double* p = base;
+    w.Q = p; p += (size_t)R * B;
+    w.X = p; p += (size_t)R * B;
+    w.Z = p; p += (size_t)R * B;
+    w.Zp = p; p += (size_t)R * B * 16;
+    w.Sp = p; p += (size_t)n_rb * B * B;
+    w.Hp = p; p += (size_t)n_rb * B * B;
+    w.Rp = p; p += (size_t)n_rb * B;
+    w.M = p; p += (size_t)B * B;
+    w.V = p; p += (size_t)B * B;
+    w.theta = p; p += B;
+    w.resid = p; p += B;
+    w.state = state;
+}
+
+TopkResult topk_eigen(const double* G, int R, int kk, int kp, int n_keep, int B, TopkWork& w, double* U, double* evals,
+                      double tol, int max_iter, int n_sms, int* h_state, cudaStream_t s) {
+    if (B != 32 || kk > 16 || n_keep > B) throw Error(6, "topk_eigen: only B = 32 (k <= 16) is built");
+    return run_topk<32>(G, R, kk, kp, n_keep, w, U, evals, tol, max_iter, n_sms, h_state, s);
+}
+
+}  // namespace ruviii

@@ -76,10 +76,11 @@ struct Shard {
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
-        evals_asc, falpha;
+        evals_asc, falpha, topk_buf;
     DevBuf<int2> tile_map;
-    DevBuf<int> ctl_idx, grp_start, grp_rows, status;
-    DevBuf<unsigned char> tma_desc;
+    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state;
+    TopkWork topk{};
+    alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
     GramPlan gp;
     int rsplit = 1;
 };
@@ -120,7 +121,10 @@ struct ruviii_handle {
     std::vector<std::pair<int, int>> dup_slots;   // (dst slot, src slot) for k values with the same effective k
     int launches = 0;
     ruviii_info info{};
-    int gram_impl = 1, eig_impl = 0;
+    int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
+    int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
+    bool use_topk = false;
+    double eig_tol = 1e-13;
 
     ~ruviii_handle();
 };
@@ -135,14 +139,14 @@ ruviii_handle::~ruviii_handle() {
         for (auto e : s.ev) cudaEventDestroy(e);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha};
+                                  &s.falpha, &s.topk_buf};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
         s.grp_start.release();
         s.grp_rows.release();
         s.status.release();
-        s.tma_desc.release();
+        s.topk_state.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     }
@@ -184,6 +188,7 @@ void finish_create(ruviii_handle* h) {
     std::memset(h->h_flags, 0, 64 * sizeof(int));
     h->gram_impl = env_int("RUVIII_GRAM_IMPL", 1);
     h->eig_impl = env_int("RUVIII_EIG_IMPL", 0);
+    if (const char* t = std::getenv("RUVIII_EIG_TOL")) h->eig_tol = std::atof(t);
 }
 
 // ---- collectives over all shards of all processes ------------------------------------------------------
@@ -286,6 +291,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     }
     // r = min(m - ncol(M), sum(ctl))  (ruvIII.R:140); fastruvIII keeps k vectors of the n_ps x n residual
     const int rank_bound = m_for_M - h->p;
+    h->rank_bound = rank_bound;
     h->r = (int)std::max<int64_t>(0, std::min<int64_t>(rank_bound, fast ? (int64_t)rank_bound : h->n_ctl_global));
     h->kk = std::min(h->kmax, h->r);
     if (h->kk > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "k > 32 is not supported by the fused update");
@@ -366,15 +372,27 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (h->n_alpha_rows > h->kk) s.falpha.alloc((size_t)h->n_alpha_rows * s.ld);
             s.W.alloc(std::max<size_t>(w_total, 1));
             if (s.gp.impl == 2) {
-                s.tma_desc.alloc(128);
-                launch_gram_tma_prepare(s.gp, s.Y0.p, s.ld, s.tma_desc.p);
+                launch_gram_tma_prepare(s.gp, s.Y0.p, s.ld, s.tmap);
             }
         }
     }
     // ---- solver (global rank 0 only) ----
+    h->use_topk = false;
     if (!skip && h->rank0 == 0 && R > 0) {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        // block subspace iteration when only the leading kk rows of fullalpha are wanted and the block (32) leaves
+        // room for oversampling; cuSOLVER otherwise and as the fallback
+        const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkBlock / 2 && R >= 4 * kTopkBlock &&
+                             h->rank_bound >= 2 * kTopkBlock;
+        if (h->eig_impl == 3 && !topk_ok)
+            throw Error(RUVIII_ERR_UNSUPPORTED, "RUVIII_EIG_IMPL=3 but the problem is outside the subspace-iteration range");
+        h->use_topk = topk_ok && (h->eig_impl == 0 || h->eig_impl == 3);
+        if (h->use_topk) {
+            s.topk_buf.alloc(topk_work_doubles(R, kTopkBlock), false);
+            s.topk_state.alloc(4);
+            topk_bind(s.topk, s.topk_buf.p, s.topk_state.p, R, kTopkBlock);
+        }
         if (!h->solver) {
             RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
             RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
@@ -423,7 +441,23 @@ void eigensolve(ruviii_handle* h) {
     Shard& s = h->shards[0];
     const int R = h->R;
     RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+    h->h_flags[0] = 0;
+    h->eig_iterations = 0;
+    if (h->use_topk) {
+        TopkResult tr = topk_eigen(s.G.p, R, h->kk, h->kp, h->n_keep, kTopkBlock, s.topk, s.U.p, s.evals.p, h->eig_tol,
+                                   env_int("RUVIII_EIG_MAXIT", 150), h->n_sms, &h->h_flags[60], s.stream);
+        h->launches += tr.launches;
+        h->eig_iterations = tr.iterations;
+        if (tr.converged) {
+            h->eig_solver_used = 3;
+            return;
+        }
+        if (h->eig_impl == 3)
+            throw Error(RUVIII_ERR_SOLVER, "subspace iteration did not converge in " + std::to_string(tr.iterations) +
+                                               " passes (RUVIII_EIG_IMPL=3 forbids the cuSOLVER fallback)");
+    }
     int n_found = R;
+    h->eig_solver_used = (h->eig_impl == 1 || h->n_keep >= R) ? 1 : 2;
     if (h->eig_impl == 1 || h->n_keep >= R) {
         RUVIII_SOLVER_CHECK(cusolverDnDsyevd(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, R, s.G.p, R,
                                              s.evals_asc.p, h->solver_work.p, (int)h->solver_work.count,
@@ -491,7 +525,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             h->launches += 1;
             rec(E_RESIDOP);
             for_shards([&](Shard& s) {
-                launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tma_desc.p, s.stream);
+                launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
             });
             h->launches += 2;
             rec(E_GRAM);
@@ -616,6 +650,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->R; I.r = h->r;
     I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = 1;
     I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
+    I.eig_solver = (skip || h->have_user_alpha) ? 0 : h->eig_solver_used; I.eig_iterations = h->eig_iterations;
     {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));

@@ -48,6 +48,22 @@ void launch_pick_top(const double* evec_colmajor, int64_t ldv, const double* eva
                      int n_keep, int kk, int kp, double* Vd_colmajor, double* U_rowmajor, double* eval_desc,
                      cudaStream_t s);
 
+// K3  ruvIII.R:140  svd(Y0 %*% t(Y0))$u[, 1:k]: block subspace iteration + Rayleigh-Ritz (eigen_topk.cu).
+struct TopkWork {
+    double *Q, *X, *Z, *Zp, *Sp, *Hp, *Rp, *M, *V, *theta, *resid;
+    int* state;                  // device: [0] converged, [1] iterations at the last check, [2] Cholesky breakdown
+};
+struct TopkResult {
+    bool converged = false;
+    int iterations = 0, launches = 0;
+};
+constexpr int kTopkBlock = 32;   // block width B; serves k <= 16 (B >= 2k)
+size_t topk_work_doubles(int R, int B);
+void topk_bind(TopkWork& w, double* base, int* state, int R, int B);
+// U: row-major R x kp (first kk columns, sign fixed); evals: n_keep descending Ritz values (only the first kk converged)
+TopkResult topk_eigen(const double* G, int R, int kk, int kp, int n_keep, int B, TopkWork& w, double* U, double* evals,
+                      double tol, int max_iter, int n_sms, int* h_state, cudaStream_t s);
+
 // K4  ruvIII.R:140  fullalpha = t(U) %*% Y  (rows 1..kk; = t(U) %*% Y0 because U is orthogonal to col(M)).
 // part: rsplit x kp x ld partial sums over row chunks of Y0 (summed by launch_alpha_finalize).
 int  project_rsplit(int R, int n, int n_sms);

@@ -171,15 +171,18 @@ ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int
         }
 }
 
-// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp, one CTA, fixed summation order)
+// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA; each warp owns entries e = warp, warp + 32, ...,
+// lanes stride the control genes and a shuffle tree closes the sum: fixed order, bitwise reproducible.
 __global__ void __launch_bounds__(1024)
 ac_gram_kernel(const double* __restrict__ acT, int n_ctl, int kp, double* __restrict__ Gm) {
-    const int e = threadIdx.x;
-    if (e >= kp * kp) return;
-    const int a = e / kp, b = e - a * kp;
-    double s = 0.0;
-    for (int c = 0; c < n_ctl; ++c) s = fma(acT[(int64_t)c * kp + a], acT[(int64_t)c * kp + b], s);
-    Gm[e] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < kp * kp; e += 32) {
+        const int a = e / kp, b = e - a * kp;
+        double s = 0.0;
+        for (int c = lane; c < n_ctl; c += 32) s = fma(acT[(int64_t)c * kp + a], acT[(int64_t)c * kp + b], s);
+        s = warp_sum(s);
+        if (lane == 0) Gm[e] = s;
+    }
 }
 
 // ---- K5c: column means of A, Cholesky of Gm[:kk,:kk], inverse of the factor -------------------------------

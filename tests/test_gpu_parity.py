@@ -125,7 +125,9 @@ def test_fast_matches_literal(engine, shape):
 
 def test_full_fullalpha_rows(engine):
     """return.info = TRUE keeps all r = min(m - ncol(M), sum(ctl)) rows of fullalpha (ruvIII.R:140,187-188)."""
-    p = make_problem(m1=80, n=500, groups=12, rep=3, n_ctl=60, k=3, seed=31)
+    # enough samples per (biology, batch) cell that no two pseudo-samples coincide: rank(Y0) = r exactly.  (With
+    # a rank-deficient Y0 the reference's trailing rows t(U) %*% Y are arbitrary null-space vectors times Y.)
+    p = make_problem(m1=400, n=500, groups=12, rep=3, n_ctl=60, k=3, seed=31)
     res = run_engine(engine, p, [3], n_alpha_rows=-1)
     ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 3, apply_log=False)
     assert res["fullalpha"].shape == ref["fullalpha"].shape == (24, 500)
@@ -260,6 +262,35 @@ def test_gram_kernels_agree():
     assert np.allclose(outs[1][1], outs[0][1], rtol=1e-12)
     S = O.ruvIII_structural(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 6, apply_log=False)
     assert np.allclose(outs[1][1][:6], S["eigenvalues"][:6], rtol=1e-11)
+
+
+def test_eigensolvers_agree():
+    """Block subspace iteration (solver 3) vs cuSOLVER syevdx (solver 2) vs the oracle, on a problem large enough
+    for the iterative solver (R >= 128, rank >= 64).  newY depends only on the top-k subspace."""
+    p = make_problem(m1=500, n=6000, groups=80, rep=3, n_ctl=300, k=8, seed=14)
+    ref = O.ruvIII_structural(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 8, apply_log=False)
+    outs = {}
+    for impl in (2, 3):
+        os.environ["RUVIII_EIG_IMPL"] = str(impl)
+        try:
+            with rv.Engine(devices=[0]) as eng:
+                res = run_engine(eng, p, [3, 8])
+                assert res["info"].eig_solver == impl
+                if impl == 3:
+                    assert 0 < res["info"].eig_iterations <= 150
+                outs[impl] = (np.vstack([res["newY"][1], res["newY_ps"][1]]), eng.eigenvalues(8), res["fullalpha"], res["W"][1])
+        finally:
+            os.environ.pop("RUVIII_EIG_IMPL", None)
+    for impl in (2, 3):
+        assert O.rel_frob(outs[impl][0], ref["newY"]) < TOL_NEWY
+        assert np.allclose(outs[impl][1], ref["eigenvalues"][:8], rtol=1e-11)
+        fa = O.align_rows_sign(outs[impl][2][:8], ref["fullalpha"][:8])
+        assert O.rel_frob(fa, ref["fullalpha"][:8]) < TOL_SIGNED
+    assert O.rel_frob(outs[3][0], outs[2][0]) < 1e-10
+    # deterministic sign convention: both solvers return the same orientation
+    assert O.rel_frob(outs[3][2], outs[2][2]) < TOL_SIGNED
+    with rv.Engine(devices=[0]) as eng:                       # auto picks the iterative solver here
+        assert run_engine(eng, p, [8])["info"].eig_solver == 3
 
 
 # ---- BASELINE.json sizes ----------------------------------------------------------------------------------------
