@@ -12,7 +12,8 @@
 #include <cublas_v2.h>
 #include <cuda.h>
 #include <cusolverDn.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen()ed, see NcclApi
 
 #include <algorithm>
 #include <cstdlib>
@@ -25,6 +26,57 @@
 namespace ruviii {
 
 int launch_gram_tma_prepare(const GramPlan& gp, const double* Y0, int64_t ldY0, void* desc_out);  // gram_tma.cu
+
+// NCCL entry points, resolved at run time.  If the process already holds a libnccl.so.2 (torch imports its own
+// 2.28 build) that one is reused; otherwise the system library is loaded.  Linking libnccl directly would let
+// whichever of the two builds is loaded first shadow the other under the shared soname.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    static NcclApi& get() {
+        static NcclApi api;
+        static std::once_flag once;
+        static std::string err;
+        std::call_once(once, [] {
+            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+            auto sym = [&](const char* name) {
+                void* p = dlsym(lib, name);
+                if (!p && err.empty()) err = std::string("libnccl lacks ") + name;
+                return p;
+            };
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+            api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+            api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+            api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+            api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+            api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        });
+        if (!err.empty()) throw ::ruviii::Error(3, err);
+        return api;
+    }
+};
+#define ncclGetUniqueId ::ruviii::NcclApi::get().GetUniqueId
+#define ncclCommInitRank ::ruviii::NcclApi::get().CommInitRank
+#define ncclCommInitAll ::ruviii::NcclApi::get().CommInitAll
+#define ncclCommDestroy ::ruviii::NcclApi::get().CommDestroy
+#define ncclAllReduce ::ruviii::NcclApi::get().AllReduce
+#define ncclBroadcast ::ruviii::NcclApi::get().Broadcast
+#define ncclGroupStart ::ruviii::NcclApi::get().GroupStart
+#define ncclGroupEnd ::ruviii::NcclApi::get().GroupEnd
+#define ncclGetErrorString ::ruviii::NcclApi::get().GetErrorString
 
 #define RUVIII_NCCL_CHECK(expr)                                                                         \
     do {                                                                                                \
@@ -788,10 +840,11 @@ int ruviii_create(ruviii_handle** out, const int32_t* devices, int32_t ndev) {
 int ruviii_nccl_unique_id(void* out128) {
     if (!out128) return RUVIII_ERR_INVALID;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
-    ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return RUVIII_ERR_NCCL; }
-    std::memcpy(out128, &id, sizeof(id));
-    return RUVIII_OK;
+    return guarded(nullptr, [&] {
+        ncclUniqueId id;
+        RUVIII_NCCL_CHECK(ncclGetUniqueId(&id));
+        std::memcpy(out128, &id, sizeof(id));
+    });
 }
 
 int ruviii_create_rank(ruviii_handle** out, int32_t device, int32_t rank, int32_t nranks, const void* id128) {
