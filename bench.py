@@ -294,7 +294,7 @@ def main():
     probes = None
     if args.probes:
         probes = {"copy_gbs": eng.probe(0, 2048), "cublas_dgemm_tflops_8192": eng.probe(1, 8192),
-                  "dmma_issue_tflops": eng.probe(2, 0)}
+                  "dmma_issue_tflops": eng.probe(2, 0), "host_gather_11000x1000_ms": eng.probe(3, 1000)}
         kernels["gram"]["frac_of_cublas_dgemm"] = kernels["gram"]["achieved"] / probes["cublas_dgemm_tflops_8192"]
 
     cpu_baseline = None

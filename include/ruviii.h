@@ -152,7 +152,8 @@ int ruviii_fast_residop(ruviii_handle* h, const double* A_rowmajor_rows_x_n, int
                         const int32_t* group_of_row, double* out);
 
 /* ---- micro-benchmarks used by bench.py to state practical ceilings beside the roofline ----------------- */
-/* which: 0 = device copy GB/s (bytes read+written), 1 = cuBLAS Dgemm TFLOP/s at size^3, 2 = DMMA issue peak TFLOP/s */
+/* which: 0 = device copy GB/s (bytes read+written), 1 = cuBLAS Dgemm TFLOP/s at size^3, 2 = DMMA issue peak TFLOP/s,
+ *        3 = ms to gather 11,000 x `size` scattered doubles out of pinned host memory (zero-copy over PCIe) */
 int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_out);
 
 #ifdef __cplusplus

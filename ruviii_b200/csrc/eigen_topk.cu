@@ -117,23 +117,111 @@ ek_ztz_kernel(const double* __restrict__ Zp, int nsplit, const double* __restric
 }
 
 // ---- one-CTA small dense work ----------------------------------------------------------------------------------
-// mode 0 (ORTHO): S = sum Sp, scale to unit diagonal, Cholesky, M = D L^-T          -> Q = Z M is orthonormal
-// mode 1 (RR):    H = sym(sum Hp), Jacobi  H = V diag(theta) V', theta descending    -> V, theta
-// mode 2 (CHECK): residual norms from Rp, converged flag, then ORTHO on the rotated block
+// RR:    H = sym(sum Hp), parallel cyclic Jacobi  H = V diag(theta) V', theta descending      -> V, theta
 template <int B>
-__global__ void __launch_bounds__(1024)
-ek_small_kernel(int mode, const double* __restrict__ Sp, const double* __restrict__ Hp, const double* __restrict__ Rp,
-                int n_part, int kk, double tol, int iter, double* __restrict__ M, double* __restrict__ V,
-                double* __restrict__ theta, double* __restrict__ resid, int* __restrict__ state) {
+__global__ void __launch_bounds__(512)
+ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, double* __restrict__ theta,
+             const int* __restrict__ state) {
     if (state[0]) return;
     __shared__ double A[B][B + 1];
     __shared__ double W[B][B + 1];
     __shared__ double cs[B / 2][2];
-    __shared__ double dscale[B];
     __shared__ int pr[B / 2][2];
     __shared__ int flag;
     const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < B * B; e += nt) {
+        double s = 0.0;
+        for (int p = 0; p < n_part; ++p) s += Hp[(int64_t)p * B * B + e];
+        W[e / B][e % B] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += nt) {
+        const int i = e / B, j = e % B;
+        A[i][j] = 0.5 * (W[i][j] + W[j][i]);
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += nt) W[e / B][e % B] = (e / B == e % B) ? 1.0 : 0.0;   // W = V
+    __syncthreads();
+    // parallel cyclic Jacobi, round-robin pairing: B/2 disjoint rotations per round, B-1 rounds per sweep
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        if (tid == 0) flag = 0;
+        __syncthreads();
+        for (int round = 0; round < B - 1; ++round) {
+            if (tid < B / 2) {
+                int p, q;
+                if (tid == 0) { p = B - 1; q = round; }
+                else { p = (round + tid) % (B - 1); q = (round - tid + (B - 1)) % (B - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+                double c = 1.0, s = 0.0;
+                if (fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+                    const double tau = (aqq - app) / (2.0 * apq);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = t * c;
+                    flag = 1;
+                }
+                cs[tid][0] = c; cs[tid][1] = s;
+                pr[tid][0] = p; pr[tid][1] = q;
+            }
+            __syncthreads();
+            for (int e = tid; e < (B / 2) * B; e += nt) {         // rows p, q:  A <- J' A
+                const int i = e / B, j = e % B;
+                const int p = pr[i][0], q = pr[i][1];
+                const double c = cs[i][0], s = cs[i][1];
+                const double x = A[p][j], y = A[q][j];
+                A[p][j] = c * x - s * y;
+                A[q][j] = s * x + c * y;
+            }
+            __syncthreads();
+            for (int e = tid; e < (B / 2) * B; e += nt) {         // columns p, q:  A <- A J,  V <- V J
+                const int i = e / B, j = e % B;
+                const int p = pr[i][0], q = pr[i][1];
+                const double c = cs[i][0], s = cs[i][1];
+                const double x = A[j][p], y = A[j][q];
+                A[j][p] = c * x - s * y;
+                A[j][q] = s * x + c * y;
+                const double vx = W[j][p], vy = W[j][q];
+                W[j][p] = c * vx - s * vy;
+                W[j][q] = s * vx + c * vy;
+            }
+            __syncthreads();
+        }
+        if (!flag) break;
+        __syncthreads();
+    }
+    // sort descending (rank sort), write V with permuted columns
+    if (tid < B) {
+        const double t = A[tid][tid];
+        int rank = 0;
+        for (int i = 0; i < B; ++i) {
+            const double u = A[i][i];
+            rank += (u > t) || (u == t && i < tid);
+        }
+        pr[tid % (B / 2)][tid / (B / 2)] = rank;      // reuse: rank of column tid
+        theta[rank] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += nt) {
+        const int i = e / B, j = e % B;
+        V[i * B + pr[j % (B / 2)][j / (B / 2)]] = W[i][j];
+    }
+}
 
+// ORTHO: S = sum Sp, scale to unit diagonal, Cholesky, M = D L^-T  -> Q = Z M is orthonormal.
+// With check != 0 it first turns the residual partials Rp into ||Z_j - theta_j X_j||, j < kk, and raises the
+// converged flag when all of them are <= tol * theta_0 (everything queued behind then exits at once).
+template <int B>
+__global__ void __launch_bounds__(256)
+ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restrict__ Rp, int n_part, int kk, double tol,
+                int iter, double* __restrict__ M, const double* __restrict__ theta, double* __restrict__ resid,
+                int* __restrict__ state) {
+    if (state[0]) return;
+    __shared__ double W[B][B + 1];
+    __shared__ double dscale[B];
+    __shared__ int flag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int mode = check ? 2 : 0;
     if (mode == 2) {
         // ||Z_j - theta_j X_j||, j < kk, against tol * theta_0
         if (tid < B) {
@@ -154,88 +242,10 @@ ek_small_kernel(int mode, const double* __restrict__ Sp, const double* __restric
         if (flag) return;
     }
 
-    if (mode == 1) {
-        for (int e = tid; e < B * B; e += nt) {
-            double s = 0.0;
-            for (int p = 0; p < n_part; ++p) s += Hp[(int64_t)p * B * B + e];
-            W[e / B][e % B] = s;
-        }
-        __syncthreads();
-        for (int e = tid; e < B * B; e += nt) {
-            const int i = e / B, j = e % B;
-            A[i][j] = 0.5 * (W[i][j] + W[j][i]);
-        }
-        __syncthreads();
-        for (int e = tid; e < B * B; e += nt) W[e / B][e % B] = (e / B == e % B) ? 1.0 : 0.0;   // W = V
-        __syncthreads();
-        // parallel cyclic Jacobi, round-robin pairing: B/2 disjoint rotations per round, B-1 rounds per sweep
-        for (int sweep = 0; sweep < 16; ++sweep) {
-            if (tid == 0) flag = 0;
-            __syncthreads();
-            for (int round = 0; round < B - 1; ++round) {
-                if (tid < B / 2) {
-                    int p, q;
-                    if (tid == 0) { p = B - 1; q = round; }
-                    else { p = (round + tid) % (B - 1); q = (round - tid + (B - 1)) % (B - 1); }
-                    if (p > q) { const int t = p; p = q; q = t; }
-                    const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
-                    double c = 1.0, s = 0.0;
-                    if (fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
-                        s = t * c;
-                        flag = 1;
-                    }
-                    cs[tid][0] = c; cs[tid][1] = s;
-                    pr[tid][0] = p; pr[tid][1] = q;
-                }
-                __syncthreads();
-                for (int e = tid; e < (B / 2) * B; e += nt) {         // rows p, q:  A <- J' A
-                    const int i = e / B, j = e % B;
-                    const int p = pr[i][0], q = pr[i][1];
-                    const double c = cs[i][0], s = cs[i][1];
-                    const double x = A[p][j], y = A[q][j];
-                    A[p][j] = c * x - s * y;
-                    A[q][j] = s * x + c * y;
-                }
-                __syncthreads();
-                for (int e = tid; e < (B / 2) * B; e += nt) {         // columns p, q:  A <- A J,  V <- V J
-                    const int i = e / B, j = e % B;
-                    const int p = pr[i][0], q = pr[i][1];
-                    const double c = cs[i][0], s = cs[i][1];
-                    const double x = A[j][p], y = A[j][q];
-                    A[j][p] = c * x - s * y;
-                    A[j][q] = s * x + c * y;
-                    const double vx = W[j][p], vy = W[j][q];
-                    W[j][p] = c * vx - s * vy;
-                    W[j][q] = s * vx + c * vy;
-                }
-                __syncthreads();
-            }
-            if (!flag) break;
-            __syncthreads();
-        }
-        // sort descending (rank sort), write V with permuted columns
-        if (tid < B) {
-            const double t = A[tid][tid];
-            int rank = 0;
-            for (int i = 0; i < B; ++i) {
-                const double u = A[i][i];
-                rank += (u > t) || (u == t && i < tid);
-            }
-            pr[tid % (B / 2)][tid / (B / 2)] = rank;      // reuse: rank of column tid
-            theta[rank] = t;
-        }
-        __syncthreads();
-        for (int e = tid; e < B * B; e += nt) {
-            const int i = e / B, j = e % B;
-            V[i * B + pr[j % (B / 2)][j / (B / 2)]] = W[i][j];
-        }
-        return;
-    }
-
-    // ---- ORTHO ----
+    // ---- ORTHO: warp-level Cholesky.  Lane i keeps row i of the scaled S in registers; pivots and columns travel
+    // by shuffle, so the 32 x 32 factorisation and the triangular inverse cost ~1000 shuffles instead of ~100 CTA
+    // barriers.
+    static_assert(B == 32, "the warp-level factorisation maps one matrix row to one lane");
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
         for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];
@@ -244,39 +254,41 @@ ek_small_kernel(int mode, const double* __restrict__ Sp, const double* __restric
     __syncthreads();
     if (tid < B) dscale[tid] = W[tid][tid] > 0.0 ? rsqrt(W[tid][tid]) : 1.0;
     __syncthreads();
-    for (int e = tid; e < B * B; e += nt) {
-        const int i = e / B, j = e % B;
-        A[i][j] = 0.5 * (W[i][j] + W[j][i]) * dscale[i] * dscale[j];
-    }
-    __syncthreads();
-    for (int j = 0; j < B; ++j) {                                  // right-looking Cholesky, lower triangle of A
-        if (tid == 0) {
-            const double d = A[j][j];
-            if (!(d > 1e-30)) { state[2] = j + 1; A[j][j] = 1.0; } else A[j][j] = sqrt(d);
-        }
-        __syncthreads();
-        if (tid > j && tid < B) A[tid][j] /= A[j][j];
-        __syncthreads();
-        for (int e = tid; e < B * B; e += nt) {
-            const int r = e / B, c = e % B;
-            if (r > j && c > j && c <= r) A[r][c] -= A[r][j] * A[c][j];
-        }
-        __syncthreads();
-    }
-    if (tid < B) {                                                 // W = L^-1, one column per thread
-        const int col = tid;
-        for (int i = 0; i < B; ++i) W[i][col] = 0.0;
-        for (int i = col; i < B; ++i) {
-            double s = (i == col) ? 1.0 : 0.0;
-            for (int q = col; q < i; ++q) s -= A[i][q] * W[q][col];
-            W[i][col] = s / A[i][i];
+    if (tid >= 32) return;
+    const int lane = tid;
+    double a[B], x[B];
+#pragma unroll
+    for (int c = 0; c < B; ++c) a[c] = 0.5 * (W[lane][c] + W[c][lane]) * dscale[lane] * dscale[c];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        const double djj = __shfl_sync(0xffffffffu, a[j], j);
+        double d = sqrt(djj);
+        if (!(djj > 1e-30)) { bad = j + 1; d = 1.0; }
+        const double lij = lane > j ? a[j] / d : (lane == j ? d : 0.0);
+        a[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < B; ++c) {
+            const double lcj = __shfl_sync(0xffffffffu, lij, c);
+            if (lane >= c) a[c] = fma(-lij, lcj, a[c]);
         }
     }
-    __syncthreads();
-    for (int e = tid; e < B * B; e += nt) {                        // M[a][b] = D[a] Linv[b][a]
-        const int a = e / B, b = e % B;
-        M[e] = (a <= b) ? dscale[a] * W[b][a] : 0.0;
+    // x[i] = Linv[i][lane]: forward substitution, row i of L broadcast from lane i
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        double s = lane == i ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < i; ++q) {
+            const double liq = __shfl_sync(0xffffffffu, a[q], i);
+            if (q >= lane) s = fma(-liq, x[q], s);
+        }
+        const double lii = __shfl_sync(0xffffffffu, a[i], i);
+        x[i] = lane <= i ? s / lii : 0.0;
     }
+    const double dl = dscale[lane];
+#pragma unroll
+    for (int bcol = 0; bcol < B; ++bcol) M[lane * B + bcol] = dl * x[bcol];      // M[a][b] = D[a] Linv[b][a], 0 for a > b
+    if (bad && lane == 0) state[2] = bad;
 }
 
 // ---- out = in M  (R x B by B x B), rows blocked through shared memory ---------------------------------------
@@ -391,7 +403,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     int launches = 0;
     ek_init_kernel<B><<<ceil_div((int64_t)R * B, 256), 256, 0, s>>>(w.Zp, R, w.state);
     ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, 1, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-    ek_small_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, nullptr, n_rb, kk, tol, 0, w.M, w.V, w.theta, w.resid, w.state);
+    ek_ortho_kernel<B><<<1, 256, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, 0, w.M, w.theta, w.resid, w.state);
     ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
     launches += 4;
     TopkResult res;
@@ -404,16 +416,16 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
             ++launches;
             if (it % T == 0) {
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, w.Q, R, w.Z, w.Sp, w.Hp, w.state);
-                ek_small_kernel<B><<<1, 1024, 0, s>>>(1, w.Sp, w.Hp, nullptr, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_rr_kernel<B><<<1, 512, 0, s>>>(w.Hp, n_rb, w.V, w.theta, w.state);
                 ek_rotate_kernel<B><<<n_rb, 256, 0, s>>>(w.Q, w.Z, w.V, w.theta, R, w.X, w.Rp, w.state);
                 // CHECK sets the flag; the ORTHO half of mode 2 needs S of the rotated block, so it is recomputed first
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, 1, nullptr, R, nullptr, w.Sp, nullptr, w.state);
-                ek_small_kernel<B><<<1, 1024, 0, s>>>(2, w.Sp, nullptr, w.Rp, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_ortho_kernel<B><<<1, 256, 0, s>>>(1, w.Sp, w.Rp, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
                 ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
                 launches += 6;
             } else {
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-                ek_small_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, nullptr, n_rb, kk, tol, it, w.M, w.V, w.theta, w.resid, w.state);
+                ek_ortho_kernel<B><<<1, 256, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
                 ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
                 launches += 3;
             }

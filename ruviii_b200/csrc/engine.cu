@@ -133,6 +133,7 @@ struct Shard {
     DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state;
     TopkWork topk{};
     alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
+    alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
     GramPlan gp;
     int rsplit = 1;
 };
@@ -173,6 +174,7 @@ struct ruviii_handle {
     std::vector<std::pair<int, int>> dup_slots;   // (dst slot, src slot) for k values with the same effective k
     int launches = 0;
     ruviii_info info{};
+    int upd_impl = 1;
     int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
     int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
     bool use_topk = false;
@@ -240,6 +242,7 @@ void finish_create(ruviii_handle* h) {
     std::memset(h->h_flags, 0, 64 * sizeof(int));
     h->gram_impl = env_int("RUVIII_GRAM_IMPL", 1);
     h->eig_impl = env_int("RUVIII_EIG_IMPL", 0);
+    h->upd_impl = env_int("RUVIII_UPD_IMPL", 1);
     if (const char* t = std::getenv("RUVIII_EIG_TOL")) h->eig_tol = std::atof(t);
 }
 
@@ -426,6 +429,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (s.gp.impl == 2) {
                 launch_gram_tma_prepare(s.gp, s.Y0.p, s.ld, s.tmap);
             }
+            if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
     }
     // ---- solver (global rank 0 only) ----
@@ -655,8 +659,12 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         rec(E_SOLVE);
         for_shards([&](Shard& s) {
             const int64_t stride = (int64_t)h->m1 * s.ld;
-            launch_update(s.Y.p, s.ld, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
-                          stride, s.stream);
+            if (h->upd_impl == 2)
+                launch_update_tma(s.tmap_y, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
+                                  stride, s.stream);
+            else
+                launch_update(s.Y.p, s.ld, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
+                              stride, s.stream);
             if (want_ps)
                 launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At.p + (size_t)h->m1 * kp, kp, s.at.p, s.ld, kk, h->kmask,
                               h->slot_of_k, s.out_ps.p, s.ld, (int64_t)h->n_ps * s.ld, s.stream);
@@ -1006,6 +1014,8 @@ int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_ou
             *value_out = probe_copy_gbs((size_t)std::max(size, 64) << 20, s.stream);
         } else if (which == 2) {
             *value_out = probe_dmma_tflops(h->n_sms, s.stream);
+        } else if (which == 3) {
+            *value_out = probe_host_gather_ms(11000, 20000, std::max(size, 1), s.stream);
         } else if (which == 1) {
             if (!h->blas && cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) throw Error(RUVIII_ERR_CUDA, "cublasCreate failed");
             cublasSetStream(h->blas, s.stream);

@@ -11,11 +11,7 @@
 // FP64 has no tcgen05 path on Blackwell (tcgen05.mma kinds are f16/tf32/f8f6f4/i8/mx*), so the sm_100a
 // content of this kernel is the TMA + mbarrier staging; the math is warp-level DMMA.
 #include "kernels.cuh"
-
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include <cstring>
+#include "tma.cuh"
 
 namespace ruviii {
 
@@ -24,7 +20,7 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 6;
 constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;       // two consumer warpgroups + one producer warpgroup
 constexpr int TILE_BYTES = BM * BK * 8;                 // 16 KB
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -34,41 +30,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-
 // element (row r, column k) of a 128 x 16-double box stored with the 128-byte swizzle
 __device__ __forceinline__ int swz(int r, int k) { return r * 16 + ((((k >> 1) ^ (r & 7)) << 1) | (k & 1)); }
 
-__global__ void __maxnreg__(216)
+__global__ void __launch_bounds__(THREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int K, int kchunk, const int2* __restrict__ tile_map,
                 int n_tiles, double* __restrict__ ws) {
     extern __shared__ unsigned char smem_raw[];
@@ -88,14 +53,16 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int K, int kchunk, con
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], CONSUMER_WARPS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
+    // Registers are allocated per warpgroup (4 warps): 12 warps x 168 registers fill the file, so the producer
+    // warpgroup hands its registers back and the two consumer warpgroups grow to what 64 accumulators need.
+    if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== producer: one thread drives the TMA unit =====
-        if (lane == 0) {
+        if (warp == CONSUMER_WARPS && lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -110,6 +77,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int K, int kchunk, con
     }
 
     // ===== consumers: 8 warps as 2 (rows) x 4 (cols), warp tile 64 x 32 =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, kq = lane & 3;
     double acc[8][4][2];
@@ -160,34 +128,11 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int K, int kchunk, con
             }
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        RUVIII_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (q != cudaDriverEntryPointSuccess || !p) throw Error(2, "cuTensorMapEncodeTiled is not available in this driver");
-        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    }
-    return fn;
-}
-
 }  // namespace
-
-static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is expected to be 128 bytes");
 
 // Encode the 2-D tensor map of Y0 (inner dimension = padded gene count, outer = R rows) into desc_out (128 B, host).
 int launch_gram_tma_prepare(const GramPlan& gp, const double* Y0, int64_t ldY0, void* desc_out) {
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {(cuuint64_t)ldY0, (cuuint64_t)gp.R};
-    const cuuint64_t strides[1] = {(cuuint64_t)ldY0 * 8};
-    const cuuint32_t box[2] = {BK, BM};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(Y0), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error(2, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-    std::memcpy(desc_out, &m, sizeof(m));
+    encode_tensor_map_2d(desc_out, Y0, (uint64_t)ldY0, (uint64_t)gp.R, (uint64_t)ldY0, BK, BM, /*swizzle128=*/true);
     return 0;
 }
 

@@ -99,8 +99,15 @@ void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const doub
                    const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k,
                    double* out, int64_t ldout, int64_t out_stride, cudaStream_t s);
 
+// K6 impl 2 (update_tma.cu): same update, Y staged through a TMA + mbarrier shared-memory ring.
+void update_tma_prepare(const double* Y, int64_t ldY, int rows, void* desc_out_host128);
+void launch_update_tma(const void* tmap_host, int rows, int n, const double* At_rows, int kp, const double* at,
+                       int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k, double* out, int64_t ldout,
+                       int64_t out_stride, cudaStream_t s);
+
 // micro-benchmarks (ceilings quoted beside the roofline)
 float probe_copy_gbs(size_t bytes, cudaStream_t s);
 float probe_dmma_tflops(int n_sms, cudaStream_t s);
+float probe_host_gather_ms(int rows, int n, int n_idx, cudaStream_t s);
 
 }  // namespace ruviii

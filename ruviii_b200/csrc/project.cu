@@ -171,18 +171,41 @@ ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int
         }
 }
 
-// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA; each warp owns entries e = warp, warp + 32, ...,
-// lanes stride the control genes and a shuffle tree closes the sum: fixed order, bitwise reproducible.
+// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA: acT is streamed through shared memory in coalesced
+// chunks of 64 control genes; thread (pair e, quarter s) sums rows s, s+4, ... of every chunk and the four
+// quarters are added in a fixed order, so the result is bitwise reproducible.
+constexpr int kAcChunk = 64;
 __global__ void __launch_bounds__(1024)
 ac_gram_kernel(const double* __restrict__ acT, int n_ctl, int kp, double* __restrict__ Gm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = warp; e < kp * kp; e += 32) {
-        const int a = e / kp, b = e - a * kp;
-        double s = 0.0;
-        for (int c = lane; c < n_ctl; c += 32) s = fma(acT[(int64_t)c * kp + a], acT[(int64_t)c * kp + b], s);
-        s = warp_sum(s);
-        if (lane == 0) Gm[e] = s;
+    __shared__ double sA[kAcChunk * kMaxK];
+    __shared__ double sP[4][kMaxK * kMaxK];
+    const int tid = threadIdx.x;
+    const int npair = kp * kp;
+    const int quarter = tid / 256, e = tid % 256;       // kp <= 16: one pair per thread; kp = 32: four pairs per thread
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c0 = 0; c0 < n_ctl; c0 += kAcChunk) {
+        const int nc = min(kAcChunk, n_ctl - c0);
+        __syncthreads();
+        for (int i = tid; i < nc * kp; i += 1024) sA[i] = acT[(int64_t)c0 * kp + i];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pe = e + u * 256;
+            if (pe < npair) {
+                const int a = pe / kp, b = pe - a * kp;
+                double s = acc[u];
+                for (int r = quarter; r < nc; r += 4) s = fma(sA[r * kp + a], sA[r * kp + b], s);
+                acc[u] = s;
+            }
+        }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int pe = e + u * 256;
+        if (pe < npair) sP[quarter][pe] = acc[u];
+    }
+    __syncthreads();
+    for (int pe = tid; pe < npair; pe += 1024) Gm[pe] = ((sP[0][pe] + sP[1][pe]) + sP[2][pe]) + sP[3][pe];
 }
 
 // ---- K5c: column means of A, Cholesky of Gm[:kk,:kk], inverse of the factor -------------------------------

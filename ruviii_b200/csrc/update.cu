@@ -12,6 +12,9 @@
 // per thread.  Y and newY are touched exactly once, so they bypass L1 allocation.
 #include "kernels.cuh"
 
+#include <cstring>
+#include <vector>
+
 namespace ruviii {
 
 namespace {
@@ -145,6 +148,52 @@ void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const doub
     }
 #undef RUVIII_UPD
     RUVIII_LAUNCH_CHECK();
+}
+
+// gather of m1 x n_ctl scattered doubles straight out of pinned HOST memory (zero-copy over PCIe): how fast could
+// the control-gene columns be fetched ahead of the bulk upload?  Returns milliseconds.
+__global__ void __launch_bounds__(256)
+host_gather_kernel(const double* __restrict__ Yh, int64_t ld, int rows, const int* __restrict__ idx, int n_idx,
+                   double* __restrict__ out) {
+    const int64_t total = (int64_t)rows * n_idx;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / n_idx;
+        const int c = (int)(e - r * n_idx);
+        out[e] = Yh[r * ld + idx[c]];
+    }
+}
+
+float probe_host_gather_ms(int rows, int n, int n_idx, cudaStream_t s) {
+    double* Yh = nullptr;
+    RUVIII_CUDA_CHECK(cudaHostAlloc((void**)&Yh, (size_t)rows * n * 8, cudaHostAllocDefault));
+    std::memset(Yh, 0, (size_t)rows * n * 8);
+    std::vector<int> idx(n_idx);
+    for (int i = 0; i < n_idx; ++i) idx[i] = (int)((int64_t)i * n / n_idx) + (i * 7) % 5;
+    int* didx = nullptr;
+    double* out = nullptr;
+    RUVIII_CUDA_CHECK(cudaMalloc(&didx, n_idx * sizeof(int)));
+    RUVIII_CUDA_CHECK(cudaMalloc(&out, (size_t)rows * n_idx * 8));
+    RUVIII_CUDA_CHECK(cudaMemcpy(didx, idx.data(), n_idx * sizeof(int), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < 3; ++it) {
+        cudaEventRecord(e0, s);
+        host_gather_kernel<<<148 * 8, 256, 0, s>>>(Yh, n, rows, didx, n_idx, out);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(didx);
+    cudaFree(out);
+    cudaFreeHost(Yh);
+    RUVIII_LAUNCH_CHECK();
+    return best;
 }
 
 float probe_copy_gbs(size_t bytes, cudaStream_t s) {

@@ -232,8 +232,14 @@ def test_dimension_errors(engine):
         engine.normalise(_cabi.make_params(), p.Y, p.replicate_data, groups, p.ctl[:-1], [1])
     with pytest.raises(rv.RuviiiError):
         engine.normalise(_cabi.make_params(), p.Y, p.replicate_data, groups, p.ctl, [-1])
-    with pytest.raises(rv.RuviiiError):
-        engine.normalise(_cabi.make_params(), p.Y, p.replicate_data, groups, p.ctl, [40])     # k > 32 unsupported
+    # k = 40 is clamped to r = 3 (ruvIII.R:142), so it is legal here; an EFFECTIVE k > 32 is what is unsupported
+    ok = engine.normalise(_cabi.make_params(), p.Y, p.replicate_data, groups, p.ctl, [40])
+    assert ok["info"].kmax_eff == 3
+    big = make_problem(m1=400, n=700, groups=40, rep=3, n_ctl=100, k=40, seed=15)            # r = 80
+    with pytest.raises(rv.RuviiiError) as e:
+        engine.normalise(_cabi.make_params(), big.Y, big.replicate_data,
+                         api.group_codes(big.sample_names + big.replicate_names), big.ctl, [40])
+    assert e.value.code == _cabi.ERR_UNSUPPORTED
 
 
 def test_fast_residop_primitive(engine):
@@ -262,6 +268,29 @@ def test_gram_kernels_agree():
     assert np.allclose(outs[1][1], outs[0][1], rtol=1e-12)
     S = O.ruvIII_structural(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 6, apply_log=False)
     assert np.allclose(outs[1][1][:6], S["eigenvalues"][:6], rtol=1e-11)
+
+
+@pytest.mark.parametrize("env", [{"RUVIII_GRAM_IMPL": "2"}, {"RUVIII_UPD_IMPL": "2"}],
+                         ids=["gram_tma", "update_tma"])
+def test_tma_kernel_variants_match(env):
+    """The TMA + mbarrier variants of the Gram and of the update give the same results as the default kernels:
+    odd gene count, R = 258 (three tile rows, last one ragged), multi-k, k = 0 included."""
+    p = make_problem(m1=333, n=4101, groups=129, rep=2, n_ctl=300, k=7, seed=16)
+    ks = [0, 2, 7]
+    with rv.Engine(devices=[0]) as eng:
+        base = run_engine(eng, p, ks)
+    os.environ.update(env)
+    try:
+        with rv.Engine(devices=[0]) as eng:
+            alt = run_engine(eng, p, ks)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    for i in range(len(ks)):
+        assert O.rel_frob(alt["newY"][i], base["newY"][i]) < 1e-12
+    ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 7, apply_log=False)
+    check_against(alt, 2, ref, 7, 333)
+    assert np.array_equal(alt["newY"][0], p.Y)
 
 
 def test_eigensolvers_agree():
