@@ -266,8 +266,9 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     nk = len(ks)
     upd_bytes = 8.0 * m1 * n_loc * (1 + nk)                          # K6: read Y once, write every requested k
-    res_bytes = 16.0 * info.active_rows * n_loc                      # K1: 16 B per non-singleton cell
-    gram_flops = float(info.active_rows) * (info.active_rows + 1) * n_loc   # K2: symmetric half, FMA = 2 flop
+    R = info.gram_order                                              # Helmert rows: active_rows - #groups = m - ncol(M)
+    res_bytes = 8.0 * (info.active_rows + R) * n_loc                 # K1: read every member row, write every contrast row
+    gram_flops = float(R) * (R + 1) * n_loc                          # K2: symmetric half of the R x R Gram, FMA = 2 flop
     kernels = {
         "update": {"bound": "hbm", "ms": stage_ms["ms_update"], "achieved": upd_bytes / (stage_ms["ms_update"] * 1e-3) / 1e9,
                    "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": upd_bytes},
@@ -316,7 +317,8 @@ def main():
                    "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next},
                    "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(
                        info.eig_solver, "none"), "eig_iterations": info.eig_iterations,
-                   "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1"))},
+                   "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1")), "gram_order": info.gram_order,
+                   "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "1"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes,
     }

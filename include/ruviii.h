@@ -82,6 +82,8 @@ typedef struct ruviii_info {
     double eig_top, eig_kmax, eig_next;/* lambda_1, lambda_kmax, lambda_kmax+1 (gap that conditions newY)       */
     int32_t eig_solver;                /* 0 none, 1 cuSOLVER syevd, 2 cuSOLVER syevdx, 3 block subspace iteration   */
     int32_t eig_iterations;            /* subspace-iteration passes (solver 3); 0 otherwise                        */
+    int32_t gram_order;                /* order of the Gram actually formed: active_rows - #non-singleton groups    */
+    int32_t reserved_i;
 } ruviii_info;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */

@@ -41,7 +41,8 @@ class Info(C.Structure):
                 ("ms_allreduce_ctl", C.c_float), ("ms_solve", C.c_float), ("ms_update", C.c_float),
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
                 ("eig_top", C.c_double), ("eig_kmax", C.c_double), ("eig_next", C.c_double),
-                ("eig_solver", C.c_int32), ("eig_iterations", C.c_int32)]
+                ("eig_solver", C.c_int32), ("eig_iterations", C.c_int32), ("gram_order", C.c_int32),
+                ("reserved_i", C.c_int32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

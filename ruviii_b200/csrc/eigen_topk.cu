@@ -95,6 +95,7 @@ ek_ztz_kernel(const double* __restrict__ Zp, int nsplit, const double* __restric
         const int r = e / B, c = e - r * B;
         double z = 0.0, q = 0.0;
         if (r0 + r < R) {
+#pragma unroll 4
             for (int s = 0; s < nsplit; ++s) z += Zp[((int64_t)s * R + r0 + r) * B + c];
             if (Z) Z[(int64_t)(r0 + r) * B + c] = z;
             if (Hp) q = Q[(int64_t)(r0 + r) * B + c];
@@ -131,7 +132,8 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
-        for (int p = 0; p < n_part; ++p) s += Hp[(int64_t)p * B * B + e];
+#pragma unroll 8
+        for (int p = 0; p < n_part; ++p) s += Hp[(int64_t)p * B * B + e];      // unrolled: 8 loads in flight, fixed order
         W[e / B][e % B] = s;
     }
     __syncthreads();
@@ -226,6 +228,7 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
         // ||Z_j - theta_j X_j||, j < kk, against tol * theta_0
         if (tid < B) {
             double s = 0.0;
+#pragma unroll 8
             for (int p = 0; p < n_part; ++p) s += Rp[(int64_t)p * B + tid];
             resid[tid] = sqrt(s);
         }
@@ -248,7 +251,8 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
     static_assert(B == 32, "the warp-level factorisation maps one matrix row to one lane");
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
-        for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];
+#pragma unroll 8
+        for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];      // unrolled: 8 loads in flight, fixed order
         W[e / B][e % B] = s;
     }
     __syncthreads();

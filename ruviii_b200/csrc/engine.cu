@@ -163,6 +163,7 @@ struct ruviii_handle {
     ruviii_params prm{};
     int m1 = 0, n_ps = 0, m = 0, n_local_total = 0;
     int p = 0, R = 0, r = 0, n_groups_active = 0, max_group = 0;
+    int active_rows = 0;                // rows in non-singleton groups; R = active_rows - n_groups_active (Helmert rows)
     int64_t n_ctl_global = 0;
     std::vector<int> ks, k_eff;
     int kmax = 0, kk = 0, kp = 4;       // kk = min(kmax, r); kp = padded register extent
@@ -309,7 +310,8 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         h->max_group = std::max(h->max_group, (int)kv.second.size());
     }
     h->n_groups_active = (int)grp_start.size() - 1;
-    h->R = (int)grp_rows.size();
+    h->active_rows = (int)grp_rows.size();
+    h->R = h->active_rows - h->n_groups_active;     // order of the Gram: sum(size - 1) = m - ncol(M)
     h->no_replicates = h->p >= m_for_M;             // ruvIII.R:128-129
 
     // ---- k values ----
@@ -575,8 +577,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         if (!h->have_user_alpha) {
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
-                launch_residop(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld,
-                               s.stream);
+                launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, s.n, s.Y0.p, s.ld, s.stream);
             });
             h->launches += 1;
             rec(E_RESIDOP);
@@ -707,7 +708,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     I.struct_size = sizeof(ruviii_info);
     I.ms_h2d = keep_h2d;
     I.ms_d2h = keep_d2h;
-    I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->R; I.r = h->r;
+    I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->active_rows; I.r = h->r; I.gram_order = h->R;
     I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = 1;
     I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
     I.eig_solver = (skip || h->have_user_alpha) ? 0 : h->eig_solver_used; I.eig_iterations = h->eig_iterations;

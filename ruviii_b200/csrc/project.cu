@@ -126,44 +126,62 @@ gather_ac_kernel(const double* __restrict__ alpha, int64_t ld, int kp, const int
     acT[e] = alpha[(int64_t)j * ld + ctl_idx[c]];
 }
 
-// ---- K5: A[i][j] = sum_c Y[i][ctl_idx[c]] * acT[c][j] ; one warp per 4 rows, lanes stride the control genes
+// ---- K5: A[i][j] = sum_c Y[i][ctl_idx[c]] * acT[c][j] -------------------------------------------------------------
+// A gather: every control gene of every row costs one 32-byte sector (64-byte DRAM granule) for 8 useful bytes, so
+// the kernel is bound by sectors in flight.  One warp owns kCtlRows rows; per tile of 128 control genes each lane
+// issues 4 x kCtlRows independent gathers before touching any of them, then multiplies against the acT tile staged
+// in shared memory (row stride kp + 1: lanes read different rows of acT, an odd stride keeps them on distinct banks).
 constexpr int kCtlWarps = 8;
+constexpr int kCtlTile = 128;
 __host__ __device__ constexpr int ctl_rows_per_warp(int kp) { return kp <= 16 ? 4 : 2; }   // 64 accumulators/thread
 
 template <int KP>
 __global__ void __launch_bounds__(kCtlWarps * 32)
 ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl,
                     const double* __restrict__ acT, double* __restrict__ A) {
-    constexpr int kCtlRowsPerWarp = ctl_rows_per_warp(KP);
+    constexpr int NR = ctl_rows_per_warp(KP);
+    __shared__ double sAc[kCtlTile][KP + 1];
+    __shared__ int sIdx[kCtlTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row0 = (blockIdx.x * kCtlWarps + warp) * kCtlRowsPerWarp;
-    if (row0 >= rows_w) return;
-    const double* rp[kCtlRowsPerWarp];
+    const int row0 = (blockIdx.x * kCtlWarps + warp) * NR;
+    const double* rp[NR];
 #pragma unroll
-    for (int u = 0; u < kCtlRowsPerWarp; ++u) rp[u] = src.row(min(row0 + u, rows_w - 1));
-    double acc[kCtlRowsPerWarp][KP];
+    for (int u = 0; u < NR; ++u) rp[u] = src.row(min(row0 + u, rows_w - 1));
+    double acc[NR][KP];
 #pragma unroll
-    for (int u = 0; u < kCtlRowsPerWarp; ++u)
+    for (int u = 0; u < NR; ++u)
 #pragma unroll
         for (int j = 0; j < KP; ++j) acc[u][j] = 0.0;
-    for (int c = lane; c < n_ctl; c += 32) {
-        const int g = ctl_idx[c];
-        double y[kCtlRowsPerWarp];
+    for (int c0 = 0; c0 < n_ctl; c0 += kCtlTile) {
+        const int nc = min(kCtlTile, n_ctl - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < kCtlTile * KP; e += kCtlWarps * 32) {
+            const int c = e / KP, j = e - c * KP;
+            sAc[c][j] = c < nc ? acT[(int64_t)(c0 + c) * KP + j] : 0.0;
+        }
+        for (int c = threadIdx.x; c < kCtlTile; c += kCtlWarps * 32) sIdx[c] = c < nc ? ctl_idx[c0 + c] : ctl_idx[c0];
+        __syncthreads();
+        double y[4][NR];
 #pragma unroll
-        for (int u = 0; u < kCtlRowsPerWarp; ++u) y[u] = rp[u][g];
-        const double* a = acT + (int64_t)c * KP;
+        for (int t = 0; t < 4; ++t) {
+            const int g = sIdx[t * 32 + lane];                   // padded entries repeat a valid gene; their acT rows are 0
 #pragma unroll
-        for (int j = 0; j < KP; j += 2) {
-            const double2 w = *reinterpret_cast<const double2*>(a + j);
+            for (int u = 0; u < NR; ++u) y[t][u] = rp[u][g];
+        }
 #pragma unroll
-            for (int u = 0; u < kCtlRowsPerWarp; ++u) {
-                acc[u][j] = fma(y[u], w.x, acc[u][j]);
-                acc[u][j + 1] = fma(y[u], w.y, acc[u][j + 1]);
+        for (int t = 0; t < 4; ++t) {
+            const double* a = &sAc[t * 32 + lane][0];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                const double w = a[j];
+#pragma unroll
+                for (int u = 0; u < NR; ++u) acc[u][j] = fma(y[t][u], w, acc[u][j]);
             }
         }
     }
+    if (row0 >= rows_w) return;
 #pragma unroll
-    for (int u = 0; u < kCtlRowsPerWarp; ++u)
+    for (int u = 0; u < NR; ++u)
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             const double v = warp_sum(acc[u][j]);

@@ -61,6 +61,47 @@ residop_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restr
     }
 }
 
+// Helmert contrasts of every replicate group (see kernels.cuh): one pass, 8 B read per member cell and 8 B written
+// per contrast cell.  Groups of up to kRegGroup members are loaded in one batch (all loads in flight before the
+// first use); larger groups stream with a running sum.
+__global__ void __launch_bounds__(kResidopThreads)
+helmert_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restrict__ grp_rows, int n_groups,
+               int n_pairs, double* __restrict__ Z, int64_t ldZ) {
+    const int pair = blockIdx.x * kResidopThreads + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const int64_t col = 2 * (int64_t)pair;
+    for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        const int s = grp_start[g];
+        const int sz = grp_start[g + 1] - s;
+        double* out = Z + (int64_t)(s - g) * ldZ + col;        // every earlier group contributed (size - 1) rows
+        if (sz <= kRegGroup) {
+            double2 v[kRegGroup];
+#pragma unroll
+            for (int t = 0; t < kRegGroup; ++t)
+                if (t < sz) v[t] = ld_stream(src.row(grp_rows[s + t]) + col);
+            double2 run = v[0];
+#pragma unroll
+            for (int j = 1; j < kRegGroup; ++j) {
+                if (j < sz) {
+                    const double c = sqrt((double)j / (double)(j + 1)), inv = 1.0 / (double)j;
+                    st_stream(out + (int64_t)(j - 1) * ldZ, make_double2(c * (run.x * inv - v[j].x), c * (run.y * inv - v[j].y)));
+                    run.x += v[j].x;
+                    run.y += v[j].y;
+                }
+            }
+        } else {
+            double2 run = ld_stream(src.row(grp_rows[s]) + col);
+            for (int j = 1; j < sz; ++j) {
+                const double2 y = ld_stream(src.row(grp_rows[s + j]) + col);
+                const double c = sqrt((double)j / (double)(j + 1)), inv = 1.0 / (double)j;
+                st_stream(out + (int64_t)(j - 1) * ldZ, make_double2(c * (run.x * inv - y.x), c * (run.y * inv - y.y)));
+                run.x += y.x;
+                run.y += y.y;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 log2_kernel(double* __restrict__ Y, int64_t ld, int rows, int n, double pc) {
     const int64_t total = (int64_t)rows * n;
@@ -88,6 +129,15 @@ void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n
     const int n_pairs = (n + 1) / 2;          // pitches are even and zero padded, so the odd tail pair is safe
     dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
     residop_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Y0, ldY0);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int n, double* Z, int64_t ldZ,
+                    cudaStream_t s) {
+    if (n_groups <= 0 || n <= 0) return;
+    const int n_pairs = (n + 1) / 2;
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    helmert_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Z, ldZ);
     RUVIII_LAUNCH_CHECK();
 }
 

@@ -12,6 +12,7 @@
 // per thread.  Y and newY are touched exactly once, so they bypass L1 allocation.
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -36,66 +37,71 @@ template <int KP>
 __global__ void __launch_bounds__(kUpdThreads, KP <= 8 ? 6 : KP <= 16 ? 4 : 2)
 update_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, const double* __restrict__ At,
               const double* __restrict__ at, int64_t ldat, int kk, uint64_t kmask, KSlots slots,
-              double* __restrict__ out, int64_t ldout, int64_t out_stride) {
+              double* __restrict__ out, int64_t ldout, int64_t out_stride, int rows_per_cta) {
     __shared__ __align__(16) double sAt[kUpdRows][KP];
     const int pair = blockIdx.x * kUpdThreads + threadIdx.x;
     const bool active = pair < n_pairs;
     const int64_t col = 2 * (int64_t)pair;
-    const int row0 = blockIdx.y * kUpdRows;
-    const int nrows = min(kUpdRows, rows - row0);
-    for (int e = threadIdx.x; e < kUpdRows * KP; e += kUpdThreads) {
-        const int r = e / KP;
-        sAt[r][e - r * KP] = r < nrows ? At[(int64_t)(row0 + r) * KP + (e - r * KP)] : 0.0;
-    }
     double2 a[KP];
 #pragma unroll
     for (int q = 0; q < KP; ++q)
         a[q] = (active && q < kk) ? *reinterpret_cast<const double2*>(at + (int64_t)q * ldat + col)
                                   : make_double2(0.0, 0.0);
-    __syncthreads();
-    if (!active) return;
     const bool want0 = kmask & 1ull;
-    for (int rb = 0; rb < nrows; rb += kUpdUnroll) {
-        double2 y[kUpdUnroll];
-#pragma unroll
-        for (int u = 0; u < kUpdUnroll; ++u)
-            y[u] = (rb + u < nrows) ? ld_stream(Y + (int64_t)(row0 + rb + u) * ldY + col) : make_double2(0.0, 0.0);
-        if (want0) {
-            double* o = out + (int64_t)slots.slot[0] * out_stride + col;
+    const int cta_row0 = blockIdx.y * rows_per_cta;
+    const int cta_row1 = min(cta_row0 + rows_per_cta, rows);
+    // a CTA keeps its gene pair columns (a~ in registers) and walks down its rows in blocks of kUpdRows
+    for (int row0 = cta_row0; row0 < cta_row1; row0 += kUpdRows) {
+        const int nrows = min(kUpdRows, cta_row1 - row0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < kUpdRows * KP; e += kUpdThreads) {
+            const int r = e / KP;
+            sAt[r][e - r * KP] = r < nrows ? At[(int64_t)(row0 + r) * KP + (e - r * KP)] : 0.0;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int rb = 0; rb < nrows; rb += kUpdUnroll) {
+            double2 y[kUpdUnroll];
 #pragma unroll
             for (int u = 0; u < kUpdUnroll; ++u)
-                if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
-        }
+                y[u] = (rb + u < nrows) ? ld_stream(Y + (int64_t)(row0 + rb + u) * ldY + col) : make_double2(0.0, 0.0);
+            if (want0) {
+                double* o = out + (int64_t)slots.slot[0] * out_stride + col;
 #pragma unroll
-        for (int q = 0; q < KP; q += 2) {
-            if (q < kk) {
-                // volatile shared loads pin the A~ reads next to their use: without them the compiler hoists all
-                // KP x 4 broadcasts to the top of the row step and the kernel needs > 200 registers
-                double2 w[kUpdUnroll];
+                for (int u = 0; u < kUpdUnroll; ++u)
+                    if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+            }
 #pragma unroll
-                for (int u = 0; u < kUpdUnroll; ++u) w[u] = lds_v2(&sAt[rb + u][q]);   // rb + u < kUpdRows always
+            for (int q = 0; q < KP; q += 2) {
+                if (q < kk) {
+                    // volatile shared loads pin the A~ reads next to their use: without them the compiler hoists all
+                    // KP x 4 broadcasts to the top of the row step and the kernel needs > 200 registers
+                    double2 w[kUpdUnroll];
 #pragma unroll
-                for (int u = 0; u < kUpdUnroll; ++u) {
-                    y[u].x = fma(-w[u].x, a[q].x, y[u].x);
-                    y[u].y = fma(-w[u].x, a[q].y, y[u].y);
-                }
-                if ((kmask >> (q + 1)) & 1ull) {
-                    double* o = out + (int64_t)slots.slot[q + 1] * out_stride + col;
-#pragma unroll
-                    for (int u = 0; u < kUpdUnroll; ++u)
-                        if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
-                }
-                if (q + 1 < kk) {
+                    for (int u = 0; u < kUpdUnroll; ++u) w[u] = lds_v2(&sAt[rb + u][q]);   // rb + u < kUpdRows always
 #pragma unroll
                     for (int u = 0; u < kUpdUnroll; ++u) {
-                        y[u].x = fma(-w[u].y, a[q + 1].x, y[u].x);
-                        y[u].y = fma(-w[u].y, a[q + 1].y, y[u].y);
+                        y[u].x = fma(-w[u].x, a[q].x, y[u].x);
+                        y[u].y = fma(-w[u].x, a[q].y, y[u].y);
                     }
-                    if ((kmask >> (q + 2)) & 1ull) {
-                        double* o = out + (int64_t)slots.slot[q + 2] * out_stride + col;
+                    if ((kmask >> (q + 1)) & 1ull) {
+                        double* o = out + (int64_t)slots.slot[q + 1] * out_stride + col;
 #pragma unroll
                         for (int u = 0; u < kUpdUnroll; ++u)
                             if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+                    }
+                    if (q + 1 < kk) {
+#pragma unroll
+                        for (int u = 0; u < kUpdUnroll; ++u) {
+                            y[u].x = fma(-w[u].y, a[q + 1].x, y[u].x);
+                            y[u].y = fma(-w[u].y, a[q + 1].y, y[u].y);
+                        }
+                        if ((kmask >> (q + 2)) & 1ull) {
+                            double* o = out + (int64_t)slots.slot[q + 2] * out_stride + col;
+#pragma unroll
+                            for (int u = 0; u < kUpdUnroll; ++u)
+                                if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+                        }
                     }
                 }
             }
@@ -136,10 +142,18 @@ void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const doub
     KSlots slots;
     for (int i = 0; i <= kMaxK; ++i) slots.slot[i] = (signed char)out_slot_of_k[i];
     const int n_pairs = (n + 1) / 2;
-    dim3 grid(ceil_div(n_pairs, kUpdThreads), ceil_div(rows, kUpdRows));
+    // rows per CTA: by default one wave of CTAs covers the matrix (every resident CTA streams one long column
+    // strip, all strips of a row block advance together, so DRAM sees whole rows); RUVIII_UPD_ROWS overrides.
+    const int col_tiles = ceil_div(n_pairs, kUpdThreads);
+    static const int env_rows = [] { const char* v = std::getenv("RUVIII_UPD_ROWS"); return v && *v ? std::atoi(v) : 0; }();
+    const int ctas_per_sm = kp <= 8 ? 6 : kp <= 16 ? 4 : 2;
+    int row_chunks = std::max(1, (148 * ctas_per_sm) / col_tiles);
+    int rows_per_cta = (int)round_up(ceil_div(rows, row_chunks), kUpdRows);
+    if (env_rows > 0) rows_per_cta = (int)round_up(env_rows, kUpdRows);
+    dim3 grid(col_tiles, ceil_div(rows, rows_per_cta));
 #define RUVIII_UPD(KP)                                                                                         \
     update_kernel<KP><<<grid, kUpdThreads, 0, s>>>(Yrows, ldY, rows, n_pairs, At_rows, at, ldat, kk, kmask,    \
-                                                   slots, out, ldout, out_stride)
+                                                   slots, out, ldout, out_stride, rows_per_cta)
     switch (kp) {
         case 4: RUVIII_UPD(4); break;
         case 8: RUVIII_UPD(8); break;
