@@ -156,10 +156,13 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
                 if (p > q) { const int t = p; p = q; q = t; }
                 const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
                 double c = 1.0, s = 0.0;
-                if (fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
-                    const double tau = (aqq - app) / (2.0 * apq);
-                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    c = 1.0 / sqrt(1.0 + t * t);
+                if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
+                    // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written with one
+                    // sqrt, one division and one rsqrt (the rotation sits on the critical path of every round)
+                    const double zeta = aqq - app, beta = 2.0 * apq;
+                    const double rr = sqrt(fma(zeta, zeta, beta * beta));
+                    const double t = beta / (zeta + (zeta >= 0.0 ? rr : -rr));
+                    c = rsqrt(fma(t, t, 1.0));
                     s = t * c;
                     flag = 1;
                 }
@@ -245,10 +248,12 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
         if (flag) return;
     }
 
-    // ---- ORTHO: warp-level Cholesky.  Lane i keeps row i of the scaled S in registers; pivots and columns travel
-    // by shuffle, so the 32 x 32 factorisation and the triangular inverse cost ~1000 shuffles instead of ~100 CTA
-    // barriers.
+    // ---- ORTHO: one warp factors the scaled 32 x 32 matrix in shared memory (lane = row, row stride 33 keeps
+    // the lanes on distinct banks, pivot-column reads are broadcasts).  Compact loops on purpose: a fully unrolled
+    // register version is ~10k straight-line instructions that run once and stall on instruction fetch.
     static_assert(B == 32, "the warp-level factorisation maps one matrix row to one lane");
+    __shared__ double L[B][B + 1];
+    __shared__ double Li[B][B + 1];
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
 #pragma unroll 8
@@ -258,40 +263,43 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
     __syncthreads();
     if (tid < B) dscale[tid] = W[tid][tid] > 0.0 ? rsqrt(W[tid][tid]) : 1.0;
     __syncthreads();
+    for (int e = tid; e < B * B; e += nt) {
+        const int i = e / B, j = e % B;
+        L[i][j] = 0.5 * (W[i][j] + W[j][i]) * dscale[i] * dscale[j];
+        Li[i][j] = 0.0;
+    }
+    __syncthreads();
     if (tid >= 32) return;
     const int lane = tid;
-    double a[B], x[B];
-#pragma unroll
-    for (int c = 0; c < B; ++c) a[c] = 0.5 * (W[lane][c] + W[c][lane]) * dscale[lane] * dscale[c];
     int bad = 0;
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, a[j], j);
-        double d = sqrt(djj);
-        if (!(djj > 1e-30)) { bad = j + 1; d = 1.0; }
-        const double lij = lane > j ? a[j] / d : (lane == j ? d : 0.0);
-        a[j] = lij;
-#pragma unroll
+    for (int j = 0; j < B; ++j) {                       // right-looking Cholesky on the lower triangle
+        const double djj = L[j][j];
+        double rd = rsqrt(djj);
+        if (!(djj > 1e-30)) { bad = j + 1; rd = 1.0; }
+        __syncwarp();
+        const double lij = lane > j ? L[lane][j] * rd : (lane == j ? djj * rd : 0.0);
+        if (lane >= j) L[lane][j] = lij;
+        __syncwarp();
+#pragma unroll 4
         for (int c = j + 1; c < B; ++c) {
-            const double lcj = __shfl_sync(0xffffffffu, lij, c);
-            if (lane >= c) a[c] = fma(-lij, lcj, a[c]);
+            const double lcj = L[c][j];                 // broadcast
+            if (lane >= c) L[lane][c] = fma(-lij, lcj, L[lane][c]);
         }
+        __syncwarp();
     }
-    // x[i] = Linv[i][lane]: forward substitution, row i of L broadcast from lane i
-#pragma unroll
+    // Li = L^-1: lane owns column `lane`; row i of L is read as a broadcast-free strided load (stride 33)
     for (int i = 0; i < B; ++i) {
         double s = lane == i ? 1.0 : 0.0;
-#pragma unroll
+#pragma unroll 4
         for (int q = 0; q < i; ++q) {
-            const double liq = __shfl_sync(0xffffffffu, a[q], i);
-            if (q >= lane) s = fma(-liq, x[q], s);
+            const double liq = L[i][q];                 // broadcast
+            if (q >= lane) s = fma(-liq, Li[q][lane], s);
         }
-        const double lii = __shfl_sync(0xffffffffu, a[i], i);
-        x[i] = lane <= i ? s / lii : 0.0;
+        if (lane <= i) Li[i][lane] = s / L[i][i];
+        __syncwarp();
     }
     const double dl = dscale[lane];
-#pragma unroll
-    for (int bcol = 0; bcol < B; ++bcol) M[lane * B + bcol] = dl * x[bcol];      // M[a][b] = D[a] Linv[b][a], 0 for a > b
+    for (int bcol = 0; bcol < B; ++bcol) M[lane * B + bcol] = lane <= bcol ? dl * Li[bcol][lane] : 0.0;   // M = D L^-T
     if (bad && lane == 0) state[2] = bad;
 }
 

@@ -1015,6 +1015,10 @@ int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_ou
             *value_out = probe_copy_gbs((size_t)std::max(size, 64) << 20, s.stream);
         } else if (which == 2) {
             *value_out = probe_dmma_tflops(h->n_sms, s.stream);
+        } else if (which == 4) {
+            double r[8];
+            probe_copy_variants(r, s.stream);
+            *value_out = r[std::min(std::max(size, 0), 7)];
         } else if (which == 3) {
             *value_out = probe_host_gather_ms(11000, 20000, std::max(size, 1), s.stream);
         } else if (which == 1) {

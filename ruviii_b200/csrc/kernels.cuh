@@ -120,5 +120,6 @@ void launch_update_tma(const void* tmap_host, int rows, int n, const double* At_
 float probe_copy_gbs(size_t bytes, cudaStream_t s);
 float probe_dmma_tflops(int n_sms, cudaStream_t s);
 float probe_host_gather_ms(int rows, int n, int n_idx, cudaStream_t s);
+void probe_copy_variants(double* results8, cudaStream_t s);
 
 }  // namespace ruviii

@@ -26,7 +26,8 @@ except Exception as e:
     print("   no result:", e)
 PY
 }
-for v in ${VARIANTS:-"gram128:RUVIII_GRAM_IMPL=4 gramtma:RUVIII_GRAM_IMPL=2 updtma:RUVIII_UPD_IMPL=2 updrows64:RUVIII_UPD_ROWS=64 updrows256:RUVIII_UPD_ROWS=256 updrows1024:RUVIII_UPD_ROWS=1024"}; do
+VARIANTS=${VARIANTS:-gramtma:RUVIII_GRAM_IMPL=2 updtma:RUVIII_UPD_IMPL=2 updrows64:RUVIII_UPD_ROWS=64 updrows256:RUVIII_UPD_ROWS=256}
+for v in $VARIANTS; do
   variant ${v%%:*} ${v#*:}
 done
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
