@@ -54,7 +54,7 @@ typedef struct ruviii_params {
     int32_t struct_size;     /* sizeof(ruviii_params), for forward compatibility                              */
     int32_t mode;            /* RUVIII_MODE_*                                                                  */
     int32_t apply_log;       /* ruvIII.R:88-92: log2(assay + pseudo_count) on the assay rows (not on PS)       */
-    int32_t average_rep;     /* ruvIII.R:148-149 (apply.average.rep); 0 = off (default)                        */
+    int32_t average_rep;     /* ruvIII.R:148-149 (apply.average.rep); 0 = off (default); see ruviii_download_averaged */
     double  pseudo_count;    /* ruvIII.R:42                                                                    */
     int32_t n_alpha_rows;    /* rows of fullalpha to produce: 0 = max(ks) (all the update needs);              *
                               * -1 = r = min(m - ncol(M), sum(ctl)) as ruvIII.R:140 keeps (return.info = TRUE)  */
@@ -140,6 +140,9 @@ int ruviii_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* 
 int ruviii_run(ruviii_handle* h, ruviii_info* info);
 int ruviii_download(ruviii_handle* h, double* newY_out, double* newY_ps_out,
                     double* fullalpha_out, double* W_out);
+/* apply.average.rep (ruvIII.R:148-149): nk blocks of p x n (row stride n), row g = mean of the rows of newY in
+ * replicate group g, groups in ascending id order (= factor level order when ids are as.integer(factor(names))). */
+int ruviii_download_averaged(ruviii_handle* h, double* averaged_out);
 /* Small replicated results of the last run: eigenvalues (descending, `count` of them are written). */
 int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count);
 

@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     lib.ruviii_upload.argtypes = [H, vp, C.c_int64, vp, C.c_int64]
     lib.ruviii_run.argtypes = [H, C.POINTER(Info)]
     lib.ruviii_download.argtypes = [H, vp, vp, vp, vp]
+    lib.ruviii_download_averaged.argtypes = [H, vp]
     lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
@@ -205,6 +206,12 @@ class Engine:
         self._check(self._lib.ruviii_eigenvalues(self._h, _ptr(out), count))
         return out
 
+    def download_averaged(self):
+        pl, info = self._plan, self._info
+        out = np.empty((len(pl["ks"]), info.p, pl["n"]), dtype=np.float64)
+        self._check(self._lib.ruviii_download_averaged(self._h, _ptr(out)))
+        return out
+
     def download(self, want_fullalpha=False, want_W=False, want_ps=False, out=None):
         pl, info = self._plan, self._info
         nk = len(pl["ks"])
@@ -251,7 +258,10 @@ class Engine:
         self.plan(params, m1, n, n_ps, group_of_row, ctl_u8, ks_arr)
         self.upload(Y, PS)
         self.run()
-        return self.download(want_fullalpha=want_fullalpha, want_W=want_W, want_ps=want_ps, out=out)
+        res = self.download(want_fullalpha=want_fullalpha, want_W=want_W, want_ps=want_ps, out=out)
+        if params.average_rep:
+            res["averaged"] = self.download_averaged()
+        return res
 
     def normalise_oneshot(self, params, Y, PS, group_of_row, ctl, ks, out):
         """The literal one-call C entry point (newY only); used by bench.py's end-to-end leg."""

@@ -61,9 +61,10 @@ def set_engine(engine):
 
 
 def group_codes(names):
-    """factor(names) codes: equal names <=> equal code (what replicate.matrix() is built from, ruvIII.R:101)."""
-    seen = {}
-    return np.fromiter((seen.setdefault(s, len(seen)) for s in names), dtype=np.int32, count=len(names))
+    """as.integer(factor(names)) - 1: equal names <=> equal code, codes in sorted level order -- the column order of
+    replicate.matrix() (ruvIII.R:101), which is also the row order of the apply.average.rep result (ruvIII.R:149)."""
+    _, inv = np.unique(np.asarray(list(names), dtype=object).astype(str), return_inverse=True)
+    return inv.astype(np.int32)
 
 
 def _tological(ctl, n):
@@ -132,6 +133,8 @@ def _core(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, ctl
         eng.run()
         res = eng.download(want_fullalpha=False, want_W=return_info, want_ps=want_ps)
         res["fullalpha"] = np.asarray(fullalpha, dtype=np.float64)
+        if apply_average_rep:
+            res["averaged"] = eng.download_averaged()
     return res, m1, n
 
 
@@ -166,11 +169,14 @@ def _single(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, c
     if return_info and undefined:
         raise RuntimeError("object 'W' not found: ncol(M) >= m, no replicates (ruvIII.R:128-129 with return.info)")
     if save_se_obj:
-        new_name = _save(se_obj, assay_name, int(k), res["newY"][0], return_info, W, fa)
+        block = res["averaged"][0][:m1] if apply_average_rep else res["newY"][0]     # t(newY[1:ncol(expr.data), ])
+        new_name = _save(se_obj, assay_name, int(k), block, return_info, W, fa)
         _printColoredMessage("The normalized data %s is saved into a new assay of the SummarizedExperiment object."
                              % new_name, verbose)
         return se_obj
     newY = res["newY"][0] if res["newY_ps"] is None else np.vstack([res["newY"][0], res["newY_ps"][0]])
+    if apply_average_rep:
+        newY = res["averaged"][0]                                                    # ruvIII.R:148-149: p rows
     if not return_info:
         return newY.T                                                                # ruvIII.R:191-192  t(newY)
     return dict(newY=newY, fullalpha=fa, W=W)                                        # ruvIII.R:193-197
@@ -215,17 +221,20 @@ def ruvIIIMultipleK(se_obj, assay_name, apply_log=True, pseudo_count=1, replicat
     Ws = res["W"] if res["W"] is not None else [None] * len(ks)
     if save_se_obj:                                                                  # :74-98
         for i, kv in enumerate(ks):
-            _save(se_obj, assay_name, kv, res["newY"][i], return_info, Ws[i], res["fullalpha"])
+            block = res["averaged"][i][:m1] if apply_average_rep else res["newY"][i]
+            _save(se_obj, assay_name, kv, block, return_info, Ws[i], res["fullalpha"])
         _printColoredMessage("------------The ruvIIIMultipleK function finished:", verbose)
         return se_obj
     if not return_info:                                                              # :101-154
         out = {}
         for i, kv in enumerate(ks):
             label = ("RUVIII_K:%d_Data:%s" if i == 0 else "RUV_K%d_Data:%s") % (kv, assay_name)   # :121,146
-            out[label] = np.vstack([res["newY"][i], res["newY_ps"][i]]).T
+            out[label] = (res["averaged"][i] if apply_average_rep else np.vstack([res["newY"][i], res["newY_ps"][i]])).T
         return out
     out = []                                                                         # :157-185
     for i, kv in enumerate(ks):
         newY = res["newY"][i] if res["newY_ps"] is None else np.vstack([res["newY"][i], res["newY_ps"][i]])
+        if apply_average_rep:
+            newY = res["averaged"][i]
         out.append(dict(newY=newY, fullalpha=res["fullalpha"], W=Ws[i]))
     return out

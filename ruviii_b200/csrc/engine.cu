@@ -128,9 +128,9 @@ struct Shard {
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
-        evals_asc, falpha, topk_buf;
+        evals_asc, falpha, topk_buf, Zt, avg;
     DevBuf<int2> tile_map;
-    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state;
+    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows;
     TopkWork topk{};
     alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
     alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
@@ -179,6 +179,8 @@ struct ruviii_handle {
     int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
     int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
     bool use_topk = false;
+    bool gene_side = false;             // Gram = Z'Z (n x n) instead of Z Z' (R x R): taken when R > n
+    int gorder = 0;                     // order of the Gram that is formed and decomposed
     double eig_tol = 1e-13;
 
     ~ruviii_handle();
@@ -194,7 +196,7 @@ ruviii_handle::~ruviii_handle() {
         for (auto e : s.ev) cudaEventDestroy(e);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha, &s.topk_buf};
+                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -202,6 +204,8 @@ ruviii_handle::~ruviii_handle() {
         s.grp_rows.release();
         s.status.release();
         s.topk_state.release();
+        s.all_start.release();
+        s.all_rows.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     }
@@ -279,8 +283,9 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         throw Error(RUVIII_ERR_INVALID, "ruviii_plan: null or non-positive argument");
     if (prm->mode != RUVIII_MODE_STACKED && prm->mode != RUVIII_MODE_FAST)
         throw Error(RUVIII_ERR_INVALID, "ruviii_plan: unknown mode");
-    if (prm->average_rep)
-        throw Error(RUVIII_ERR_UNSUPPORTED, "apply.average.rep (ruvIII.R:148-149) is not implemented yet");
+    if (prm->average_rep && prm->mode == RUVIII_MODE_FAST && m1 != n_ps)
+        throw Error(RUVIII_ERR_INVALID, "apply.average.rep in fastruvIII multiplies t(M) (n_ps rows) with newY (m1 rows): "
+                                        "non-conformable arguments (fastruvIII.R:179-180)");
     if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
     h->prm = *prm;
     h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = false;
@@ -308,6 +313,13 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         for (int r : kv.second) grp_rows.push_back(r);
         grp_start.push_back((int)grp_rows.size());
         h->max_group = std::max(h->max_group, (int)kv.second.size());
+    }
+    std::vector<int> all_start{0}, all_rows;               // every group, id order = factor level order (K9)
+    if (prm->average_rep) {
+        for (auto& kv : groups) {
+            for (int r : kv.second) all_rows.push_back(fast ? r - row_offset : r);   // fast: row i of newY <-> PS row i
+            all_start.push_back((int)all_rows.size());
+        }
     }
     h->n_groups_active = (int)grp_start.size() - 1;
     h->active_rows = (int)grp_rows.size();
@@ -358,8 +370,16 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     h->n_keep = skip ? 0 : std::min(h->R, std::max(h->n_alpha_rows, h->kk + 1));   // one extra: the gap lambda_kk+1
     h->rows_w = fast ? m1 : h->m;
     h->mu_rows = fast ? m1 : h->m;                  // ruvIII.R:118 vs fastruvIII.R:136
-    if (!skip && h->R > 0 && prm->gram_side == 2)
-        throw Error(RUVIII_ERR_UNSUPPORTED, "gene-side Gram is not implemented yet");
+    // Gram side: Z Z' (R x R) or Z'Z (n x n), whichever is smaller unless forced
+    h->gene_side = !skip && (prm->gram_side == 2 || (prm->gram_side == 0 && h->R > n));
+    if (h->gene_side) {
+        if (h->world != 1) throw Error(RUVIII_ERR_UNSUPPORTED, "the gene-side Gram couples gene shards: one GPU only for now");
+        if (h->n_alpha_rows > h->kk)
+            throw Error(RUVIII_ERR_UNSUPPORTED, "gene-side Gram produces the leading max(k) rows of fullalpha only");
+        if (h->kk + 1 > n) throw Error(RUVIII_ERR_INVALID, "k exceeds the number of genes");
+    }
+    h->gorder = h->gene_side ? n : h->R;
+    if (!skip) h->n_keep = std::min(h->gorder, std::max(h->n_alpha_rows, h->kk + 1));
 
     // ---- output slots ----
     h->k_eff.resize(nk);
@@ -381,7 +401,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
 
     // ---- device buffers ----
     const int kp = h->kp, R = h->R;
-    const bool want_ps = prm->want_ps_rows && !fast && n_ps > 0;
+    const bool want_ps = (prm->want_ps_rows || prm->average_rep) && !fast && n_ps > 0;
     size_t w_total = 0;
     for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
     for (int i = 0; i < nsh; ++i) {
@@ -396,6 +416,14 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         s.out.alloc((size_t)nk * std::max(m1, 1) * s.ld, false);
         if (want_ps) s.out_ps.alloc((size_t)nk * n_ps * s.ld, false);
         s.status.alloc(4);
+        if (prm->average_rep) {
+            s.all_start.alloc(all_start.size());
+            s.all_rows.alloc(std::max<size_t>(all_rows.size(), 1));
+            RUVIII_CUDA_CHECK(cudaMemcpy(s.all_start.p, all_start.data(), all_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (!all_rows.empty())
+                RUVIII_CUDA_CHECK(cudaMemcpy(s.all_rows.p, all_rows.data(), all_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+            s.avg.alloc((size_t)nk * h->p * s.ld, false);
+        }
         if (!skip) {
             s.ctl_idx.alloc(std::max<size_t>(cidx.size(), 1));
             if (!cidx.empty())
@@ -406,17 +434,20 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (!grp_rows.empty())
                 RUVIII_CUDA_CHECK(cudaMemcpy(s.grp_rows.p, grp_rows.data(), grp_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
             s.Y0.alloc((size_t)R * s.ld);
-            s.gp = plan_gram(R, (int)s.ld, h->n_sms, h->gram_impl);
+            const int GO = h->gorder;
+            const int64_t ldR = round_up(R, kRowAlign);
+            if (h->gene_side) s.Zt.alloc((size_t)s.n * ldR);
+            s.gp = h->gene_side ? plan_gram(GO, (int)ldR, h->n_sms, h->gram_impl) : plan_gram(R, (int)s.ld, h->n_sms, h->gram_impl);
             s.gram_ws.alloc(s.gp.workspace_bytes / sizeof(double), false);
             std::vector<int2> tm(s.gp.n_tiles);
             fill_gram_tile_map(s.gp, tm.data());
             s.tile_map.alloc(tm.size());
             RUVIII_CUDA_CHECK(cudaMemcpy(s.tile_map.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            s.G.alloc((size_t)R * R);
-            s.evals_asc.alloc(R);
+            s.G.alloc((size_t)GO * GO);
+            s.evals_asc.alloc(GO);
             s.evals.alloc(std::max(h->n_keep, kp) + 2);
-            s.U.alloc((size_t)R * kp);
-            if (h->n_alpha_rows > h->kk) s.Vd.alloc((size_t)R * h->n_keep);
+            s.U.alloc((size_t)GO * kp);
+            if (h->n_alpha_rows > h->kk) s.Vd.alloc((size_t)GO * h->n_keep);
             s.rsplit = project_rsplit(R, s.n, h->n_sms);
             s.part.alloc((size_t)s.rsplit * kp * s.ld);
             s.alpha.alloc((size_t)kp * s.ld);
@@ -429,7 +460,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (h->n_alpha_rows > h->kk) s.falpha.alloc((size_t)h->n_alpha_rows * s.ld);
             s.W.alloc(std::max<size_t>(w_total, 1));
             if (s.gp.impl == 2) {
-                launch_gram_tma_prepare(s.gp, s.Y0.p, s.ld, s.tmap);
+                launch_gram_tma_prepare(s.gp, h->gene_side ? s.Zt.p : s.Y0.p, h->gene_side ? ldR : s.ld, s.tmap);
             }
             if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
@@ -437,32 +468,33 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     // ---- solver (global rank 0 only) ----
     h->use_topk = false;
     if (!skip && h->rank0 == 0 && R > 0) {
+        const int GO = h->gorder;
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         // block subspace iteration when only the leading kk rows of fullalpha are wanted and the block (32) leaves
         // room for oversampling; cuSOLVER otherwise and as the fallback
-        const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkBlock / 2 && R >= 4 * kTopkBlock &&
+        const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkBlock / 2 && GO >= 4 * kTopkBlock &&
                              h->rank_bound >= 2 * kTopkBlock;
         if (h->eig_impl == 3 && !topk_ok)
             throw Error(RUVIII_ERR_UNSUPPORTED, "RUVIII_EIG_IMPL=3 but the problem is outside the subspace-iteration range");
         h->use_topk = topk_ok && (h->eig_impl == 0 || h->eig_impl == 3);
         if (h->use_topk) {
-            s.topk_buf.alloc(topk_work_doubles(R, kTopkBlock), false);
+            s.topk_buf.alloc(topk_work_doubles(GO, kTopkBlock), false);
             s.topk_state.alloc(4);
-            topk_bind(s.topk, s.topk_buf.p, s.topk_state.p, R, kTopkBlock);
+            topk_bind(s.topk, s.topk_buf.p, s.topk_state.p, GO, kTopkBlock);
         }
         if (!h->solver) {
             RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
             RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
         }
         int lwork = 0, meig = 0;
-        if (h->eig_impl == 1 || h->n_keep >= R) {
-            RUVIII_SOLVER_CHECK(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, R,
-                                                            s.G.p, R, s.evals_asc.p, &lwork));
+        if (h->eig_impl == 1 || h->n_keep >= GO) {
+            RUVIII_SOLVER_CHECK(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, GO,
+                                                            s.G.p, GO, s.evals_asc.p, &lwork));
         } else {
             RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
-                                                             CUBLAS_FILL_MODE_UPPER, R, s.G.p, R, 0.0, 0.0,
-                                                             R - h->n_keep + 1, R, &meig, s.evals_asc.p, &lwork));
+                                                             CUBLAS_FILL_MODE_UPPER, GO, s.G.p, GO, 0.0, 0.0,
+                                                             GO - h->n_keep + 1, GO, &meig, s.evals_asc.p, &lwork));
         }
         h->solver_work.alloc((size_t)lwork, false);
         h->solver_info.alloc(4);
@@ -497,7 +529,7 @@ void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS,
 
 void eigensolve(ruviii_handle* h) {
     Shard& s = h->shards[0];
-    const int R = h->R;
+    const int R = h->gorder;            // order of the Gram being decomposed
     RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
     h->h_flags[0] = 0;
     h->eig_iterations = 0;
@@ -540,7 +572,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     const bool fast = h->prm.mode == RUVIII_MODE_FAST;
     const bool skip = h->no_replicates || h->kk == 0;
     const int kp = h->kp, kk = h->kk, R = h->R, nk = (int)h->ks.size();
-    const bool want_ps = h->prm.want_ps_rows && !fast && h->n_ps > 0;
+    const bool want_ps = (h->prm.want_ps_rows || h->prm.average_rep) && !fast && h->n_ps > 0;
     h->launches = 0;
     auto rec = [&](int e) {
         for (auto& s : h->shards) {
@@ -581,15 +613,22 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             });
             h->launches += 1;
             rec(E_RESIDOP);
+            const int GO = h->gorder;
             for_shards([&](Shard& s) {
-                launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+                if (h->gene_side) {
+                    const int64_t ldR = round_up(R, kRowAlign);
+                    launch_transpose(s.Y0.p, s.ld, R, s.n, s.Zt.p, ldR, s.stream);
+                    launch_gram(s.gp, s.Zt.p, ldR, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+                } else {
+                    launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+                }
             });
-            h->launches += 2;
+            h->launches += h->gene_side ? 3 : 2;
             rec(E_GRAM);
             {
                 std::vector<double*> b;
                 for (auto& s : h->shards) b.push_back(s.G.p);
-                allreduce_sum(h, b, (size_t)R * R);
+                allreduce_sum(h, b, (size_t)GO * GO);
             }
             rec(E_AR1);
             if (h->rank0 == 0) eigensolve(h);
@@ -597,20 +636,25 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             {
                 std::vector<double*> b;
                 for (auto& s : h->shards) b.push_back(s.U.p);
-                broadcast0(h, b, (size_t)R * kp);
+                broadcast0(h, b, (size_t)GO * kp);
                 b.clear();
                 for (auto& s : h->shards) b.push_back(s.evals.p);
                 broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
                 if (h->n_alpha_rows > kk) {
                     b.clear();
                     for (auto& s : h->shards) b.push_back(s.Vd.p);
-                    broadcast0(h, b, (size_t)R * h->n_keep);
+                    broadcast0(h, b, (size_t)GO * h->n_keep);
                 }
             }
             rec(E_BCAST);
             for_shards([&](Shard& s) {
-                launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
-                launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+                if (h->gene_side) {
+                    launch_alpha_from_v(s.U.p, s.evals.p, s.n, kk, kp, s.ld, s.alpha.p, s.stream);
+                    launch_alpha_finalize(s.alpha.p, 1, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+                } else {
+                    launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
+                    launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+                }
             });
             h->launches += 3;
             if (h->n_alpha_rows > kk) {
@@ -660,7 +704,10 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         rec(E_SOLVE);
         for_shards([&](Shard& s) {
             const int64_t stride = (int64_t)h->m1 * s.ld;
-            if (h->upd_impl == 2)
+            if (h->upd_impl == 3)
+                launch_update_smem(s.Y.p, s.ld, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
+                                   stride, s.stream);
+            else if (h->upd_impl == 2)
                 launch_update_tma(s.tmap_y, h->m1, s.n, s.At.p, kp, s.at.p, s.ld, kk, h->kmask, h->slot_of_k, s.out.p, s.ld,
                                   stride, s.stream);
             else
@@ -691,6 +738,16 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[1 + i], s.status.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
     }
+    if (h->prm.average_rep) {                               // ruvIII.R:148-149, after either branch
+        for_shards([&](Shard& s) {
+            for (int i = 0; i < nk; ++i) {
+                RowSrc src{s.out.p + (size_t)i * h->m1 * s.ld, s.ld,
+                           want_ps ? s.out_ps.p + (size_t)i * h->n_ps * s.ld : nullptr, s.ld, h->m1};
+                launch_group_mean(src, s.all_start.p, s.all_rows.p, h->p, s.n, s.avg.p + (size_t)i * h->p * s.ld, s.ld, s.stream);
+            }
+        });
+        h->launches += nk;
+    }
     sync_all(h);
     if (!skip) {
         if (h->rank0 == 0 && !h->have_user_alpha && h->h_flags[0] != 0)
@@ -708,8 +765,8 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     I.struct_size = sizeof(ruviii_info);
     I.ms_h2d = keep_h2d;
     I.ms_d2h = keep_d2h;
-    I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->active_rows; I.r = h->r; I.gram_order = h->R;
-    I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = 1;
+    I.m = h->m; I.m1 = h->m1; I.n_ps = h->n_ps; I.n = h->n_local_total; I.p = h->p; I.active_rows = h->active_rows; I.r = h->r; I.gram_order = h->gorder;
+    I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = h->gene_side ? 2 : 1;
     I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
     I.eig_solver = (skip || h->have_user_alpha) ? 0 : h->eig_solver_used; I.eig_iterations = h->eig_iterations;
     {
@@ -907,6 +964,23 @@ int ruviii_run(ruviii_handle* h, ruviii_info* info) {
 int ruviii_download(ruviii_handle* h, double* newY_out, double* newY_ps_out, double* fullalpha_out, double* W_out) {
     if (!h) return RUVIII_ERR_INVALID;
     return guarded(h, [&] { do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out); });
+}
+
+int ruviii_download_averaged(ruviii_handle* h, double* out) {
+    if (!h || !out) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->ran) throw Error(RUVIII_ERR_STATE, "ruviii_download_averaged before ruviii_run");
+        if (!h->prm.average_rep) throw Error(RUVIII_ERR_STATE, "the plan was made without average_rep");
+        const int nk = (int)h->ks.size();
+        const int64_t n = h->n_local_total;
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            for (int i = 0; i < nk; ++i)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(out + (size_t)i * h->p * n + s.g0, n * 8, s.avg.p + (size_t)i * h->p * s.ld,
+                                                    s.ld * 8, (size_t)s.n * 8, h->p, cudaMemcpyDeviceToHost, s.stream));
+        }
+        sync_all(h);
+    });
 }
 
 int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count) {

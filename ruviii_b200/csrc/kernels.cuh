@@ -36,6 +36,15 @@ void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n
 void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int n, double* Z,
                     int64_t ldZ, cudaStream_t s);
 
+// K9  ruvIII.R:148-149  apply.average.rep: out[g, ] = mean of the rows of newY in replicate group g (all p groups).
+void launch_group_mean(RowSrc src, const int* all_start, const int* all_rows, int n_groups, int n, double* out, int64_t ld,
+                       cudaStream_t s);
+
+// Transpose (gene-side Gram: t(Z) with the rows of Z contiguous) and alpha = diag(sigma) V' (appendix A-5).
+void launch_transpose(const double* in, int64_t ld_in, int rows, int cols, double* out, int64_t ld_out, cudaStream_t s);
+void launch_alpha_from_v(const double* V_rowmajor, const double* evals, int n, int kk, int kp, int64_t ld, double* alpha,
+                         cudaStream_t s);
+
 // K2  ruvIII.R:140  Y0 %*% t(Y0): symmetric FP64 Gram on DMMA, split over the contraction (genes).
 struct GramPlan {
     int R = 0, K = 0;            // order of the Gram, contraction length (padded to kRowAlign)
@@ -110,6 +119,10 @@ void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const doub
                    const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k,
                    double* out, int64_t ldout, int64_t out_stride, cudaStream_t s);
 
+// K6 impl 3 (update.cu): a~ in shared memory, ~64 registers, 8 CTAs per SM, software-pipelined row loads.
+void launch_update_smem(const double* Yrows, int64_t ldY, int rows, int n, const double* At_rows, int kp,
+                        const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k,
+                        double* out, int64_t ldout, int64_t out_stride, cudaStream_t s);
 // K6 impl 2 (update_tma.cu): same update, Y staged through a TMA + mbarrier shared-memory ring.
 void update_tma_prepare(const double* Y, int64_t ldY, int rows, void* desc_out_host128);
 void launch_update_tma(const void* tmap_host, int rows, int n, const double* At_rows, int kp, const double* at,

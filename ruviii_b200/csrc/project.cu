@@ -117,6 +117,19 @@ alpha_finalize_kernel(const double* __restrict__ part, int rsplit, int kp, int64
     alpha[(int64_t)j * ld + g] = s;
 }
 
+// Gene-side route: with Z'Z = V diag(lambda) V' the left vectors are U = Z V / sigma, so
+// fullalpha = t(U) %*% Z = diag(sigma) V':  alpha[j][g] = sqrt(lambda_j) V[g][j].  V is row-major n x kp.
+__global__ void __launch_bounds__(256)
+alpha_from_v_kernel(const double* __restrict__ V, const double* __restrict__ evals, int n, int kk, int kp, int64_t ld,
+                    double* __restrict__ alpha) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (g >= ld) return;
+    double v = 0.0;
+    if (j < kk && g < n) v = sqrt(fmax(evals[j], 0.0)) * V[g * kp + j];
+    alpha[(int64_t)j * ld + g] = v;
+}
+
 __global__ void __launch_bounds__(256)
 gather_ac_kernel(const double* __restrict__ alpha, int64_t ld, int kp, const int* __restrict__ ctl_idx,
                  int n_ctl, double* __restrict__ acT) {
@@ -355,6 +368,13 @@ void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_
         gather_ac_kernel<<<ceil_div((int64_t)n_ctl * kp, 256), 256, 0, s>>>(alpha, ld, kp, ctl_idx, n_ctl, acT);
         RUVIII_LAUNCH_CHECK();
     }
+}
+
+void launch_alpha_from_v(const double* V, const double* evals, int n, int kk, int kp, int64_t ld, double* alpha,
+                         cudaStream_t s) {
+    dim3 grid(ceil_div(ld, 256), kp);
+    alpha_from_v_kernel<<<grid, 256, 0, s>>>(V, evals, n, kk, kp, ld, alpha);
+    RUVIII_LAUNCH_CHECK();
 }
 
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,

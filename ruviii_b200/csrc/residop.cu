@@ -102,6 +102,42 @@ helmert_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restr
     }
 }
 
+// K9  ruvIII.R:148-149  newY <- ((1 / colSums(M)) * t(M)) %*% newY: one output row per replicate group (every
+// column of M, singletons included), the mean of the group's rows of newY.  all_start/all_rows: CSR over ALL groups.
+__global__ void __launch_bounds__(kResidopThreads)
+group_mean_kernel(RowSrc src, const int* __restrict__ all_start, const int* __restrict__ all_rows, int n_groups,
+                  int n_pairs, double* __restrict__ out, int64_t ld) {
+    const int pair = blockIdx.x * kResidopThreads + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const int64_t col = 2 * (int64_t)pair;
+    for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        const int s = all_start[g], e = all_start[g + 1];
+        double2 sum = make_double2(0.0, 0.0);
+        for (int t = s; t < e; ++t) {
+            const double2 v = *reinterpret_cast<const double2*>(src.row(all_rows[t]) + col);
+            sum.x += v.x;
+            sum.y += v.y;
+        }
+        const double inv = 1.0 / (double)(e - s);
+        st_stream(out + (int64_t)g * ld + col, make_double2(sum.x * inv, sum.y * inv));
+    }
+}
+
+// out (cols x ld_out, row-major) = in' for in (rows x ld_in, row-major): 32 x 32 tiles through padded shared memory,
+// coalesced on both sides.  Used by the gene-side Gram, whose contraction runs over the rows of Z.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ in, int64_t ld_in, int rows, int cols, double* __restrict__ out,
+                 int64_t ld_out) {
+    __shared__ double t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        t[i][tx] = (r0 + i < rows && c0 + tx < cols) ? in[(int64_t)(r0 + i) * ld_in + c0 + tx] : 0.0;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) out[(int64_t)(c0 + i) * ld_out + r0 + tx] = t[tx][i];
+}
+
 __global__ void __launch_bounds__(256)
 log2_kernel(double* __restrict__ Y, int64_t ld, int rows, int n, double pc) {
     const int64_t total = (int64_t)rows * n;
@@ -129,6 +165,22 @@ void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n
     const int n_pairs = (n + 1) / 2;          // pitches are even and zero padded, so the odd tail pair is safe
     dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
     residop_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Y0, ldY0);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_group_mean(RowSrc src, const int* all_start, const int* all_rows, int n_groups, int n, double* out, int64_t ld,
+                       cudaStream_t s) {
+    if (n_groups <= 0 || n <= 0) return;
+    const int n_pairs = (n + 1) / 2;
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    group_mean_kernel<<<grid, kResidopThreads, 0, s>>>(src, all_start, all_rows, n_groups, n_pairs, out, ld);
+    RUVIII_LAUNCH_CHECK();
+}
+
+void launch_transpose(const double* in, int64_t ld_in, int rows, int cols, double* out, int64_t ld_out, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+    transpose_kernel<<<grid, 256, 0, s>>>(in, ld_in, rows, cols, out, ld_out);
     RUVIII_LAUNCH_CHECK();
 }
 

@@ -109,6 +109,71 @@ update_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, 
     }
 }
 
+// K6 impl 3: a~ lives in shared memory instead of registers.  The register version above needs 2 x kp doubles per
+// thread for a~ (128 registers at kp = 16 -> 4 CTAs = 16 warps per SM), and with so few warps the load, FP64 and
+// store phases of a warp barely overlap (ncu: 57 % DRAM, long-scoreboard stalls) although a plain copy with the same
+// tiling reaches the copy peak.  Here a~ (kk x 128 double2) and the A~ rows sit in shared memory, a thread needs ~64
+// registers (8 CTAs = 32 warps per SM), the next four rows are loaded before the current four are touched, and one
+// kernel serves every k <= 32 (runtime loop over q, no register arrays).
+__global__ void __launch_bounds__(kUpdThreads, 8)
+update_smem_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, const double* __restrict__ At, int kp,
+                   const double* __restrict__ at, int64_t ldat, int kk, uint64_t kmask, KSlots slots,
+                   double* __restrict__ out, int64_t ldout, int64_t out_stride) {
+    extern __shared__ __align__(16) unsigned char upd_smem[];
+    double2* sA = reinterpret_cast<double2*>(upd_smem);                       // [kk][128]
+    double* sAt = reinterpret_cast<double*>(upd_smem + (size_t)kk * kUpdThreads * 16);   // [kUpdRows][kk]
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.x * kUpdThreads + tid;
+    const bool active = pair < n_pairs;
+    const int64_t col = 2 * (int64_t)pair;
+    const int row0 = blockIdx.y * kUpdRows;
+    const int nrows = min(kUpdRows, rows - row0);
+    for (int q = 0; q < kk; ++q)
+        sA[q * kUpdThreads + tid] = active ? *reinterpret_cast<const double2*>(at + (int64_t)q * ldat + col) : make_double2(0.0, 0.0);
+    for (int e = tid; e < kUpdRows * kk; e += kUpdThreads) {
+        const int r = e / kk, q = e - r * kk;
+        sAt[e] = r < nrows ? At[(int64_t)(row0 + r) * kp + q] : 0.0;
+    }
+    __syncthreads();
+    if (!active) return;
+    const bool want0 = kmask & 1ull;
+    const double* yp = Y + (int64_t)row0 * ldY + col;
+    double2 nxt[kUpdUnroll];
+#pragma unroll
+    for (int u = 0; u < kUpdUnroll; ++u) nxt[u] = u < nrows ? ld_stream(yp + (int64_t)u * ldY) : make_double2(0.0, 0.0);
+    for (int rb = 0; rb < nrows; rb += kUpdUnroll) {
+        double2 y[kUpdUnroll];
+#pragma unroll
+        for (int u = 0; u < kUpdUnroll; ++u) y[u] = nxt[u];
+#pragma unroll
+        for (int u = 0; u < kUpdUnroll; ++u)                                  // next four rows are in flight during the math
+            nxt[u] = (rb + kUpdUnroll + u < nrows) ? ld_stream(yp + (int64_t)(rb + kUpdUnroll + u) * ldY) : make_double2(0.0, 0.0);
+        if (want0) {
+            double* o = out + (int64_t)slots.slot[0] * out_stride + col;
+#pragma unroll
+            for (int u = 0; u < kUpdUnroll; ++u)
+                if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+        }
+        const double* w = sAt + rb * kk;
+#pragma unroll 2
+        for (int q = 0; q < kk; ++q) {
+            const double2 a = sA[q * kUpdThreads + tid];
+#pragma unroll
+            for (int u = 0; u < kUpdUnroll; ++u) {
+                const double wq = w[u * kk + q];                               // rows beyond nrows are zero padded
+                y[u].x = fma(-wq, a.x, y[u].x);
+                y[u].y = fma(-wq, a.y, y[u].y);
+            }
+            if ((kmask >> (q + 1)) & 1ull) {
+                double* o = out + (int64_t)slots.slot[q + 1] * out_stride + col;
+#pragma unroll
+                for (int u = 0; u < kUpdUnroll; ++u)
+                    if (rb + u < nrows) st_stream(o + (int64_t)(row0 + rb + u) * ldout, y[u]);
+            }
+        }
+    }
+}
+
 // ---- micro-benchmarks -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ a, double2* __restrict__ b, size_t n2) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
@@ -135,6 +200,21 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 
 }  // namespace
 
+void launch_update_smem(const double* Yrows, int64_t ldY, int rows, int n, const double* At_rows, int kp,
+                        const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k, double* out,
+                        int64_t ldout, int64_t out_stride, cudaStream_t s) {
+    if (rows <= 0 || n <= 0) return;
+    KSlots slots;
+    for (int i = 0; i <= kMaxK; ++i) slots.slot[i] = (signed char)out_slot_of_k[i];
+    const int n_pairs = (n + 1) / 2;
+    const size_t smem = (size_t)std::max(kk, 1) * (kUpdThreads * 16 + kUpdRows * 8);
+    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(n_pairs, kUpdThreads), ceil_div(rows, kUpdRows));
+    update_smem_kernel<<<grid, kUpdThreads, smem, s>>>(Yrows, ldY, rows, n_pairs, At_rows, kp, at, ldat, kk, kmask, slots, out,
+                                                       ldout, out_stride);
+    RUVIII_LAUNCH_CHECK();
+}
+
 void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const double* At_rows, int kp,
                    const double* at, int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k, double* out,
                    int64_t ldout, int64_t out_stride, cudaStream_t s) {
@@ -142,13 +222,11 @@ void launch_update(const double* Yrows, int64_t ldY, int rows, int n, const doub
     KSlots slots;
     for (int i = 0; i <= kMaxK; ++i) slots.slot[i] = (signed char)out_slot_of_k[i];
     const int n_pairs = (n + 1) / 2;
-    // rows per CTA: by default one wave of CTAs covers the matrix (every resident CTA streams one long column
-    // strip, all strips of a row block advance together, so DRAM sees whole rows); RUVIII_UPD_ROWS overrides.
+    // rows per CTA: 64.  Long column strips (one wave of persistent CTAs) were measured slower (r01e: 0.774 vs 0.730 ms
+    // at C3; a pure copy with 1,600-row strips drops from 6.4 to 4.8 TB/s); RUVIII_UPD_ROWS overrides for experiments.
     const int col_tiles = ceil_div(n_pairs, kUpdThreads);
     static const int env_rows = [] { const char* v = std::getenv("RUVIII_UPD_ROWS"); return v && *v ? std::atoi(v) : 0; }();
-    const int ctas_per_sm = kp <= 8 ? 6 : kp <= 16 ? 4 : 2;
-    int row_chunks = std::max(1, (148 * ctas_per_sm) / col_tiles);
-    int rows_per_cta = (int)round_up(ceil_div(rows, row_chunks), kUpdRows);
+    int rows_per_cta = kUpdRows;
     if (env_rows > 0) rows_per_cta = (int)round_up(env_rows, kUpdRows);
     dim3 grid(col_tiles, ceil_div(rows, rows_per_cta));
 #define RUVIII_UPD(KP)                                                                                         \

@@ -26,19 +26,20 @@ except Exception as e:
     print("   no result:", e)
 PY
 }
-VARIANTS=${VARIANTS:-gramtma:RUVIII_GRAM_IMPL=2 updtma:RUVIII_UPD_IMPL=2 updrows64:RUVIII_UPD_ROWS=64 updrows256:RUVIII_UPD_ROWS=256}
+VARIANTS=${VARIANTS:-gramtma:RUVIII_GRAM_IMPL=2 updtma:RUVIII_UPD_IMPL=2 updsmem:RUVIII_UPD_IMPL=3}
 for v in $VARIANTS; do
   variant ${v%%:*} ${v#*:}
 done
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 cat $OUT/bench_ref.json
 # launch list + full capture of our kernels (only after the same command exited 0 without ncu)
-echo "ncu with RUVIII_GRAM_IMPL=$RUVIII_GRAM_IMPL RUVIII_UPD_IMPL=$RUVIII_UPD_IMPL" > $OUT/ncu_env.txt
+for kv in $NCU_ENV; do export $kv; done
+echo "ncu with NCU_ENV=$NCU_ENV" > $OUT/ncu_env.txt
 CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 timeout 300 $CMD > $OUT/plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
 timeout 300 $CMD > $OUT/plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"${NCU_KERNELS:-update_kernel|update_tma_kernel|gram_dmma_kernel|gram_tma_kernel|helmert_kernel|project_kernel|ctl_products}" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-6} \
+    -k regex:"${NCU_KERNELS:-update_kernel|update_tma_kernel|update_smem_kernel|gram_dmma_kernel|gram_tma_kernel|helmert_kernel|project_kernel|ctl_products}" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-6} \
     -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
 ls -la $OUT

@@ -197,6 +197,43 @@ def test_dense_design_sample_side(engine):
     check_against(res, 0, ref, 4, 300, stacked=False)
 
 
+def test_gene_side_gram(engine):
+    """More non-singleton rows than genes (BASELINE config 5's regime at small scale): the engine decomposes
+    t(Z) %*% Z (genes x genes) and takes alpha = diag(sigma) V' (SURVEY.md appendix A-5)."""
+    Y, gid, ctl = make_dense_design(m=600, n=150, group_size=3, n_ctl=60, k=4, seed=17)
+    res = engine.normalise(_cabi.make_params(), Y, np.zeros((0, 150)), gid, ctl, [2, 4], want_fullalpha=True, want_W=True)
+    assert res["info"].gram_side == 2 and res["info"].gram_order == 150 and res["info"].active_rows == 600
+    names = ["g%d" % g for g in gid]
+    for i, k in enumerate([2, 4]):
+        ref = O.ruvIII_literal(Y.T, names, np.zeros((0, 150)), [], ctl, k, apply_log=False)
+        check_against(res, i, ref, k, 600, stacked=False)
+    # forcing the gene side on an ordinary PRPS problem gives the sample-side answer
+    p = make_problem(m1=120, n=900, groups=40, rep=3, n_ctl=80, k=5, seed=18)
+    groups = api.group_codes(p.sample_names + p.replicate_names)
+    a = engine.normalise(_cabi.make_params(gram_side=1), p.Y, p.replicate_data, groups, p.ctl, [5])
+    b = engine.normalise(_cabi.make_params(gram_side=2), p.Y, p.replicate_data, groups, p.ctl, [5])
+    assert a["info"].gram_side == 1 and b["info"].gram_side == 2 and b["info"].gram_order == 900
+    assert O.rel_frob(b["newY"][0], a["newY"][0]) < 1e-10
+
+
+def test_apply_average_rep(engine):
+    """apply.average.rep = TRUE (ruvIII.R:148-149): one row per column of M, the mean of the group's rows of newY."""
+    p = make_problem(m1=50, n=260, groups=6, rep=3, n_ctl=35, k=3, seed=19)
+    names = list(p.sample_names)
+    names[7] = names[3]                                              # one pair of technical replicates among the samples
+    api.set_engine(engine)
+    se = rv.SummarizedExperiment(assays={"a": p.assay}, col_names=names)
+    rd = rv.ReplicateData(p.replicate_data, p.replicate_names)
+    out = rv.ruvIII(se, "a", apply_log=False, replicate_data=rd, ctl=p.ctl, k=3, apply_average_rep=True,
+                    return_info=True, save_se_obj=False, verbose=False)
+    ref = O.ruvIII_literal(p.assay, names, p.replicate_data, p.replicate_names, p.ctl, 3, apply_log=False,
+                           apply_average_rep=True)
+    assert out["newY"].shape == ref["newY"].shape == (49 + 6, 260)
+    assert O.rel_frob(out["newY"], ref["newY"]) < TOL_NEWY
+    with pytest.raises(rv.RuviiiError):                            # fastruvIII: t(M) (n_ps rows) x newY (m1 rows) does not conform
+        rv.fastruvIII(se, "a", apply_log=False, replicate_data=rd, ctl=p.ctl, k=3, apply_average_rep=True, verbose=False)
+
+
 def test_user_supplied_fullalpha(engine):
     """fullalpha argument skips residop / Gram / SVD (ruvIII.R:138)."""
     p = make_problem(m1=45, n=260, groups=6, rep=3, n_ctl=35, k=4, seed=10)
@@ -270,8 +307,9 @@ def test_gram_kernels_agree():
     assert np.allclose(outs[1][1][:6], S["eigenvalues"][:6], rtol=1e-11)
 
 
-@pytest.mark.parametrize("env", [{"RUVIII_GRAM_IMPL": "2"}, {"RUVIII_UPD_IMPL": "2"}],
-                         ids=["gram_tma", "update_tma"])
+@pytest.mark.parametrize("env", [{"RUVIII_GRAM_IMPL": "2"}, {"RUVIII_GRAM_IMPL": "4"}, {"RUVIII_UPD_IMPL": "2"},
+                                 {"RUVIII_UPD_IMPL": "3"}],
+                         ids=["gram_tma", "gram_128", "update_tma", "update_smem"])
 def test_tma_kernel_variants_match(env):
     """The TMA + mbarrier variants of the Gram and of the update give the same results as the default kernels:
     odd gene count, R = 258 (three tile rows, last one ragged), multi-k, k = 0 included."""
