@@ -287,7 +287,7 @@ def main():
     except Exception:
         pass
     up = kernels["update"]
-    roofline = {"kernel": "update_kernel (K6, ruvIII.R:145)", "bound": "hbm", "achieved": up["achieved"], "peak": hbm_peak,
+    roofline = {"kernel": "update_smem_kernel (K6, ruvIII.R:145)", "bound": "hbm", "achieved": up["achieved"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": up["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": upd_bytes,
                 "share_of_step": stage_ms["ms_update"] / max(stage_ms["ms_total"], 1e-9)}
@@ -321,7 +321,7 @@ def main():
                    "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(
                        info.eig_solver, "none"), "eig_iterations": info.eig_iterations,
                    "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1")), "gram_order": info.gram_order,
-                   "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "1"))},
+                   "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "3"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes,
     }

@@ -175,7 +175,7 @@ struct ruviii_handle {
     std::vector<std::pair<int, int>> dup_slots;   // (dst slot, src slot) for k values with the same effective k
     int launches = 0;
     ruviii_info info{};
-    int upd_impl = 1;
+    int upd_impl = 3;
     int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
     int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
     bool use_topk = false;
@@ -247,7 +247,7 @@ void finish_create(ruviii_handle* h) {
     std::memset(h->h_flags, 0, 64 * sizeof(int));
     h->gram_impl = env_int("RUVIII_GRAM_IMPL", 1);
     h->eig_impl = env_int("RUVIII_EIG_IMPL", 0);
-    h->upd_impl = env_int("RUVIII_UPD_IMPL", 1);
+    h->upd_impl = env_int("RUVIII_UPD_IMPL", 3);   // 1 a~ in registers, 2 TMA ring, 3 a~ in shared memory (default)
     if (const char* t = std::getenv("RUVIII_EIG_TOL")) h->eig_tol = std::atof(t);
 }
 

@@ -115,6 +115,7 @@ update_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, 
 // tiling reaches the copy peak.  Here a~ (kk x 128 double2) and the A~ rows sit in shared memory, a thread needs ~64
 // registers (8 CTAs = 32 warps per SM), the next four rows are loaded before the current four are touched, and one
 // kernel serves every k <= 32 (runtime loop over q, no register arrays).
+template <int PF>   // PF > 0: rows PF*4 .. PF*4+3 ahead are pulled into L2 with prefetch.global.L2 (costs no registers)
 __global__ void __launch_bounds__(kUpdThreads, 8)
 update_smem_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pairs, const double* __restrict__ At, int kp,
                    const double* __restrict__ at, int64_t ldat, int kk, uint64_t kmask, KSlots slots,
@@ -148,6 +149,12 @@ update_smem_kernel(const double* __restrict__ Y, int64_t ldY, int rows, int n_pa
 #pragma unroll
         for (int u = 0; u < kUpdUnroll; ++u)                                  // next four rows are in flight during the math
             nxt[u] = (rb + kUpdUnroll + u < nrows) ? ld_stream(yp + (int64_t)(rb + kUpdUnroll + u) * ldY) : make_double2(0.0, 0.0);
+        if (PF > 0) {
+#pragma unroll
+            for (int u = 0; u < kUpdUnroll; ++u)
+                if (rb + (PF + 1) * kUpdUnroll + u < nrows)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + (int64_t)(rb + (PF + 1) * kUpdUnroll + u) * ldY));
+        }
         if (want0) {
             double* o = out + (int64_t)slots.slot[0] * out_stride + col;
 #pragma unroll
@@ -208,10 +215,19 @@ void launch_update_smem(const double* Yrows, int64_t ldY, int rows, int n, const
     for (int i = 0; i <= kMaxK; ++i) slots.slot[i] = (signed char)out_slot_of_k[i];
     const int n_pairs = (n + 1) / 2;
     const size_t smem = (size_t)std::max(kk, 1) * (kUpdThreads * 16 + kUpdRows * 8);
-    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int pf = [] { const char* v = std::getenv("RUVIII_UPD_PREFETCH"); return v && *v ? std::atoi(v) : 2; }();
     dim3 grid(ceil_div(n_pairs, kUpdThreads), ceil_div(rows, kUpdRows));
-    update_smem_kernel<<<grid, kUpdThreads, smem, s>>>(Yrows, ldY, rows, n_pairs, At_rows, kp, at, ldat, kk, kmask, slots, out,
-                                                       ldout, out_stride);
+#define RUVIII_UPDS(PF)                                                                                                   \
+    do {                                                                                                                  \
+        RUVIII_CUDA_CHECK(cudaFuncSetAttribute(update_smem_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        update_smem_kernel<PF><<<grid, kUpdThreads, smem, s>>>(Yrows, ldY, rows, n_pairs, At_rows, kp, at, ldat, kk, kmask, \
+                                                               slots, out, ldout, out_stride);                            \
+    } while (0)
+    if (pf <= 0) RUVIII_UPDS(0);
+    else if (pf == 1) RUVIII_UPDS(1);
+    else if (pf == 2) RUVIII_UPDS(2);
+    else RUVIII_UPDS(4);
+#undef RUVIII_UPDS
     RUVIII_LAUNCH_CHECK();
 }
 

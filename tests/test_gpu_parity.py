@@ -308,8 +308,8 @@ def test_gram_kernels_agree():
 
 
 @pytest.mark.parametrize("env", [{"RUVIII_GRAM_IMPL": "2"}, {"RUVIII_GRAM_IMPL": "4"}, {"RUVIII_UPD_IMPL": "2"},
-                                 {"RUVIII_UPD_IMPL": "3"}],
-                         ids=["gram_tma", "gram_128", "update_tma", "update_smem"])
+                                 {"RUVIII_UPD_IMPL": "1"}, {"RUVIII_UPD_PREFETCH": "0"}],
+                         ids=["gram_tma", "gram_128", "update_tma", "update_regs", "update_noprefetch"])
 def test_tma_kernel_variants_match(env):
     """The TMA + mbarrier variants of the Gram and of the update give the same results as the default kernels:
     odd gene count, R = 258 (three tile rows, last one ragged), multi-k, k = 0 included."""
