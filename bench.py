@@ -238,6 +238,10 @@ def main():
     cells = float(m1) * n * len(ks)
     value = cells / (dev_ms * 1e-3)
 
+    allreduce_us = None
+    if args.probes and world > 1:            # every rank takes part
+        allreduce_us = {"%d KiB" % kb: round(eng.probe(5, kb), 1) for kb in (8, 128, 1500, 5000, 20000)}
+
     # ---- end-to-end leg: ruviii_normalise, pinned host in / pinned host out -----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -293,7 +297,7 @@ def main():
                 "share_of_step": stage_ms["ms_update"] / max(stage_ms["ms_total"], 1e-9)}
 
     probes = None
-    if args.probes:
+    if args.probes and world == 1:
         probes = {"copy_gbs": eng.probe(0, 2048), "cublas_dgemm_tflops_8192": eng.probe(1, 8192),
                   "dmma_issue_tflops": eng.probe(2, 0), "host_gather_11000x1000_ms": eng.probe(3, 1000),
                   "copy_variants_gbs": dict(zip(["linear", "tiled_r4_plain", "tiled_r4_hint", "tiled_r8_hint", "tiled_r4_hint_16rows",
@@ -323,7 +327,7 @@ def main():
                    "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1")), "gram_order": info.gram_order,
                    "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "3"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
-        "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes,
+        "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes, "nccl_allreduce_us": allreduce_us,
     }
     print(json.dumps(line))
     eng.close()

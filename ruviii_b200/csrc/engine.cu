@@ -1089,6 +1089,37 @@ int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_ou
             *value_out = probe_copy_gbs((size_t)std::max(size, 64) << 20, s.stream);
         } else if (which == 2) {
             *value_out = probe_dmma_tflops(h->n_sms, s.stream);
+        } else if (which == 5) {
+            // median microseconds of an in-place FP64 sum-allreduce of `size` KiB over all shards (every rank must call)
+            const size_t count = (size_t)std::max(size, 1) * 128;
+            std::vector<DevBuf<double>> bufs(h->shards.size());
+            std::vector<double*> ptrs;
+            for (size_t i = 0; i < h->shards.size(); ++i) {
+                RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[i].device));
+                bufs[i].alloc(count);
+                ptrs.push_back(bufs[i].p);
+            }
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            std::vector<float> t;
+            for (int it = 0; it < 25; ++it) {
+                sync_all(h);
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                cudaEventRecord(e0, s.stream);
+                allreduce_sum(h, ptrs, count);
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                cudaEventRecord(e1, s.stream);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (it >= 5) t.push_back(ms);
+            }
+            sync_all(h);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            for (size_t i = 0; i < h->shards.size(); ++i) { cudaSetDevice(h->shards[i].device); bufs[i].release(); }
+            std::sort(t.begin(), t.end());
+            *value_out = 1e3 * t[t.size() / 2];
         } else if (which == 4) {
             double r[8];
             probe_copy_variants(r, s.stream);

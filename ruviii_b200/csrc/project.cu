@@ -140,66 +140,85 @@ gather_ac_kernel(const double* __restrict__ alpha, int64_t ld, int kp, const int
 }
 
 // ---- K5: A[i][j] = sum_c Y[i][ctl_idx[c]] * acT[c][j] -------------------------------------------------------------
-// A gather: every control gene of every row costs one 32-byte sector (64-byte DRAM granule) for 8 useful bytes, so
-// the kernel is bound by sectors in flight.  One warp owns kCtlRows rows; per tile of 128 control genes each lane
-// issues 4 x kCtlRows independent gathers before touching any of them, then multiplies against the acT tile staged
-// in shared memory (row stride kp + 1: lanes read different rows of acT, an odd stride keeps them on distinct banks).
-constexpr int kCtlWarps = 8;
+// A gather: every control gene of every row costs one 32-byte sector (a 64-byte DRAM granule) for 8 useful bytes, so
+// the kernel is bound by sectors in flight, not by arithmetic.  The gather therefore runs through cp.async (8-byte
+// copies straight into shared memory, no registers held per outstanding load): a CTA owns 32 rows, tiles of 128
+// control genes are double buffered, so 2 x 4,096 gathers per CTA are in flight while the previous tile is
+// multiplied against its slice of acT.  Products are plain DFMA (2 m c kp flop is negligible).
+constexpr int kCtlThreads = 256;
+constexpr int kCtlRowsPerCta = 32;
 constexpr int kCtlTile = 128;
-__host__ __device__ constexpr int ctl_rows_per_warp(int kp) { return kp <= 16 ? 4 : 2; }   // 64 accumulators/thread
+constexpr int kCtlYStride = kCtlTile + 1;          // doubles; odd stride: the 32 rows of a column land in distinct banks
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
 
 template <int KP>
-__global__ void __launch_bounds__(kCtlWarps * 32)
+__global__ void __launch_bounds__(kCtlThreads)
 ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl,
                     const double* __restrict__ acT, double* __restrict__ A) {
-    constexpr int NR = ctl_rows_per_warp(KP);
-    __shared__ double sAc[kCtlTile][KP + 1];
-    __shared__ int sIdx[kCtlTile];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row0 = (blockIdx.x * kCtlWarps + warp) * NR;
-    const double* rp[NR];
+    constexpr int AS = KP + 4;                       // acT tile row stride (doubles), keeps rows 16-byte aligned
+    extern __shared__ __align__(16) double ctl_smem[];
+    double* sY = ctl_smem;                           // [2][32][129]
+    double* sAc = ctl_smem + 2 * kCtlRowsPerCta * kCtlYStride;   // [2][128][AS]
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * kCtlRowsPerCta;
+    const int n_tiles = (n_ctl + kCtlTile - 1) / kCtlTile;
+    // gather role: control gene c = tid % 128 of the tile, rows (tid / 128) + 2 i, i = 0..15
+    const int gc = tid & (kCtlTile - 1), gr0 = tid >> 7;
+    auto issue_tile = [&](int t, int buf) {
+        const int c = t * kCtlTile + gc;
+        const bool cok = c < n_ctl;
+        const int g = ctl_idx[cok ? c : 0];
+        double* dY = sY + buf * kCtlRowsPerCta * kCtlYStride + gc;
 #pragma unroll
-    for (int u = 0; u < NR; ++u) rp[u] = src.row(min(row0 + u, rows_w - 1));
-    double acc[NR][KP];
+        for (int i = 0; i < kCtlRowsPerCta / 2; ++i) {
+            const int r = gr0 + 2 * i;
+            cp_async8(dY + r * kCtlYStride, src.row(min(row0 + r, rows_w - 1)) + g, cok);
+        }
+        double* dA = sAc + buf * kCtlTile * AS;
+        for (int e = tid; e < kCtlTile * KP; e += kCtlThreads) {
+            const int cc = e / KP, j = e - cc * KP;
+            const bool ok = t * kCtlTile + cc < n_ctl;
+            cp_async8(dA + cc * AS + j, acT + (int64_t)(ok ? t * kCtlTile + cc : 0) * KP + j, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // compute role: row r = tid / 8, columns j = (tid % 8) + 8 u
+    constexpr int NJ = (KP + 7) / 8;
+    const int cr = tid >> 3, cj = tid & 7;
+    double acc[NJ];
 #pragma unroll
-    for (int u = 0; u < NR; ++u)
-#pragma unroll
-        for (int j = 0; j < KP; ++j) acc[u][j] = 0.0;
-    for (int c0 = 0; c0 < n_ctl; c0 += kCtlTile) {
-        const int nc = min(kCtlTile, n_ctl - c0);
+    for (int u = 0; u < NJ; ++u) acc[u] = 0.0;
+    issue_tile(0, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) {
+            issue_tile(t + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
-        for (int e = threadIdx.x; e < kCtlTile * KP; e += kCtlWarps * 32) {
-            const int c = e / KP, j = e - c * KP;
-            sAc[c][j] = c < nc ? acT[(int64_t)(c0 + c) * KP + j] : 0.0;
+        const double* y = sY + buf * kCtlRowsPerCta * kCtlYStride + cr * kCtlYStride;
+        const double* a = sAc + buf * kCtlTile * AS + cj;
+#pragma unroll 8
+        for (int c = 0; c < kCtlTile; ++c) {
+            const double yv = y[c];
+#pragma unroll
+            for (int u = 0; u < NJ; ++u)
+                if (cj + 8 * u < KP) acc[u] = fma(yv, a[c * AS + 8 * u], acc[u]);
         }
-        for (int c = threadIdx.x; c < kCtlTile; c += kCtlWarps * 32) sIdx[c] = c < nc ? ctl_idx[c0 + c] : ctl_idx[c0];
-        __syncthreads();
-        double y[4][NR];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int g = sIdx[t * 32 + lane];                   // padded entries repeat a valid gene; their acT rows are 0
-#pragma unroll
-            for (int u = 0; u < NR; ++u) y[t][u] = rp[u][g];
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const double* a = &sAc[t * 32 + lane][0];
-#pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const double w = a[j];
-#pragma unroll
-                for (int u = 0; u < NR; ++u) acc[u][j] = fma(y[t][u], w, acc[u][j]);
-            }
-        }
+        __syncthreads();                              // the buffer is refilled by the next iteration's issue_tile
     }
-    if (row0 >= rows_w) return;
+    if (row0 + cr < rows_w) {
 #pragma unroll
-    for (int u = 0; u < NR; ++u)
-#pragma unroll
-        for (int j = 0; j < KP; ++j) {
-            const double v = warp_sum(acc[u][j]);
-            if (lane == 0 && row0 + u < rows_w) A[(int64_t)(row0 + u) * KP + j] = v;
-        }
+        for (int u = 0; u < NJ; ++u)
+            if (cj + 8 * u < KP) A[(int64_t)(row0 + cr) * KP + cj + 8 * u] = acc[u];
+    }
 }
 
 // Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA: acT is streamed through shared memory in coalesced
@@ -379,12 +398,23 @@ void launch_alpha_from_v(const double* V, const double* evals, int n, int kk, in
 
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
                          double* A, double* Gm, cudaStream_t s) {
-    const int blocks = ceil_div(rows_w, kCtlWarps * ctl_rows_per_warp(kp));
-    switch (kp) {
-        case 4: ctl_products_kernel<4><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
-        case 8: ctl_products_kernel<8><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
-        case 16: ctl_products_kernel<16><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
-        default: ctl_products_kernel<32><<<blocks, kCtlWarps * 32, 0, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A); break;
+    const int blocks = ceil_div(rows_w, kCtlRowsPerCta);
+    if (n_ctl > 0) {
+#define RUVIII_CTL(KP)                                                                                                   \
+    do {                                                                                                                 \
+        const int smem = (2 * kCtlRowsPerCta * kCtlYStride + 2 * kCtlTile * (KP + 4)) * 8;                               \
+        RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ctl_products_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        ctl_products_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A);                  \
+    } while (0)
+        switch (kp) {
+            case 4: RUVIII_CTL(4); break;
+            case 8: RUVIII_CTL(8); break;
+            case 16: RUVIII_CTL(16); break;
+            default: RUVIII_CTL(32); break;
+        }
+#undef RUVIII_CTL
+    } else {
+        RUVIII_CUDA_CHECK(cudaMemsetAsync(A, 0, (size_t)rows_w * kp * sizeof(double), s));
     }
     RUVIII_LAUNCH_CHECK();
     ac_gram_kernel<<<1, 1024, 0, s>>>(acT, n_ctl, kp, Gm);

@@ -13,8 +13,8 @@ for n in 1 2 4 8; do
   if [ $n = 1 ]; then
     timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/scale_$n.json 2> $OUT/scale_$n.err
   else
-    NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n \
-      bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline > $OUT/scale_$n.json 2> $OUT/scale_$n.err
+    NCCL_DEBUG=${NCCL_DEBUG:-WARN} timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n \
+      bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline --probes > $OUT/scale_$n.json 2> $OUT/scale_$n.err
   fi
   echo "scale $n exit $?"; tail -c 1500 $OUT/scale_$n.json; echo; tail -3 $OUT/scale_$n.err
 done
