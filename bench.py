@@ -234,6 +234,11 @@ def main():
     wall_ms = max_over_ranks((t1 - t0) * 1e3 / args.steps)
     dev_ms = max_over_ranks(dev_ms / args.steps)
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    stage_ms_per_rank = None
+    if world > 1:                                   # every rank's view of the stages (skew shows up as allreduce time)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: round(v, 4) for k, v in stage_ms.items() if v > 0.002})
+        stage_ms_per_rank = gathered
     launches = info.kernel_launches * args.steps
     cells = float(m1) * n * len(ks)
     value = cells / (dev_ms * 1e-3)
@@ -328,6 +333,7 @@ def main():
                    "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "3"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes, "nccl_allreduce_us": allreduce_us,
+        "stage_ms_per_rank": stage_ms_per_rank,
     }
     print(json.dumps(line))
     eng.close()

@@ -217,7 +217,7 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
 // With check != 0 it first turns the residual partials Rp into ||Z_j - theta_j X_j||, j < kk, and raises the
 // converged flag when all of them are <= tol * theta_0 (everything queued behind then exits at once).
 template <int B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restrict__ Rp, int n_part, int kk, double tol,
                 int iter, double* __restrict__ M, const double* __restrict__ theta, double* __restrict__ resid,
                 int* __restrict__ state) {
@@ -415,7 +415,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     int launches = 0;
     ek_init_kernel<B><<<ceil_div((int64_t)R * B, 256), 256, 0, s>>>(w.Zp, R, w.state);
     ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, 1, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-    ek_ortho_kernel<B><<<1, 256, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, 0, w.M, w.theta, w.resid, w.state);
+    ek_ortho_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, 0, w.M, w.theta, w.resid, w.state);
     ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
     launches += 4;
     TopkResult res;
@@ -432,12 +432,12 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
                 ek_rotate_kernel<B><<<n_rb, 256, 0, s>>>(w.Q, w.Z, w.V, w.theta, R, w.X, w.Rp, w.state);
                 // CHECK sets the flag; the ORTHO half of mode 2 needs S of the rotated block, so it is recomputed first
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, 1, nullptr, R, nullptr, w.Sp, nullptr, w.state);
-                ek_ortho_kernel<B><<<1, 256, 0, s>>>(1, w.Sp, w.Rp, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
+                ek_ortho_kernel<B><<<1, 1024, 0, s>>>(1, w.Sp, w.Rp, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
                 ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
                 launches += 6;
             } else {
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-                ek_ortho_kernel<B><<<1, 256, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
+                ek_ortho_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
                 ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
                 launches += 3;
             }

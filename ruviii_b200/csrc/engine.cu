@@ -127,8 +127,10 @@ struct Shard {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
+    cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
+    int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
-        evals_asc, falpha, topk_buf, Zt, avg;
+        evals_asc, falpha, topk_buf, Zt, avg, Yc;
     DevBuf<int2> tile_map;
     DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows;
     TopkWork topk{};
@@ -194,9 +196,11 @@ ruviii_handle::~ruviii_handle() {
         cudaDeviceSynchronize();
         if (s.comm) ncclCommDestroy(s.comm);
         for (auto e : s.ev) cudaEventDestroy(e);
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        if (s.ev_gather) cudaEventDestroy(s.ev_gather);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg};
+                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -236,6 +240,8 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
     RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
     s.ev.resize(E_COUNT);
     for (auto& e : s.ev) RUVIII_CUDA_CHECK(cudaEventCreate(&e));
+    RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_gather, cudaEventDisableTiming));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     h->n_sms = sms;
@@ -454,6 +460,8 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.at.alloc((size_t)kp * s.ld);
             s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
             s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp);
+            s.ldc = round_up(std::max(s.n_ctl, 1), kRowAlign);
+            s.Yc.alloc((size_t)h->rows_w * s.ldc, false);
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
             s.colmean.alloc(kp);
@@ -606,6 +614,15 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         });
         for (int e = E_RESIDOP; e < E_COUNT; ++e) rec(e);
     } else {
+        // control-gene gather on the auxiliary stream: it depends on Y only, so it overlaps residop / Gram / eigensolve
+        for_shards([&](Shard& s) {
+            RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
+            launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, s.copy_stream);
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
+        });
+        h->launches += 1;
         if (!h->have_user_alpha) {
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
@@ -682,8 +699,9 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         rec(E_PROJECT);
         for_shards([&](Shard& s) {
             RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));
             launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
-                                s.stream);
+                                s.n_ctl > 0 ? s.Yc.p : nullptr, s.ldc, s.stream);
         });
         h->launches += 2;
         rec(E_CTL);

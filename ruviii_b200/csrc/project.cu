@@ -156,10 +156,27 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
 }
 
+// Yc[r][c] = Y[r][ctl_idx[c]]: the gather itself needs no eigenvector, so the engine runs it on a second stream
+// while the (latency-bound, few-CTA) eigensolve occupies the main stream; the products then read Yc contiguously.
+constexpr int kGatherRows = 8;
+__global__ void __launch_bounds__(256)
+ctl_gather_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl, double* __restrict__ Yc, int64_t ldc) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_ctl) return;
+    const int g = ctl_idx[c];
+    const int r0 = blockIdx.y * kGatherRows;
+    double y[kGatherRows];
+#pragma unroll
+    for (int u = 0; u < kGatherRows; ++u) y[u] = (r0 + u < rows_w) ? src.row(r0 + u)[g] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kGatherRows; ++u)
+        if (r0 + u < rows_w) Yc[(int64_t)(r0 + u) * ldc + c] = y[u];
+}
+
 template <int KP>
 __global__ void __launch_bounds__(kCtlThreads)
 ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl,
-                    const double* __restrict__ acT, double* __restrict__ A) {
+                    const double* __restrict__ acT, double* __restrict__ A, const double* __restrict__ Yc, int64_t ldc) {
     constexpr int AS = KP + 4;                       // acT tile row stride (doubles), keeps rows 16-byte aligned
     extern __shared__ __align__(16) double ctl_smem[];
     double* sY = ctl_smem;                           // [2][32][129]
@@ -172,12 +189,20 @@ ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int
     auto issue_tile = [&](int t, int buf) {
         const int c = t * kCtlTile + gc;
         const bool cok = c < n_ctl;
-        const int g = ctl_idx[cok ? c : 0];
         double* dY = sY + buf * kCtlRowsPerCta * kCtlYStride + gc;
+        if (Yc) {                                      // pre-gathered: contiguous 8-byte copies, whole lines per warp
 #pragma unroll
-        for (int i = 0; i < kCtlRowsPerCta / 2; ++i) {
-            const int r = gr0 + 2 * i;
-            cp_async8(dY + r * kCtlYStride, src.row(min(row0 + r, rows_w - 1)) + g, cok);
+            for (int i = 0; i < kCtlRowsPerCta / 2; ++i) {
+                const int r = gr0 + 2 * i;
+                cp_async8(dY + r * kCtlYStride, Yc + (int64_t)min(row0 + r, rows_w - 1) * ldc + (cok ? c : 0), cok);
+            }
+        } else {
+            const int g = ctl_idx[cok ? c : 0];
+#pragma unroll
+            for (int i = 0; i < kCtlRowsPerCta / 2; ++i) {
+                const int r = gr0 + 2 * i;
+                cp_async8(dY + r * kCtlYStride, src.row(min(row0 + r, rows_w - 1)) + g, cok);
+            }
         }
         double* dA = sAc + buf * kCtlTile * AS;
         for (int e = tid; e < kCtlTile * KP; e += kCtlThreads) {
@@ -396,15 +421,22 @@ void launch_alpha_from_v(const double* V, const double* evals, int n, int kk, in
     RUVIII_LAUNCH_CHECK();
 }
 
+void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, cudaStream_t s) {
+    if (n_ctl <= 0 || rows_w <= 0) return;
+    dim3 grid(ceil_div(n_ctl, 256), ceil_div(rows_w, kGatherRows));
+    ctl_gather_kernel<<<grid, 256, 0, s>>>(src, rows_w, ctl_idx, n_ctl, Yc, ldc);
+    RUVIII_LAUNCH_CHECK();
+}
+
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
-                         double* A, double* Gm, cudaStream_t s) {
+                         double* A, double* Gm, const double* Yc, int64_t ldc, cudaStream_t s) {
     const int blocks = ceil_div(rows_w, kCtlRowsPerCta);
     if (n_ctl > 0) {
 #define RUVIII_CTL(KP)                                                                                                   \
     do {                                                                                                                 \
         const int smem = (2 * kCtlRowsPerCta * kCtlYStride + 2 * kCtlTile * (KP + 4)) * 8;                               \
         RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ctl_products_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        ctl_products_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A);                  \
+        ctl_products_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A, Yc, ldc);         \
     } while (0)
         switch (kp) {
             case 4: RUVIII_CTL(4); break;
