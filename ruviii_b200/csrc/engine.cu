@@ -614,15 +614,20 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         });
         for (int e = E_RESIDOP; e < E_COUNT; ++e) rec(e);
     } else {
-        // control-gene gather on the auxiliary stream: it depends on Y only, so it overlaps residop / Gram / eigensolve
-        for_shards([&](Shard& s) {
-            RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
-            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
-            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
-            launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, s.copy_stream);
-            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
-        });
-        h->launches += 1;
+        // Control-gene gather on the auxiliary stream.  It depends on Y only; it is forked AFTER the (bandwidth- and
+        // tensor-bound) residop and Gram so that it fills the otherwise idle GPU during the eigensolve, whose kernels
+        // are latency-bound and occupy a handful of SMs (forked at the start it only stole HBM bandwidth from K1).
+        auto fork_gather = [&]() {
+            for_shards([&](Shard& s) {
+                RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
+                RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
+                launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, s.copy_stream);
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
+            });
+            h->launches += 1;
+        };
+        if (h->have_user_alpha) fork_gather();
         if (!h->have_user_alpha) {
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
@@ -642,6 +647,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             });
             h->launches += h->gene_side ? 3 : 2;
             rec(E_GRAM);
+            fork_gather();
             {
                 std::vector<double*> b;
                 for (auto& s : h->shards) b.push_back(s.G.p);
