@@ -444,6 +444,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
         }
         RUVIII_LAUNCH_CHECK();
         RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        for (int spin = 0; spin < (1 << 22) && cudaStreamQuery(s) == cudaErrorNotReady; ++spin) {}   // poll, do not sleep
         RUVIII_CUDA_CHECK(cudaStreamSynchronize(s));
         if (h_state[0]) break;
     }
