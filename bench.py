@@ -215,14 +215,17 @@ def main():
     eng.upload(Y_h, PS_h)
     for _ in range(args.warmup):
         eng.run()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.barrier()      # device-side: the host barrier releases ranks milliseconds apart, which is several passes
     stage_ms = {}
     dev_ms = 0.0
+    host_marks = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         info = eng.run()
+        host_marks.append((info.host_t_enter, info.host_t_done, time.monotonic()))
         dev_ms += info.ms_total
         for name, _ in info._fields_:
             if name.startswith("ms_"):
@@ -237,7 +240,11 @@ def main():
     stage_ms_per_rank = None
     if world > 1:                                   # every rank's view of the stages (skew shows up as allreduce time)
         gathered = [None] * world
-        dist.all_gather_object(gathered, {k: round(v, 4) for k, v in stage_ms.items() if v > 0.002})
+        mine = {k: round(v, 4) for k, v in stage_ms.items() if v > 0.002}
+        base = host_marks[0][0]
+        mine["host_marks_ms"] = [[round((a - base) * 1e3, 3), round((b - base) * 1e3, 3), round((c - base) * 1e3, 3)] for a, b, c in host_marks[:6]]
+        mine["host_base"] = base
+        dist.all_gather_object(gathered, mine)
         stage_ms_per_rank = gathered
     launches = info.kernel_launches * args.steps
     cells = float(m1) * n * len(ks)
@@ -253,6 +260,7 @@ def main():
         for _ in range(min(args.warmup, 2)):
             eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
         barrier()
+        eng.barrier()
         te0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
         for _ in range(n_e2e):

@@ -84,6 +84,7 @@ typedef struct ruviii_info {
     int32_t eig_iterations;            /* subspace-iteration passes (solver 3); 0 otherwise                        */
     int32_t gram_order;                /* order of the Gram actually formed: active_rows - #non-singleton groups    */
     int32_t reserved_i;
+    double host_t_enter, host_t_done;  /* CLOCK_MONOTONIC seconds at ruviii_run entry and when its last stream drained */
 } ruviii_info;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */
@@ -155,6 +156,10 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */
 int ruviii_fast_residop(ruviii_handle* h, const double* A_rowmajor_rows_x_n, int32_t rows, int32_t n,
                         const int32_t* group_of_row, double* out);
+
+/* Device-side barrier over all shards of all processes (a one-element allreduce followed by a stream drain): aligns
+ * the ranks to within microseconds, which a host-side (gloo/MPI) barrier does not.  No-op for a single shard. */
+int ruviii_barrier(ruviii_handle* h);
 
 /* ---- micro-benchmarks used by bench.py to state practical ceilings beside the roofline ----------------- */
 /* which: 0 = device copy GB/s (bytes read+written), 1 = cuBLAS Dgemm TFLOP/s at size^3, 2 = DMMA issue peak TFLOP/s,

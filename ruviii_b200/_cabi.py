@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
 ]
 
 
@@ -42,7 +42,7 @@ class Info(C.Structure):
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
                 ("eig_top", C.c_double), ("eig_kmax", C.c_double), ("eig_next", C.c_double),
                 ("eig_solver", C.c_int32), ("eig_iterations", C.c_int32), ("gram_order", C.c_int32),
-                ("reserved_i", C.c_int32)]
+                ("reserved_i", C.c_int32), ("host_t_enter", C.c_double), ("host_t_done", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -85,6 +85,7 @@ def load_library():
     lib.ruviii_run.argtypes = [H, C.POINTER(Info)]
     lib.ruviii_download.argtypes = [H, vp, vp, vp, vp]
     lib.ruviii_download_averaged.argtypes = [H, vp]
+    lib.ruviii_barrier.argtypes = [H]
     lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
@@ -196,6 +197,9 @@ class Engine:
         self._check(self._lib.ruviii_run(self._h, C.byref(info)))
         self._info = info
         return info
+
+    def barrier(self):
+        self._check(self._lib.ruviii_barrier(self._h))
 
     def set_fullalpha(self, fullalpha):
         fa = _rowmajor(fullalpha, "fullalpha")

@@ -599,6 +599,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     const int kp = h->kp, kk = h->kk, R = h->R, nk = (int)h->ks.size();
     const bool want_ps = (h->prm.want_ps_rows || h->prm.average_rep) && !fast && h->n_ps > 0;
     h->launches = 0;
+    const double host_t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     auto rec = [&](int e) {
         for (auto& s : h->shards) {
             RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
@@ -790,6 +791,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         h->launches += nk;
     }
     sync_all(h);
+    const double host_t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     if (!skip) {
         if (h->rank0 == 0 && !h->have_user_alpha && h->h_flags[0] != 0)
             throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
@@ -810,6 +812,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = h->kk; I.no_replicates = h->no_replicates; I.gram_side = h->gene_side ? 2 : 1;
     I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
     I.eig_solver = (skip || h->have_user_alpha) ? 0 : h->eig_solver_used; I.eig_iterations = h->eig_iterations;
+    I.host_t_enter = host_t_enter; I.host_t_done = host_t_done;
     {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
@@ -1118,6 +1121,22 @@ int ruviii_fast_residop(ruviii_handle* h, const double* A, int32_t rows, int32_t
         RUVIII_CUDA_CHECK(cudaMemcpy2D(tmp.data(), (size_t)n * 8, dO.p, ld * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost));
         for (int t = 0; t < rows; ++t) std::memcpy(out + (size_t)gr[t] * n, tmp.data() + (size_t)t * n, (size_t)n * 8);
         dA.release(); dO.release(); dgs.release(); dgr.release();
+    });
+}
+
+int ruviii_barrier(ruviii_handle* h) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (h->world > 1) {
+            std::vector<double*> ptrs;
+            for (auto& s : h->shards) {
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                s.status.alloc(4);
+                ptrs.push_back(reinterpret_cast<double*>(s.status.p));     // 16 bytes, used as one double
+            }
+            allreduce_sum(h, ptrs, 1);
+        }
+        sync_all(h);
     });
 }
 
