@@ -270,7 +270,8 @@ def main():
         e2e = {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3,
                "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world,
                "d2h_bytes_per_step": int(out_h.nbytes) * world, "steps": n_e2e,
-               "api": "ruviii_normalise (C ABI) with pinned host buffers, copies inside the timed region"}
+               "api": "ruviii_normalise (C ABI) with pinned host buffers, copies inside the timed region",
+               "pipelined": int(eng._info.pipelined)}
 
     if rank != 0:
         eng.close()

@@ -83,7 +83,7 @@ typedef struct ruviii_info {
     int32_t eig_solver;                /* 0 none, 1 cuSOLVER syevd, 2 cuSOLVER syevdx, 3 block subspace iteration   */
     int32_t eig_iterations;            /* subspace-iteration passes (solver 3); 0 otherwise                        */
     int32_t gram_order;                /* order of the Gram actually formed: active_rows - #non-singleton groups    */
-    int32_t reserved_i;
+    int32_t pipelined;                 /* 1 when ruviii_normalise overlapped upload, compute and download (pinned buffers) */
     double host_t_enter, host_t_done;  /* CLOCK_MONOTONIC seconds at ruviii_run entry and when its last stream drained */
 } ruviii_info;
 
@@ -156,6 +156,12 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */
 int ruviii_fast_residop(ruviii_handle* h, const double* A_rowmajor_rows_x_n, int32_t rows, int32_t n,
                         const int32_t* group_of_row, double* out);
+
+/* Page-locked host memory.  ruviii_normalise overlaps upload, compute and download only when Y and newY_out are
+ * page-locked (these helpers, cudaHostAlloc or cudaHostRegister); with pageable buffers it copies, computes and
+ * copies back in sequence.  Returns NULL when no CUDA device is present. */
+void* ruviii_host_alloc(size_t bytes);
+void  ruviii_host_free(void* p);
 
 /* Device-side barrier over all shards of all processes (a one-element allreduce followed by a stream drain): aligns
  * the ranks to within microseconds, which a host-side (gloo/MPI) barrier does not.  No-op for a single shard. */

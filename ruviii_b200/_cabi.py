@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
 ]
 
 
@@ -42,7 +42,7 @@ class Info(C.Structure):
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
                 ("eig_top", C.c_double), ("eig_kmax", C.c_double), ("eig_next", C.c_double),
                 ("eig_solver", C.c_int32), ("eig_iterations", C.c_int32), ("gram_order", C.c_int32),
-                ("reserved_i", C.c_int32), ("host_t_enter", C.c_double), ("host_t_done", C.c_double)]
+                ("pipelined", C.c_int32), ("host_t_enter", C.c_double), ("host_t_done", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -86,13 +86,17 @@ def load_library():
     lib.ruviii_download.argtypes = [H, vp, vp, vp, vp]
     lib.ruviii_download_averaged.argtypes = [H, vp]
     lib.ruviii_barrier.argtypes = [H]
+    lib.ruviii_host_alloc.argtypes = [C.c_size_t]
+    lib.ruviii_host_alloc.restype = C.c_void_p
+    lib.ruviii_host_free.argtypes = [C.c_void_p]
+    lib.ruviii_host_free.restype = None
     lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
     lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("ruviii_destroy", "ruviii_last_error"):
+        if name not in ("ruviii_destroy", "ruviii_last_error", "ruviii_host_alloc", "ruviii_host_free"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -124,6 +128,29 @@ def make_params(mode=MODE_STACKED, apply_log=False, pseudo_count=1.0, average_re
     p.want_ps_rows = int(bool(want_ps_rows))
     p.gram_side = int(gram_side)
     return p
+
+
+class PinnedArray:
+    """A float64 numpy array in page-locked host memory (ruviii_host_alloc); keep the object alive while in use."""
+
+    def __init__(self, shape):
+        lib = load_library()
+        self._lib = lib
+        n = int(np.prod(shape))
+        self._ptr = lib.ruviii_host_alloc(max(n, 1) * 8)
+        if not self._ptr:
+            raise RuviiiError(ERR_CUDA, "ruviii_host_alloc failed (no CUDA device?)")
+        buf = (C.c_double * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                self.array = None
+                self._lib.ruviii_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
 
 
 class Engine:

@@ -125,7 +125,8 @@ struct Shard {
     int g0 = 0, n = 0;            // first gene (in the caller's matrix) and gene count of this shard
     int64_t ld = 0;               // device row pitch (doubles) of every genes-contiguous matrix
     int n_ctl = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_chunk, ev_upd;   // pipelined host path: chunk uploaded / chunk updated
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
@@ -182,6 +183,8 @@ struct ruviii_handle {
     int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
     int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
     bool use_topk = false;
+    bool active_all_ps = false;         // every non-singleton row is a PRPS row (the PRPS regime)
+    int pipelined_last = 0;             // 1 when the last ruviii_normalise took the pipelined host path
     bool gene_side = false;             // Gram = Z'Z (n x n) instead of Z Z' (R x R): taken when R > n
     int gorder = 0;                     // order of the Gram that is formed and decomposed
     double eig_tol = 1e-13;
@@ -213,6 +216,9 @@ ruviii_handle::~ruviii_handle() {
         s.all_rows.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
+        for (auto e : s.ev_chunk) cudaEventDestroy(e);
+        for (auto e : s.ev_upd) cudaEventDestroy(e);
     }
     if (!shards.empty()) cudaSetDevice(shards[0].device);
     solver_work.release();
@@ -239,6 +245,7 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
     RUVIII_CUDA_CHECK(cudaSetDevice(device));
     RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.d2h_stream, cudaStreamNonBlocking));
     s.ev.resize(E_COUNT);
     for (auto& e : s.ev) RUVIII_CUDA_CHECK(cudaEventCreate(&e));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
@@ -296,6 +303,7 @@ void sync_all(ruviii_handle* h) {
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         spin_sync(s.stream);
         spin_sync(s.copy_stream);
+        spin_sync(s.d2h_stream);
     }
 }
 
@@ -346,6 +354,8 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     }
     h->n_groups_active = (int)grp_start.size() - 1;
     h->active_rows = (int)grp_rows.size();
+    h->active_all_ps = true;
+    for (int r : grp_rows) h->active_all_ps = h->active_all_ps && r >= m1;
     h->R = h->active_rows - h->n_groups_active;     // order of the Gram: sum(size - 1) = m - ncol(M)
     h->no_replicates = h->p >= m_for_M;             // ruvIII.R:128-129
 
@@ -640,7 +650,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
                 RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
                 RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
-                launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, s.copy_stream);
+                launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, 0, 0.0, s.copy_stream);
                 RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
             });
             h->launches += 1;
@@ -885,6 +895,188 @@ void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullal
     h->info.ms_d2h = ms;
 }
 
+// ---- pipelined host-to-host path of ruviii_normalise -----------------------------------------------------------
+// The one-shot call is PCIe-bound (C3: 1.95 GB in, 1.76 GB out, ~35 ms each way at ~55 GB/s against ~2 ms of
+// kernels), and the link is full duplex, so the only real lever is to start the download before the upload has
+// finished.  W needs the control columns of EVERY row of Y, which would serialise the two directions; so those
+// columns (m1 x c doubles, 5 % of Y) are gathered straight out of the pinned host buffer by a zero-copy kernel while
+// the bulk DMA is still streaming Y in row chunks.  Timeline per shard:
+//   copy stream : PS -> Y chunk 0 -> Y chunk 1 -> ...                              (H2D DMA)
+//   d2h stream  : zero-copy gather of Y[, ctl]  ....  newY chunk 0 -> newY chunk 1 -> ...   (D2H DMA)
+//   main stream : K1 K2 [allreduce] K3 [bcast] K4 | wait gather | K5 [allreduce] solve | per chunk: wait upload, K6
+// Taken when the host buffers are pinned, every replicate row is a PRPS row (the PRPS regime: residop/Gram/eigen
+// need PS only), the sample-side Gram is used and nothing but newY / W / the leading rows of fullalpha is wanted.
+// Device-visible alias of a pinned (cudaHostAlloc'ed / registered) host pointer, or nullptr for pageable memory.
+const void* host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+bool can_pipeline(ruviii_handle* h, const double* Y, const double* newY_out, const double* newY_ps_out) {
+    const int off = env_int("RUVIII_NO_PIPELINE", 0);
+    const bool skip = h->no_replicates || h->kk == 0;
+    return !off && !skip && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
+           h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;
+}
+
+void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* newY_out,
+                            double* fullalpha_out, double* W_out) {
+    const bool fast = h->prm.mode == RUVIII_MODE_FAST;
+    const int kp = h->kp, kk = h->kk, R = h->R, nk = (int)h->ks.size(), m1 = h->m1;
+    const int64_t n = h->n_local_total;
+    const double t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    h->launches = 0;
+    auto for_shards = [&](auto&& fn) {
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            fn(s);
+        }
+    };
+    // row chunks of ~1/12 of the assay (>= 256 rows, multiple of 64)
+    const int chunk = (int)round_up(std::max(256, ceil_div(m1, 12)), 64);
+    const int n_chunks = ceil_div(m1, chunk);
+    for_shards([&](Shard& s) {
+        while ((int)s.ev_chunk.size() < n_chunks + 2) {
+            cudaEvent_t e;
+            RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s.ev_chunk.push_back(e);
+            RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s.ev_upd.push_back(e);
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        // --- uploads: PS first, then Y in row chunks (copy stream) ---
+        if (h->n_ps > 0)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
+                                                cudaMemcpyHostToDevice, s.copy_stream));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[n_chunks], s.copy_stream));          // PS resident
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8,
+                                                (size_t)s.n * 8, rows, cudaMemcpyHostToDevice, s.copy_stream));
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
+        }
+        // --- zero-copy gather of the control columns out of the pinned host assay (d2h stream, idle until K6) ---
+        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.d2h_stream, s.ev_chunk[n_chunks], 0));   // PS rows come from the device copy
+        RowSrc hsrc{static_cast<const double*>(host_pinned(Y)) + s.g0, ldY, s.PS.p, s.ld, m1};
+        launch_ctl_gather(hsrc, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, h->prm.apply_log ? m1 : 0,
+                          h->prm.pseudo_count, s.d2h_stream);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.d2h_stream));
+        // --- K1, K2 on the PRPS rows ---
+        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[n_chunks], 0));
+        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
+        launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, s.n, s.Y0.p, s.ld, s.stream);
+        launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+    });
+    h->launches += 4;
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.G.p);
+        allreduce_sum(h, b, (size_t)R * R);
+    }
+    if (h->rank0 == 0) eigensolve(h);
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.U.p);
+        broadcast0(h, b, (size_t)R * kp);
+        b.clear();
+        for (auto& s : h->shards) b.push_back(s.evals.p);
+        broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
+    }
+    for_shards([&](Shard& s) {
+        launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
+        launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
+        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
+        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));
+        launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
+                            s.n_ctl > 0 ? s.Yc.p : nullptr, s.ldc, s.stream);
+    });
+    h->launches += 5;
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.AG.p);
+        allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
+    }
+    for_shards([&](Shard& s) {
+        const double* A = s.AG.p;
+        const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
+        launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
+        launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
+        launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
+        const int64_t stride = (int64_t)m1 * s.ld;
+        // --- K6 per chunk as it lands, download right behind it ---
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[c], 0));
+            if (h->prm.apply_log) launch_log2_inplace(s.Y.p + (size_t)r0 * s.ld, s.ld, rows, s.n, h->prm.pseudo_count, s.stream);
+            launch_update_smem(s.Y.p + (size_t)r0 * s.ld, s.ld, rows, s.n, s.At.p + (size_t)r0 * kp, kp, s.at.p, s.ld, kk,
+                               h->kmask, h->slot_of_k, s.out.p + (size_t)r0 * s.ld, s.ld, stride, s.stream);
+            for (auto& d : h->dup_slots)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.out.p + (size_t)d.first * stride + (size_t)r0 * s.ld, s.ld * 8,
+                                                    s.out.p + (size_t)d.second * stride + (size_t)r0 * s.ld, s.ld * 8,
+                                                    (size_t)s.n * 8, rows, cudaMemcpyDeviceToDevice, s.stream));
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_upd[c], s.stream));
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.d2h_stream, s.ev_upd[c], 0));
+            for (int i = 0; i < nk; ++i)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY_out + (size_t)i * m1 * n + (size_t)r0 * n + s.g0, n * 8,
+                                                    s.out.p + (size_t)i * stride + (size_t)r0 * s.ld, s.ld * 8, (size_t)s.n * 8,
+                                                    rows, cudaMemcpyDeviceToHost, s.d2h_stream));
+        }
+        size_t off = 0;
+        for (int i = 0; i < nk; ++i) {
+            launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
+            off += (size_t)h->rows_w * h->k_eff[i];
+        }
+        if (fullalpha_out)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(fullalpha_out + s.g0, n * 8, s.alpha.p, s.ld * 8, (size_t)s.n * 8, h->n_alpha_rows,
+                                                cudaMemcpyDeviceToHost, s.stream));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_UPDATE], s.stream));
+    });
+    h->launches += 3 + n_chunks * (h->prm.apply_log ? 2 : 1) + nk;
+    if (W_out) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        size_t w_total = 0;
+        for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(W_out, s.W.p, w_total * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[1 + i], s.status.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    }
+    sync_all(h);
+    const double t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (h->rank0 == 0 && h->h_flags[0] != 0)
+        throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
+    for (size_t i = 0; i < h->shards.size(); ++i)
+        if (h->h_flags[1 + i] != 0)
+            throw Error(RUVIII_ERR_SINGULAR, "ac %*% t(ac) is not positive definite at pivot " + std::to_string(h->h_flags[1 + i]) +
+                                                 " (solve() in ruvIII.R:144 would fail)");
+    ruviii_info& I = h->info;
+    std::memset(&I, 0, sizeof(I));
+    I.struct_size = sizeof(ruviii_info);
+    I.m = h->m; I.m1 = m1; I.n_ps = h->n_ps; I.n = (int)n; I.p = h->p; I.active_rows = h->active_rows; I.r = h->r;
+    I.gram_order = h->gorder; I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = kk; I.gram_side = 1;
+    I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
+    I.eig_solver = h->eig_solver_used; I.eig_iterations = h->eig_iterations; I.pipelined = 1;
+    I.host_t_enter = t_enter; I.host_t_done = t_done;
+    I.ms_total = (float)((t_done - t_enter) * 1e3);          // host wall time of the overlapped copy + compute pipeline
+    {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        std::vector<double> ev(kk + 1, 0.0);
+        const int have = std::min(kk + 1, h->n_keep);
+        RUVIII_CUDA_CHECK(cudaMemcpy(ev.data(), s.evals.p, have * sizeof(double), cudaMemcpyDeviceToHost));
+        I.eig_top = ev[0]; I.eig_kmax = ev[kk - 1]; I.eig_next = have > kk ? ev[kk] : 0.0;
+    }
+    (void)fast;
+    h->uploaded = true;
+    h->logged = h->prm.apply_log != 0;
+    h->ran = true;
+    h->pipelined_last = 1;
+}
+
 template <class F>
 int guarded(ruviii_handle* h, F&& fn) {
     try {
@@ -1082,9 +1274,15 @@ int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double
     return guarded(h, [&] {
         if (!newY_out) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
         do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk);
-        do_upload(h, Y, ldY, PS, ldPS);
-        do_run(h, nullptr);
-        do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out);
+        h->pipelined_last = 0;
+        if (can_pipeline(h, Y, newY_out, newY_ps_out)) {
+            if ((m1 > 0 && ldY < n) || (n_ps > 0 && (!PS || ldPS < n))) throw Error(RUVIII_ERR_INVALID, "row stride < n");
+            do_normalise_pipelined(h, Y, ldY, PS, ldPS, newY_out, fullalpha_out, W_out);
+        } else {
+            do_upload(h, Y, ldY, PS, ldPS);
+            do_run(h, nullptr);
+            do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out);
+        }
         if (info) *info = h->info;
     });
 }
@@ -1122,6 +1320,16 @@ int ruviii_fast_residop(ruviii_handle* h, const double* A, int32_t rows, int32_t
         for (int t = 0; t < rows; ++t) std::memcpy(out + (size_t)gr[t] * n, tmp.data() + (size_t)t * n, (size_t)n * 8);
         dA.release(); dO.release(); dgs.release(); dgr.release();
     });
+}
+
+void* ruviii_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void ruviii_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int ruviii_barrier(ruviii_handle* h) {

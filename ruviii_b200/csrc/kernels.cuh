@@ -96,7 +96,8 @@ void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_
 // K5  ruvIII.R:144  A = Y[, ctl] %*% t(ac)  (rows_w x kp, row-major) and Gm = ac %*% t(ac) (kp x kp).
 // The centring Y.stand = Y - 1 mu' (ruvIII.R:118-120) is applied later as A - 1 colMeans(A) (exact algebra).
 // Yc (optional): the control columns gathered beforehand by launch_ctl_gather (rows_w x ldc), read contiguously.
-void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, cudaStream_t s);
+void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, int log_rows,
+                       double pseudo_count, cudaStream_t s);
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
                          double* A, double* Gm, const double* Yc, int64_t ldc, cudaStream_t s);
 

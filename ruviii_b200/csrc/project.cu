@@ -159,8 +159,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 // Yc[r][c] = Y[r][ctl_idx[c]]: the gather itself needs no eigenvector, so the engine runs it on a second stream
 // while the (latency-bound, few-CTA) eigensolve occupies the main stream; the products then read Yc contiguously.
 constexpr int kGatherRows = 8;
+// log_rows > 0: rows [0, log_rows) are raw assay values still to be transformed (the pipelined host path gathers them
+// straight out of pinned host memory, before the device copy of the assay exists): apply ruvIII.R:89 on the fly.
 __global__ void __launch_bounds__(256)
-ctl_gather_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl, double* __restrict__ Yc, int64_t ldc) {
+ctl_gather_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n_ctl, double* __restrict__ Yc, int64_t ldc,
+                  int log_rows, double pseudo_count) {
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= n_ctl) return;
     const int g = ctl_idx[c];
@@ -170,7 +173,7 @@ ctl_gather_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int n
     for (int u = 0; u < kGatherRows; ++u) y[u] = (r0 + u < rows_w) ? src.row(r0 + u)[g] : 0.0;
 #pragma unroll
     for (int u = 0; u < kGatherRows; ++u)
-        if (r0 + u < rows_w) Yc[(int64_t)(r0 + u) * ldc + c] = y[u];
+        if (r0 + u < rows_w) Yc[(int64_t)(r0 + u) * ldc + c] = (r0 + u < log_rows) ? log2(y[u] + pseudo_count) : y[u];
 }
 
 template <int KP>
@@ -421,10 +424,11 @@ void launch_alpha_from_v(const double* V, const double* evals, int n, int kk, in
     RUVIII_LAUNCH_CHECK();
 }
 
-void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, cudaStream_t s) {
+void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, int log_rows,
+                       double pseudo_count, cudaStream_t s) {
     if (n_ctl <= 0 || rows_w <= 0) return;
     dim3 grid(ceil_div(n_ctl, 256), ceil_div(rows_w, kGatherRows));
-    ctl_gather_kernel<<<grid, 256, 0, s>>>(src, rows_w, ctl_idx, n_ctl, Yc, ldc);
+    ctl_gather_kernel<<<grid, 256, 0, s>>>(src, rows_w, ctl_idx, n_ctl, Yc, ldc, log_rows, pseudo_count);
     RUVIII_LAUNCH_CHECK();
 }
 

@@ -331,6 +331,28 @@ def test_tma_kernel_variants_match(env):
     assert np.array_equal(alt["newY"][0], p.Y)
 
 
+@pytest.mark.parametrize("apply_log", [False, True], ids=["log2_input", "counts_apply_log"])
+def test_pipelined_host_path_matches_sequential(engine, apply_log):
+    """ruviii_normalise with page-locked buffers overlaps upload / compute / download (zero-copy gather of the control
+    columns, chunked update); it must return exactly what the sequential upload -> run -> download path returns."""
+    p = make_problem(m1=700, n=3001, groups=60, rep=3, n_ctl=200, k=7, seed=20, counts=apply_log)
+    ks = [0, 3, 7]
+    groups = api.group_codes(p.sample_names + p.replicate_names)
+    prm = _cabi.make_params(apply_log=apply_log, pseudo_count=1.0)
+    seq = engine.normalise(prm, p.Y, p.replicate_data, groups, p.ctl, ks)
+    assert seq["info"].pipelined == 0
+    Yp, outp = _cabi.PinnedArray((700, 3001)), _cabi.PinnedArray((3, 700, 3001))
+    Yp.array[...] = p.Y
+    outp.array[...] = -1.0
+    info = engine.normalise_oneshot(prm, Yp.array, p.replicate_data, groups, p.ctl, ks, outp.array)
+    assert info.pipelined == 1
+    for i in range(3):
+        assert np.array_equal(outp.array[i], seq["newY"][i])
+    ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 7, apply_log=apply_log,
+                           pseudo_count=1.0)
+    assert O.rel_frob(outp.array[2], ref["newY"][:700]) < TOL_NEWY
+
+
 def test_eigensolvers_agree():
     """Block subspace iteration (solver 3) vs cuSOLVER syevdx (solver 2) vs the oracle, on a problem large enough
     for the iterative solver (R >= 128, rank >= 64).  newY depends only on the top-k subspace."""
