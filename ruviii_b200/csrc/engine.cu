@@ -243,9 +243,14 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
     s.device = device;
     check_device(device);
     RUVIII_CUDA_CHECK(cudaSetDevice(device));
-    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-    RUVIII_CUDA_CHECK(cudaStreamCreateWithFlags(&s.d2h_stream, cudaStreamNonBlocking));
+    // The main stream carries the critical path (including the tiny latency-bound eigensolver kernels); the auxiliary
+    // streams carry the control-gene gather and the copies.  Priorities make the block scheduler hand freed SM slots to
+    // the main stream first, otherwise the 6,000-CTA gather delays every few-CTA eigensolver launch behind it.
+    int prio_lo = 0, prio_hi = 0;
+    RUVIII_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithPriority(&s.copy_stream, cudaStreamNonBlocking, prio_lo));
+    RUVIII_CUDA_CHECK(cudaStreamCreateWithPriority(&s.d2h_stream, cudaStreamNonBlocking, prio_lo));
     s.ev.resize(E_COUNT);
     for (auto& e : s.ev) RUVIII_CUDA_CHECK(cudaEventCreate(&e));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
