@@ -34,7 +34,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C1", "C3", "C4", "tiny"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C3", "C4", "C3d", "C5", "tiny"],
+                    help="C3 = the BASELINE metric's configuration (default); C3d / C5 = dense replicate designs "
+                         "(12,200 / 60,000 rows in groups of 3, no PRPS rows; C5 takes the gene-side Gram), 1 GPU only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--probes", action="store_true", help="also measure copy / cuBLAS Dgemm / DMMA ceilings")
@@ -42,7 +44,13 @@ def parse():
 
 
 def workload_problem(name):
-    from ruviii_b200.synth import make_config, make_problem
+    from ruviii_b200.synth import Problem, make_config, make_dense_design, make_problem
+    if name in ("C3d", "C5"):
+        m = 12200 if name == "C3d" else 60000
+        Y, gid, ctl = make_dense_design(m=m, n=20000, group_size=3, n_ctl=1000, k=10)
+        names = ["g%d" % g for g in gid]
+        return Problem(assay=Y.T, sample_names=names, replicate_data=np.zeros((0, 20000)), replicate_names=[], ctl=ctl, k=10,
+                       meta=dict(m1=m, n=20000, n_ps=0, groups=int(gid.max()) + 1, n_ctl=int(ctl.sum()))), [10]
     if name == "tiny":
         return make_problem(m1=600, n=4000, groups=40, rep=3, n_ctl=300, k=5, seed=99), [5]
     p = make_config("C3" if name == "C4" else name)
@@ -138,6 +146,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         args.gpus = world
+    if args.workload in ("C3d", "C5"):          # evidence runs for the dense designs: no CPU arm (a 60,000^2 SVD)
+        args.no_cpu_baseline = True
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
