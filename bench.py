@@ -43,19 +43,21 @@ def parse():
     return ap.parse_args()
 
 
-def workload_problem(name):
+def workload_problem(name, rank=0, world=1):
+    """(problem, ks, sliced): `sliced` means the problem already holds only this rank's gene columns."""
     from ruviii_b200.synth import Problem, make_config, make_dense_design, make_problem
     if name in ("C3d", "C5"):
-        m = 12200 if name == "C3d" else 60000
-        Y, gid, ctl = make_dense_design(m=m, n=20000, group_size=3, n_ctl=1000, k=10)
+        m, n = (12200 if name == "C3d" else 60000), 20000
+        g0, g1 = n * rank // world, n * (rank + 1) // world
+        Y, gid, ctl = make_dense_design(m=m, n=n, group_size=3, n_ctl=1000, k=10, cols=(g0, g1))
         names = ["g%d" % g for g in gid]
-        return Problem(assay=Y.T, sample_names=names, replicate_data=np.zeros((0, 20000)), replicate_names=[], ctl=ctl, k=10,
-                       meta=dict(m1=m, n=20000, n_ps=0, groups=int(gid.max()) + 1, n_ctl=int(ctl.sum()))), [10]
+        return Problem(assay=Y.T, sample_names=names, replicate_data=np.zeros((0, g1 - g0)), replicate_names=[], ctl=ctl, k=10,
+                       meta=dict(m1=m, n=n, n_ps=0, groups=int(gid.max()) + 1, n_ctl=1000)), [10], True
     if name == "tiny":
-        return make_problem(m1=600, n=4000, groups=40, rep=3, n_ctl=300, k=5, seed=99), [5]
+        return make_problem(m1=600, n=4000, groups=40, rep=3, n_ctl=300, k=5, seed=99), [5], False
     p = make_config("C3" if name == "C4" else name)
     ks = list(range(1, 21)) if name == "C4" else [p.k]
-    return p, ks
+    return p, ks, False
 
 
 def measured_peaks():
@@ -185,10 +187,11 @@ def main():
 
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
-    p, ks = workload_problem(args.workload)
+    p, ks, sliced = workload_problem(args.workload, rank, world)
     m1, n, n_ps = p.meta["m1"], p.meta["n"], p.meta["n_ps"]
     g0, g1 = n * rank // world, n * (rank + 1) // world
     n_loc = g1 - g0
+    cols = slice(None) if sliced else slice(g0, g1)
     groups = api.group_codes(list(p.sample_names) + list(p.replicate_names))
 
     # pinned host buffers holding this rank's gene shard (the R shim would hand over the assay slab)
@@ -196,9 +199,9 @@ def main():
         return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
     Y_h = pinned((m1, n_loc))
     PS_h = pinned((n_ps, n_loc))
-    Y_h[...] = p.Y[:, g0:g1]
-    PS_h[...] = p.replicate_data[:, g0:g1]
-    ctl_loc = np.ascontiguousarray(p.ctl[g0:g1])
+    Y_h[...] = p.Y[:, cols]
+    PS_h[...] = p.replicate_data[:, cols]
+    ctl_loc = np.ascontiguousarray(p.ctl[cols])
     out_h = pinned((len(ks), m1, n_loc))
 
     if world > 1:
@@ -294,9 +297,13 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     nk = len(ks)
     upd_bytes = 8.0 * m1 * n_loc * (1 + nk)                          # K6: read Y once, write every requested k
-    R = info.gram_order                                              # Helmert rows: active_rows - #groups = m - ncol(M)
-    res_bytes = 8.0 * (info.active_rows + R) * n_loc                 # K1: read every member row, write every contrast row
-    gram_flops = float(R) * (R + 1) * n_loc                          # K2: symmetric half of the R x R Gram, FMA = 2 flop
+    R = info.gram_order                                              # order of the Gram that was formed
+    helm = info.m - info.p                                           # Helmert rows: active_rows - #groups = m - ncol(M)
+    res_bytes = 8.0 * (info.active_rows + helm) * n_loc              # K1: read every member row, write every contrast row
+    if info.gram_side == 2:                                          # t(Z) Z: order n (all genes), contraction = this rank's rows of Z
+        gram_flops = float(R) * (R + 1) * helm / world
+    else:                                                            # Z t(Z): order = Helmert rows, contraction = this rank's genes
+        gram_flops = float(R) * (R + 1) * n_loc                      # symmetric half, FMA = 2 flop
     kernels = {
         "update": {"bound": "hbm", "ms": stage_ms["ms_update"], "achieved": upd_bytes / (stage_ms["ms_update"] * 1e-3) / 1e9,
                    "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": upd_bytes},
@@ -343,7 +350,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %d samples x %d genes, %d PRPS rows in %d sets, %d control genes, k=%s, ruvIII (stacked) "
                                "semantics, genes sharded over %d GPU(s)" % (args.workload, m1, n, n_ps, p.meta["groups"],
-                                                                          int(p.ctl.sum()), ks if nk > 1 else ks[0], world),
+                                                                          int(p.meta["n_ctl"]), ks if nk > 1 else ks[0], world),
                    "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % ((Y_h.nbytes + PS_h.nbytes) / 1e9),
                    "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next},
                    "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(

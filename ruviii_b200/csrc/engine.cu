@@ -38,6 +38,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -61,6 +63,8 @@ struct NcclApi {
             api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
             api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
             api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+            api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+            api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
             api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
             api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
             api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
@@ -75,6 +79,8 @@ struct NcclApi {
 #define ncclCommDestroy ::ruviii::NcclApi::get().CommDestroy
 #define ncclAllReduce ::ruviii::NcclApi::get().AllReduce
 #define ncclBroadcast ::ruviii::NcclApi::get().Broadcast
+#define ncclSend ::ruviii::NcclApi::get().Send
+#define ncclRecv ::ruviii::NcclApi::get().Recv
 #define ncclGroupStart ::ruviii::NcclApi::get().GroupStart
 #define ncclGroupEnd ::ruviii::NcclApi::get().GroupEnd
 #define ncclGetErrorString ::ruviii::NcclApi::get().GetErrorString
@@ -132,7 +138,7 @@ struct Shard {
     cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
     int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
-        evals_asc, falpha, topk_buf, Zt, avg, Yc;
+        evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
     DevBuf<int2> tile_map;
     DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows;
     TopkWork topk{};
@@ -187,6 +193,10 @@ struct ruviii_handle {
     int pipelined_last = 0;             // 1 when the last ruviii_normalise took the pipelined host path
     bool gene_side = false;             // Gram = Z'Z (n x n) instead of Z Z' (R x R): taken when R > n
     int gorder = 0;                     // order of the Gram that is formed and decomposed
+    // gene-side Gram over several shards: gene count / first gene of every GLOBAL rank, and the split of
+    // the R Helmert rows over the ranks after the all-to-all (rank j contracts rows [zrow[j], zrow[j+1]))
+    std::vector<int> gn, goff, zrow;
+    int n_total = 0;                    // genes over all shards of all processes
     double eig_tol = 1e-13;
 
     ~ruviii_handle();
@@ -204,7 +214,7 @@ ruviii_handle::~ruviii_handle() {
         if (s.ev_gather) cudaEventDestroy(s.ev_gather);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc};
+                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -383,19 +393,29 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         s.n = (int)((int64_t)n * (i + 1) / nsh) - s.g0;
         s.ld = round_up(std::max(s.n, 1), kRowAlign);
     }
-    // total number of control genes over all processes (r depends on it, ruvIII.R:140)
+    // total number of control genes over all processes (r depends on it, ruvIII.R:140) and the gene count of every
+    // global rank (the gene-side Gram needs to know where each peer's genes sit in the n_total x n_total matrix)
     h->n_ctl_global = local_ctl;
+    h->gn.assign(h->world, 0);
     if (h->multi_process) {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        s.AG.alloc(16);
-        double v = (double)local_ctl;
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.AG.p, &v, 8, cudaMemcpyHostToDevice, s.stream));
-        RUVIII_NCCL_CHECK(ncclAllReduce(s.AG.p, s.AG.p, 1, ncclDouble, ncclSum, s.comm, s.stream));
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&v, s.AG.p, 8, cudaMemcpyDeviceToHost, s.stream));
+        std::vector<double> v(h->world + 1, 0.0);
+        v[0] = (double)local_ctl;
+        v[1 + h->rank0] = (double)n;
+        s.AG.alloc(v.size() + 16);
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.AG.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice, s.stream));
+        RUVIII_NCCL_CHECK(ncclAllReduce(s.AG.p, s.AG.p, v.size(), ncclDouble, ncclSum, s.comm, s.stream));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(v.data(), s.AG.p, v.size() * 8, cudaMemcpyDeviceToHost, s.stream));
         RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        h->n_ctl_global = (int64_t)(v + 0.5);
+        h->n_ctl_global = (int64_t)(v[0] + 0.5);
+        for (int j = 0; j < h->world; ++j) h->gn[j] = (int)(v[1 + j] + 0.5);
+    } else {
+        for (int i = 0; i < nsh; ++i) h->gn[i] = h->shards[i].n;
     }
+    h->goff.assign(h->world + 1, 0);
+    for (int j = 0; j < h->world; ++j) h->goff[j + 1] = h->goff[j] + h->gn[j];
+    h->n_total = h->goff[h->world];
     // r = min(m - ncol(M), sum(ctl))  (ruvIII.R:140); fastruvIII keeps k vectors of the n_ps x n residual
     const int rank_bound = m_for_M - h->p;
     h->rank_bound = rank_bound;
@@ -409,15 +429,19 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     h->rows_w = fast ? m1 : h->m;
     h->mu_rows = fast ? m1 : h->m;                  // ruvIII.R:118 vs fastruvIII.R:136
     // Gram side: Z Z' (R x R) or Z'Z (n x n), whichever is smaller unless forced
-    h->gene_side = !skip && (prm->gram_side == 2 || (prm->gram_side == 0 && h->R > n));
+    h->gene_side = !skip && (prm->gram_side == 2 || (prm->gram_side == 0 && h->R > h->n_total));
     if (h->gene_side) {
-        if (h->world != 1) throw Error(RUVIII_ERR_UNSUPPORTED, "the gene-side Gram couples gene shards: one GPU only for now");
         if (h->n_alpha_rows > h->kk)
             throw Error(RUVIII_ERR_UNSUPPORTED, "gene-side Gram produces the leading max(k) rows of fullalpha only");
-        if (h->kk + 1 > n) throw Error(RUVIII_ERR_INVALID, "k exceeds the number of genes");
+        if (h->kk + 1 > h->n_total) throw Error(RUVIII_ERR_INVALID, "k exceeds the number of genes");
     }
-    h->gorder = h->gene_side ? n : h->R;
+    h->gorder = h->gene_side ? h->n_total : h->R;
     if (!skip) h->n_keep = std::min(h->gorder, std::max(h->n_alpha_rows, h->kk + 1));
+    // Gene side over several shards: Z'Z couples the gene shards, so the contraction is re-split over the ROWS of Z:
+    // an all-to-all hands rank j the rows [zrow[j], zrow[j+1]) of every shard's Z, rank j forms the full
+    // n_total x n_total partial Gram of those rows (balanced, symmetric half only) and the partials are allreduced.
+    h->zrow.assign(h->world + 1, 0);
+    for (int j = 0; j <= h->world; ++j) h->zrow[j] = (int)((int64_t)h->R * j / h->world);
 
     // ---- output slots ----
     h->k_eff.resize(nk);
@@ -474,8 +498,19 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.Y0.alloc((size_t)R * s.ld);
             const int GO = h->gorder;
             const int64_t ldR = round_up(R, kRowAlign);
-            if (h->gene_side) s.Zt.alloc((size_t)s.n * ldR);
-            s.gp = h->gene_side ? plan_gram(GO, (int)ldR, h->n_sms, h->gram_impl) : plan_gram(R, (int)s.ld, h->n_sms, h->gram_impl);
+            int64_t ldZt = ldR;                        // pitch of t(Z): the rows of Z this shard contracts, padded
+            if (h->gene_side) {
+                const int j = h->rank0 + i;
+                const int rows_me = h->zrow[j + 1] - h->zrow[j];
+                ldZt = round_up(std::max(rows_me, 1), kRowAlign);
+                s.Zt.alloc((size_t)h->n_total * ldZt);                     // zeroed: the padding columns stay zero
+                if (h->world > 1) {
+                    size_t stage = 0;
+                    for (int q = 0; q < h->world; ++q) stage += (size_t)round_up(std::max(h->gn[q], 1), kRowAlign);
+                    s.Zstage.alloc((size_t)std::max(rows_me, 1) * stage, false);
+                }
+            }
+            s.gp = h->gene_side ? plan_gram(GO, (int)ldZt, h->n_sms, h->gram_impl) : plan_gram(R, (int)s.ld, h->n_sms, h->gram_impl);
             s.gram_ws.alloc(s.gp.workspace_bytes / sizeof(double), false);
             std::vector<int2> tm(s.gp.n_tiles);
             fill_gram_tile_map(s.gp, tm.data());
@@ -500,7 +535,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (h->n_alpha_rows > h->kk) s.falpha.alloc((size_t)h->n_alpha_rows * s.ld);
             s.W.alloc(std::max<size_t>(w_total, 1));
             if (s.gp.impl == 2) {
-                launch_gram_tma_prepare(s.gp, h->gene_side ? s.Zt.p : s.Y0.p, h->gene_side ? ldR : s.ld, s.tmap);
+                launch_gram_tma_prepare(s.gp, h->gene_side ? s.Zt.p : s.Y0.p, h->gene_side ? ldZt : s.ld, s.tmap);
             }
             if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
@@ -669,16 +704,53 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             h->launches += 1;
             rec(E_RESIDOP);
             const int GO = h->gorder;
-            for_shards([&](Shard& s) {
-                if (h->gene_side) {
-                    const int64_t ldR = round_up(R, kRowAlign);
-                    launch_transpose(s.Y0.p, s.ld, R, s.n, s.Zt.p, ldR, s.stream);
-                    launch_gram(s.gp, s.Zt.p, ldR, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
-                } else {
-                    launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+            if (h->gene_side) {
+                // t(Z) restricted to the rows this shard contracts.  One shard: all of Z.  Several: all-to-all of row
+                // blocks first (every shard sends rows [zrow[q], zrow[q+1]) of its gene slab to rank q).
+                if (h->world > 1) {
+                    RUVIII_NCCL_CHECK(ncclGroupStart());
+                    for (size_t i = 0; i < h->shards.size(); ++i) {
+                        Shard& s = h->shards[i];
+                        const int j = h->rank0 + (int)i;
+                        const int rows_me = h->zrow[j + 1] - h->zrow[j];
+                        size_t off = 0;
+                        for (int q = 0; q < h->world; ++q) {
+                            const int rows_q = h->zrow[q + 1] - h->zrow[q];
+                            const int64_t ld_q = round_up(std::max(h->gn[q], 1), kRowAlign);
+                            if (rows_q > 0)
+                                RUVIII_NCCL_CHECK(ncclSend(s.Y0.p + (size_t)h->zrow[q] * s.ld, (size_t)rows_q * s.ld, ncclDouble, q,
+                                                           s.comm, s.stream));
+                            if (rows_me > 0)
+                                RUVIII_NCCL_CHECK(ncclRecv(s.Zstage.p + off, (size_t)rows_me * ld_q, ncclDouble, q, s.comm, s.stream));
+                            off += (size_t)rows_me * ld_q;
+                        }
+                    }
+                    RUVIII_NCCL_CHECK(ncclGroupEnd());
                 }
-            });
-            h->launches += h->gene_side ? 3 : 2;
+                for (size_t i = 0; i < h->shards.size(); ++i) {
+                    Shard& s = h->shards[i];
+                    RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                    const int j = h->rank0 + (int)i;
+                    const int rows_me = h->zrow[j + 1] - h->zrow[j];
+                    const int64_t ldZt = round_up(std::max(rows_me, 1), kRowAlign);
+                    if (h->world == 1) {
+                        launch_transpose(s.Y0.p, s.ld, R, s.n, s.Zt.p, ldZt, s.stream);
+                    } else {
+                        size_t off = 0;
+                        for (int q = 0; q < h->world; ++q) {
+                            const int64_t ld_q = round_up(std::max(h->gn[q], 1), kRowAlign);
+                            launch_transpose(s.Zstage.p + off, ld_q, rows_me, h->gn[q], s.Zt.p + (size_t)h->goff[q] * ldZt, ldZt,
+                                             s.stream);
+                            off += (size_t)rows_me * ld_q;
+                        }
+                    }
+                    launch_gram(s.gp, s.Zt.p, ldZt, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
+                }
+                h->launches += 2 + h->world;
+            } else {
+                for_shards([&](Shard& s) { launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream); });
+                h->launches += 2;
+            }
             rec(E_GRAM);
             fork_gather();
             {
@@ -705,7 +777,8 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             rec(E_BCAST);
             for_shards([&](Shard& s) {
                 if (h->gene_side) {
-                    launch_alpha_from_v(s.U.p, s.evals.p, s.n, kk, kp, s.ld, s.alpha.p, s.stream);
+                    const int j = h->rank0 + (int)(&s - h->shards.data());      // this shard's rows of V
+                    launch_alpha_from_v(s.U.p + (size_t)h->goff[j] * kp, s.evals.p, s.n, kk, kp, s.ld, s.alpha.p, s.stream);
                     launch_alpha_finalize(s.alpha.p, 1, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
                 } else {
                     launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);

@@ -102,21 +102,35 @@ def make_config(name, scale_rows=1.0):
     return make_problem(**c)
 
 
-def make_dense_design(m, n, group_size=3, n_ctl=1000, k=10, seed=BASE_SEED + 30, q=24):
+def make_dense_design(m, n, group_size=3, n_ctl=1000, k=10, seed=BASE_SEED + 30, q=24, cols=None, block=1024):
     """Dense replicate design: every row belongs to a replicate group of ``group_size``
     technical replicates (last group takes the remainder, minimum 2), no extra PRPS rows.  Returns
-    (Y m x n row-major, group_ids int32[m], ctl bool[n])."""
+    (Y m x n row-major, group_ids int32[m], ctl bool[n]).
+
+    Row factors come from ``seed``; gene columns are generated in blocks of ``block`` genes, block b from
+    ``seed + 1 + b``, so ``cols = (g0, g1)`` returns exactly the columns [g0, g1) of the full matrix without
+    generating the rest (one rank of a gene-sharded bench holds only its slab); ctl is restricted likewise."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_groups = max(1, m // group_size)
     gid = np.minimum(np.arange(m) // group_size, n_groups - 1).astype(np.int32)
-    mu_g = np.clip(rng.normal(8.0, 2.0, n), 0.0, 18.0)
     s = 1.5 * 0.85 ** np.arange(q)
-    alpha_star = rng.normal(0.0, 1.0, (q, n)) * s[:, None]
-    signal = rng.normal(0.0, 1.0, (n_groups, 6)) @ rng.normal(0.0, 0.5, (6, n))   # per-group biology
-    Y = rng.normal(0.0, 0.4, (m, n))
-    Y += mu_g[None, :]
-    Y += signal[gid]
-    Y += rng.normal(0.0, 1.0, (m, q)) @ alpha_star          # unwanted variation differs between replicates
+    group_factors = rng.normal(0.0, 1.0, (n_groups, 6))[gid]          # per-group biology
+    W_star = rng.normal(0.0, 1.0, (m, q))                             # unwanted variation differs between replicates
     ctl = np.zeros(n, dtype=bool)
     ctl[rng.choice(n, size=min(n_ctl, n), replace=False)] = True
-    return Y, gid, ctl
+    g0, g1 = (0, n) if cols is None else cols
+    Y = np.empty((m, g1 - g0), dtype=np.float64)
+    for b in range(g0 // block, (g1 + block - 1) // block):
+        lo, hi = b * block, min((b + 1) * block, n)
+        rb = np.random.Generator(np.random.PCG64(seed + 1 + b))
+        w = hi - lo
+        mu_g = np.clip(rb.normal(8.0, 2.0, w), 0.0, 18.0)
+        alpha_star = rb.normal(0.0, 1.0, (q, w)) * s[:, None]
+        loadings = rb.normal(0.0, 0.5, (6, w))
+        blk = rb.normal(0.0, 0.4, (m, w))
+        blk += mu_g[None, :]
+        blk += group_factors @ loadings
+        blk += W_star @ alpha_star
+        a, z = max(lo, g0), min(hi, g1)
+        Y[:, a - g0:z - g0] = blk[:, a - lo:z - lo]
+    return Y, gid, ctl[g0:g1]

@@ -42,6 +42,58 @@ def test_single_process_gene_shards(ndev):
     assert O.rel_frob(O.align_rows_sign(many["fullalpha"], one["fullalpha"]), one["fullalpha"]) < 1e-8
 
 
+@pytest.mark.parametrize("ndev", [2, 4, 8])
+def test_gene_side_gram_over_shards(ndev):
+    """BASELINE config 5's regime (more replicate rows than genes) on several GPUs: t(Z) Z couples the gene shards, so
+    the engine re-splits the contraction over the rows of Z with an all-to-all and allreduces the n x n partials."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    from ruviii_b200.synth import make_dense_design
+    Y, gid, ctl = make_dense_design(m=1203, n=389, group_size=3, n_ctl=120, k=6, seed=31)     # ragged shards and row blocks
+    PS = np.zeros((0, 389))
+    with rv.Engine(devices=[0]) as e1:
+        one = e1.normalise(_cabi.make_params(), Y, PS, gid, ctl, [3, 6], want_fullalpha=True, want_W=True)
+    with rv.Engine(devices=list(range(ndev))) as en:
+        many = en.normalise(_cabi.make_params(), Y, PS, gid, ctl, [3, 6], want_fullalpha=True, want_W=True)
+        assert many["info"].n_shards == ndev and many["info"].gram_side == 2 and many["info"].gram_order == 389
+    ref = O.ruvIII_literal(Y.T, ["g%d" % g for g in gid], PS, [], ctl, 6, apply_log=False)
+    for res in (one, many):
+        assert O.rel_frob(res["newY"][1], ref["newY"]) < 1e-9
+    assert O.rel_frob(many["newY"][0], one["newY"][0]) < 1e-10
+    assert O.rel_frob(O.align_rows_sign(many["fullalpha"], one["fullalpha"]), one["fullalpha"]) < 1e-8
+
+
+def test_torchrun_two_ranks_gene_side(tmp_path):
+    """One process per GPU: the per-rank gene counts travel through the plan-time allreduce."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    code = (
+        "import os, numpy as np, torch.distributed as dist\n"
+        "from ruviii_b200 import _cabi\n"
+        "from ruviii_b200.sharding import engine_from_torch_distributed, gene_range\n"
+        "from ruviii_b200.synth import make_dense_design\n"
+        "from oracle import ruviii_oracle as O\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "Y, gid, ctl = make_dense_design(m=903, n=301, group_size=3, n_ctl=90, k=5, seed=33)\n"
+        "g0, g1 = gene_range(301, r, w)\n"
+        "eng = engine_from_torch_distributed()\n"
+        "res = eng.normalise(_cabi.make_params(), np.ascontiguousarray(Y[:, g0:g1]), np.zeros((0, g1 - g0)), gid, ctl[g0:g1], [5])\n"
+        "assert res['info'].gram_side == 2 and res['info'].gram_order == 301, (res['info'].gram_side, res['info'].gram_order)\n"
+        "ref = O.ruvIII_literal(Y.T, ['g%d' % g for g in gid], np.zeros((0, 301)), [], ctl, 5, apply_log=False)\n"
+        "err = O.rel_frob(res['newY'][0], ref['newY'][:, g0:g1])\n"
+        "print('rank', r, 'err', err)\n"
+        "assert err < 1e-9\n"
+        "eng.close(); dist.destroy_process_group()\n")
+    script = tmp_path / "gene_side_rank.py"
+    script.write_text(code)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", str(script)]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-2500:])
+
+
 def test_torchrun_two_ranks_bench():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

@@ -90,6 +90,75 @@ def test_gene_sharded_exchange_matches_unsharded_oracle(tmp_path, world, first_o
         assert np.array_equal(np.load(tmp_path / "W_0.npy"), np.load(tmp_path / ("W_%d.npy" % r)))
 
 
+def _worker_gene_side(rank, world, port, outdir):
+    """The gene-side regime over several shards, as engine.cu::do_run does it: all-to-all of row blocks of Z, a full
+    n x n partial Gram per rank over its rows, allreduce, eigensolve on rank 0, alpha = diag(sigma) V' (appendix A-5)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import ruviii_oracle as O
+    from ruviii_b200.synth import make_dense_design
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n, k = 61, 3
+    Y, gid, ctl = make_dense_design(m=150, n=n, group_size=3, n_ctl=20, k=k, seed=41)
+    Ys, ctls = shard_columns(Y, rank, world), shard_columns(ctl, rank, world)
+    m = Y.shape[0]
+    active, Z, pcols = O._group_mean_residual(Ys, gid)           # residual rows of this gene slab (R x n_loc)
+    R = Z.shape[0]
+    zrow = [R * j // world for j in range(world + 1)]            # the row split of engine.cu (h->zrow)
+    edges = [gene_range(n, j, world) for j in range(world)]
+    rows_me = zrow[rank + 1] - zrow[rank]
+    # exchange 1: all-to-all -- rank q receives rows [zrow[q], zrow[q+1]) of every slab
+    stage = [torch.zeros((rows_me, b - a), dtype=torch.float64) for a, b in edges]
+    reqs = []
+    for q in range(world):
+        blk = torch.from_numpy(np.ascontiguousarray(Z[zrow[q]:zrow[q + 1]]))
+        if q == rank:
+            stage[q].copy_(blk)
+        else:
+            reqs.append(dist.isend(blk, dst=q))
+            reqs.append(dist.irecv(stage[q], src=q))
+    for r_ in reqs:
+        r_.wait()
+    Zrows = np.concatenate([t.numpy() for t in stage], axis=1)   # rows_me x n: all genes of my rows
+    G = torch.from_numpy(Zrows.T @ Zrows)                        # exchange 2: allreduce of the n x n partials
+    dist.all_reduce(G)
+    n_ctl = torch.tensor([float(ctls.sum())], dtype=torch.float64)
+    dist.all_reduce(n_ctl)
+    assert min(m - pcols, int(n_ctl.item())) >= k
+    V = torch.zeros((n, k), dtype=torch.float64)
+    lam = torch.zeros(k, dtype=torch.float64)
+    if rank == 0:
+        w, Q = np.linalg.eigh(G.numpy())
+        top = np.argsort(w)[::-1][:k]
+        V, lam = torch.from_numpy(np.ascontiguousarray(Q[:, top])), torch.from_numpy(np.ascontiguousarray(w[top]))
+    dist.broadcast(V, src=0)                                     # exchange 3: V and the eigenvalues
+    dist.broadcast(lam, src=0)
+    a, b = edges[rank]
+    alpha = np.sqrt(lam.numpy())[:, None] * V.numpy()[a:b].T     # this shard's columns of diag(sigma) V'
+    ac = alpha[:, ctls]
+    AG = torch.from_numpy(np.concatenate([(Ys[:, ctls] @ ac.T).ravel(), (ac @ ac.T).ravel()]))
+    dist.all_reduce(AG)                                          # exchange 4: [A | Gm]
+    A = AG.numpy()[:m * k].reshape(m, k)
+    Gm = AG.numpy()[m * k:].reshape(k, k)
+    A = A - A.mean(axis=0, keepdims=True)
+    W = np.linalg.solve(Gm, A.T).T
+    np.save(os.path.join(outdir, "newY_%d.npy" % rank), Ys - W @ alpha)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gene_side_row_resplit_matches_unsharded_oracle(tmp_path, world):
+    import torch.multiprocessing as mp
+    from oracle import ruviii_oracle as O
+    from ruviii_b200.synth import make_dense_design
+    mp.spawn(_worker_gene_side, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    Y, gid, ctl = make_dense_design(m=150, n=61, group_size=3, n_ctl=20, k=3, seed=41)
+    ref = O.ruvIII_literal(Y.T, ["g%d" % g for g in gid], np.zeros((0, 61)), [], ctl, 3, apply_log=False)
+    newY = assemble_columns([np.load(tmp_path / ("newY_%d.npy" % r)) for r in range(world)])
+    assert O.rel_frob(newY, ref["newY"]) < 1e-10
+
+
 def test_gene_ranges_tile_the_genome():
     for n in (1, 7, 403, 20000):
         for world in (1, 2, 3, 4, 8):
