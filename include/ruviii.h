@@ -151,6 +151,15 @@ int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count);
  * only reuse mechanism).  rows x n row-major; must be called after ruviii_plan and before ruviii_run. */
 int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows);
 
+/* ruv::RUV1 pre-step (ruvIII.R:116; fastruvIII.R:133-134 applies it to Y and to replicate.data).  ruv is not vendored in the
+ * reference tree; the statement restated here is ruv 0.9.7.1's
+ *     Y - Y[, ctl] %*% t(eta[, ctl]) %*% solve(eta[, ctl] %*% t(eta[, ctl])) %*% eta       with eta q x n.
+ * eta: q x n row-major, i.e. the bytes of R's n x q gene-wise design matrix, the intercept column already included by
+ * the caller when include.intercept = TRUE (design.matrix()).  Sticky: it applies to every later plan / ruviii_normalise
+ * on this handle (n must match; with one process per GPU pass the local gene slab of eta).  eta = NULL or q = 0 clears
+ * it (the reference default eta = NULL: RUV1 is the identity).  q <= 32.  A singular eta_c eta_c' is RUVIII_ERR_SINGULAR. */
+int ruviii_set_eta(ruviii_handle* h, const double* eta, int32_t q, int32_t n);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

@@ -20,7 +20,8 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_fast_residop", "ruviii_probe",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta",
+    "ruviii_fast_residop", "ruviii_probe",
 ]
 
 
@@ -92,6 +93,7 @@ def load_library():
     lib.ruviii_host_free.restype = None
     lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
+    lib.ruviii_set_eta.argtypes = [H, vp, C.c_int32, C.c_int32]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
     lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     for name in SYMBOLS:
@@ -231,6 +233,14 @@ class Engine:
     def set_fullalpha(self, fullalpha):
         fa = _rowmajor(fullalpha, "fullalpha")
         self._check(self._lib.ruviii_set_fullalpha(self._h, _ptr(fa), fa.shape[0]))
+
+    def set_eta(self, eta):
+        """ruv::RUV1 pre-step (ruvIII.R:116): eta is q x n row-major, intercept row included by the caller; None clears."""
+        if eta is None:
+            self._check(self._lib.ruviii_set_eta(self._h, None, 0, 0))
+            return
+        e = _rowmajor(eta, "eta")
+        self._check(self._lib.ruviii_set_eta(self._h, _ptr(e), e.shape[0], e.shape[1]))
 
     def eigenvalues(self, count):
         out = np.empty(count, dtype=np.float64)

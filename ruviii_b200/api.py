@@ -107,10 +107,25 @@ def _prepare(se_obj, assay_name, replicate_data, ctl, inputcheck, n_rows_for_che
     return assay, Y, PS, ctl, n, m1
 
 
+def _design_matrix_t(eta, n, include_intercept):
+    """t(design.matrix(eta, include.intercept)) of ruv::RUV1: q x n with one column per gene.  A single number means
+    "intercept only" (RUV1: ``if (length(eta) == 1) eta = matrix(1, n, 1)``); a gene-wise matrix may be given as n x q
+    (R's orientation) or q x n; the row of ones is prepended unless a constant row is already present."""
+    e = np.asarray(eta, dtype=np.float64)
+    if e.ndim == 0 or e.size == 1:
+        return np.ones((1, n))
+    e = np.atleast_2d(e)
+    if e.shape[1] != n and e.shape[0] == n:
+        e = e.T
+    if e.shape[1] != n:
+        raise ValueError("eta must have one row per gene (n x q)")
+    if include_intercept and not any(np.ptp(row) == 0 and row[0] != 0 for row in e):
+        e = np.vstack([np.ones((1, n)), e])
+    return np.ascontiguousarray(e)
+
+
 def _core(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, ctl, ks, eta, apply_average_rep,
-          fullalpha, return_info, inputcheck, want_ps):
-    if eta is not None:
-        raise NotImplementedError("eta != NULL (ruv::RUV1 pre-step, ruvIII.R:116) is not implemented in the CUDA engine")
+          fullalpha, return_info, inputcheck, want_ps, include_intercept=True):
     n_ps = len(replicate_data.row_names) if isinstance(replicate_data, ReplicateData) else 0
     m1_guess = np.asarray(se_obj.assay(assay_name)).shape[1]
     assay, Y, PS, ctl, n, m1 = _prepare(se_obj, assay_name, replicate_data, ctl, inputcheck,
@@ -122,7 +137,17 @@ def _core(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, ctl
     params = make_params(mode=mode, apply_log=apply_log, pseudo_count=pseudo_count, average_rep=apply_average_rep,
                          n_alpha_rows=-1 if (return_info and mode == MODE_STACKED) else 0,   # fastruvIII.R:171: k rows
                          want_ps_rows=want_ps)
+    eta_t = None if eta is None else _design_matrix_t(eta, n, include_intercept)
     eng = get_engine()
+    eng.set_eta(eta_t)                                                                  # ruvIII.R:116 RUV1(Y, eta, ctl)
+    try:
+        return _core_run(eng, params, Y, PS, groups, ctl, ks, m1, n, fullalpha, return_info, want_ps, apply_average_rep)
+    finally:
+        if eta is not None:
+            eng.set_eta(None)
+
+
+def _core_run(eng, params, Y, PS, groups, ctl, ks, m1, n, fullalpha, return_info, want_ps, apply_average_rep):
     if fullalpha is None:
         res = eng.normalise(params, Y, PS, groups, ctl, ks, want_fullalpha=return_info, want_W=return_info,
                             want_ps=want_ps)
@@ -161,7 +186,7 @@ def _single(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, c
     want_ps = (mode == MODE_STACKED) and not save_se_obj     # t(newY) / newY carry the PRPS rows too (ruvIII.R:192,195)
     _printColoredMessage("### Performing the RUVIII normalization", verbose)
     res, m1, n = _core(mode, se_obj, assay_name, apply_log, pseudo_count, replicate_data, ctl, [int(k)], eta,
-                       apply_average_rep, fullalpha, return_info, inputcheck, want_ps)
+                       apply_average_rep, fullalpha, return_info, inputcheck, want_ps, include_intercept)
     info = res["info"]
     undefined = info.no_replicates                   # ruvIII.R:128-129 leaves W / fullalpha undefined
     W = None if res["W"] is None else res["W"][0]
@@ -215,7 +240,7 @@ def ruvIIIMultipleK(se_obj, assay_name, apply_log=True, pseudo_count=1, replicat
     ks = [int(x) for x in np.atleast_1d(k)]
     want_ps = not save_se_obj
     res, m1, n = _core(MODE_STACKED, se_obj, assay_name, apply_log, pseudo_count, replicate_data, ctl, ks, eta,
-                       apply_average_rep, fullalpha, return_info, inputcheck, want_ps)
+                       apply_average_rep, fullalpha, return_info, inputcheck, want_ps, include_intercept)
     if return_info and res["info"].no_replicates:
         raise RuntimeError("object 'W' not found: ncol(M) >= m, no replicates (ruvIII.R:128-129 with return.info)")
     Ws = res["W"] if res["W"] is not None else [None] * len(ks)

@@ -139,8 +139,9 @@ struct Shard {
     int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
+    DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
     DevBuf<int2> tile_map;
-    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows;
+    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1;
     TopkWork topk{};
     alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
     alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
@@ -197,6 +198,10 @@ struct ruviii_handle {
     // the R Helmert rows over the ranks after the all-to-all (rank j contracts rows [zrow[j], zrow[j+1]))
     std::vector<int> gn, goff, zrow;
     int n_total = 0;                    // genes over all shards of all processes
+    // ruv::RUV1 pre-step (ruvIII.R:116): eta as handed over by ruviii_set_eta (q x n row-major, host copy), sticky
+    std::vector<double> eta_host;
+    int eta_q = 0, eta_n = 0;
+    bool eta_applied = false;           // once per upload, like the log transform
     double eig_tol = 1e-13;
 
     ~ruviii_handle();
@@ -214,7 +219,8 @@ ruviii_handle::~ruviii_handle() {
         if (s.ev_gather) cudaEventDestroy(s.ev_gather);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage};
+                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
+                                  &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -224,6 +230,7 @@ ruviii_handle::~ruviii_handle() {
         s.topk_state.release();
         s.all_start.release();
         s.all_rows.release();
+        s.status1.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
@@ -334,7 +341,10 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
                                         "non-conformable arguments (fastruvIII.R:179-180)");
     if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
     h->prm = *prm;
-    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = false;
+    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = false;
+    if (h->eta_q > 0 && h->eta_n != n)
+        throw Error(RUVIII_ERR_INVALID, "eta has " + std::to_string(h->eta_n) + " columns, the assay has " + std::to_string(n) +
+                                            " genes (ruviii_set_eta)");
     h->m1 = m1;
     h->n_ps = n_ps;
     h->m = m1 + n_ps;
@@ -486,10 +496,27 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
                 RUVIII_CUDA_CHECK(cudaMemcpy(s.all_rows.p, all_rows.data(), all_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
             s.avg.alloc((size_t)nk * h->p * s.ld, false);
         }
-        if (!skip) {
+        s.ldc = round_up(std::max(s.n_ctl, 1), kRowAlign);
+        if (!skip || h->eta_q > 0) {
             s.ctl_idx.alloc(std::max<size_t>(cidx.size(), 1));
             if (!cidx.empty())
                 RUVIII_CUDA_CHECK(cudaMemcpy(s.ctl_idx.p, cidx.data(), cidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        if (h->eta_q > 0) {
+            const int q = h->eta_q, qp = pad_k(q);
+            s.eta.alloc((size_t)qp * s.ld);
+            RUVIII_CUDA_CHECK(cudaMemcpy2D(s.eta.p, s.ld * 8, h->eta_host.data() + s.g0, (size_t)n * 8, (size_t)s.n * 8, q,
+                                           cudaMemcpyHostToDevice));
+            s.eta_t.alloc((size_t)qp * s.ld);
+            s.etacT.alloc((size_t)std::max(s.n_ctl, 1) * qp);
+            s.AG1.alloc((size_t)h->m * qp + (size_t)qp * qp);
+            s.At1.alloc((size_t)h->m * qp);
+            s.Linv1.alloc((size_t)qp * qp);
+            s.cm1.alloc(qp);
+            s.Yc1.alloc((size_t)h->m * s.ldc, false);
+            s.status1.alloc(4);
+        }
+        if (!skip) {
             s.grp_start.alloc(grp_start.size());
             s.grp_rows.alloc(std::max<size_t>(grp_rows.size(), 1));
             RUVIII_CUDA_CHECK(cudaMemcpy(s.grp_start.p, grp_start.data(), grp_start.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -527,7 +554,6 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.at.alloc((size_t)kp * s.ld);
             s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
             s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp);
-            s.ldc = round_up(std::max(s.n_ctl, 1), kRowAlign);
             s.Yc.alloc((size_t)h->rows_w * s.ldc, false);
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
@@ -599,6 +625,7 @@ void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS,
     h->info.ms_h2d = ms;
     h->uploaded = true;
     h->logged = false;
+    h->eta_applied = false;
     h->ran = false;
 }
 
@@ -642,6 +669,50 @@ void eigensolve(ruviii_handle* h) {
     h->launches += 1;
 }
 
+// ruv::RUV1 (ruvIII.R:116; fastruvIII.R:133-134 applies it to Y and to replicate.data): every row y of the stacked matrix
+// becomes y - y[ctl] eta_c' (eta_c eta_c')^-1 eta.  Same shape as the RUV-III update itself with eta in the role of alpha
+// and no centring, so it reuses K5/K6: A1 = Y[, ctl] eta_c' and eta_c eta_c' (allreduced over gene shards), Cholesky,
+// then an in-place rank-q update of the device copies of Y and replicate.data.
+void apply_ruv1(ruviii_handle* h) {
+    const int q = h->eta_q, qp = pad_k(q), m = h->m, m1 = h->m1;
+    int slot0[kMaxK + 1] = {0};
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
+        launch_alpha_finalize(s.eta.p, 1, qp, s.n, s.ld, s.eta.p, s.ctl_idx.p, s.n_ctl, s.etacT.p, s.stream);
+        launch_ctl_gather(src, m, s.ctl_idx.p, s.n_ctl, s.Yc1.p, s.ldc, 0, 0.0, s.stream);
+        launch_ctl_products(src, m, s.ctl_idx.p, s.n_ctl, s.etacT.p, qp, s.AG1.p, s.AG1.p + (size_t)m * qp,
+                            s.n_ctl > 0 ? s.Yc1.p : nullptr, s.ldc, s.stream);
+    }
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.AG1.p);
+        allreduce_sum(h, b, (size_t)m * qp + (size_t)qp * qp);
+    }
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const double* A = s.AG1.p;
+        launch_chol_solve(A, m, 0, s.AG1.p + (size_t)m * qp, q, qp, s.Linv1.p, s.cm1.p, s.status1.p, s.stream);   // mu_rows = 0: no centring
+        launch_atilde(A, m, s.cm1.p, s.Linv1.p, q, qp, s.At1.p, s.stream);
+        launch_alpha_tilde(s.eta.p, s.Linv1.p, q, qp, s.n, s.ld, s.eta_t.p, s.stream);
+        if (m1 > 0)
+            launch_update_smem(s.Y.p, s.ld, m1, s.n, s.At1.p, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.Y.p, s.ld, 0, s.stream);
+        if (h->n_ps > 0)
+            launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At1.p + (size_t)m1 * qp, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.PS.p,
+                          s.ld, 0, s.stream);
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[32 + i], s.status1.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    }
+    h->launches += 8 + (h->n_ps > 0 ? 1 : 0);
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[i].device));
+        spin_sync(h->shards[i].stream);
+        if (h->h_flags[32 + i] != 0)
+            throw Error(RUVIII_ERR_SINGULAR, "etac %*% t(etac) is not positive definite at pivot " +
+                                                 std::to_string(h->h_flags[32 + i]) + " (solve() in ruv::RUV1 would fail)");
+    }
+}
+
 void do_run(ruviii_handle* h, ruviii_info* info_out) {
     if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_run needs ruviii_plan and ruviii_upload first");
     const bool fast = h->prm.mode == RUVIII_MODE_FAST;
@@ -667,6 +738,10 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         for_shards([&](Shard& s) { launch_log2_inplace(s.Y.p, s.ld, h->m1, s.n, h->prm.pseudo_count, s.stream); });
         h->logged = true;
         h->launches += 1;
+    }
+    if (h->eta_q > 0 && !h->eta_applied) {
+        apply_ruv1(h);
+        h->eta_applied = true;
     }
     rec(E_LOG);
     if (skip) {
@@ -994,7 +1069,7 @@ const void* host_pinned(const void* p) {
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* newY_out, const double* newY_ps_out) {
     const int off = env_int("RUVIII_NO_PIPELINE", 0);
     const bool skip = h->no_replicates || h->kk == 0;
-    return !off && !skip && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
+    return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
            h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;
 }
 
@@ -1341,6 +1416,23 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
         }
         for (int i = 0; i <= kMaxK; ++i) if (h->slot_of_k[i] < 0) h->slot_of_k[i] = 0;
         h->have_user_alpha = true;
+    });
+}
+
+int ruviii_set_eta(ruviii_handle* h, const double* eta, int32_t q, int32_t n) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!eta || q <= 0) {
+            h->eta_host.clear();
+            h->eta_q = h->eta_n = 0;
+        } else {
+            if (n <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_eta: n <= 0");
+            if (q > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "eta with more than 32 rows is not supported");
+            h->eta_host.assign(eta, eta + (size_t)q * n);
+            h->eta_q = q;
+            h->eta_n = n;
+        }
+        h->planned = false;                 // the plan sizes the RUV1 buffers
     });
 }
 

@@ -318,7 +318,7 @@ chol_solve_kernel(const double* __restrict__ A, int rows_w, int mu_rows, const d
         if (tid < kp) {
             double t = 0.0;
             for (int q = 0; q < stride; ++q) t += red[q * kp + tid];
-            colmean[tid] = t / (double)mu_rows;
+            colmean[tid] = mu_rows > 0 ? t / (double)mu_rows : 0.0;   // mu_rows = 0: no centring (RUV1)
         }
     }
     const int r = tid / kMaxK, c = tid % kMaxK;       // 32 x 32 threads, one per matrix element

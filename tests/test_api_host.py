@@ -44,8 +44,21 @@ def test_shape_validation_happens_before_the_gpu(small):
     with pytest.raises(ValueError, match="one column per gene"):
         rv.ruvIII(se, "logcounts", replicate_data=rv.ReplicateData(p.replicate_data[:, :-1], p.replicate_names),
                   ctl=p.ctl, k=1, verbose=False)
-    with pytest.raises(NotImplementedError):
-        rv.ruvIII(se, "logcounts", replicate_data=rd, ctl=p.ctl, k=1, eta=np.ones((1, 50)), verbose=False)
+    with pytest.raises(ValueError, match="one row per gene"):
+        rv.ruvIII(se, "logcounts", replicate_data=rd, ctl=p.ctl, k=1, eta=np.ones((2, 49)), verbose=False)
+
+
+def test_eta_design_matrix_follows_ruv1():
+    """ruv::RUV1 (called at ruvIII.R:116): a single number means intercept only; a gene-wise matrix (n x q, R's orientation, or
+    q x n) gets a column of ones when include.intercept and no constant column is already there (design.matrix)."""
+    n = 7
+    assert api._design_matrix_t(1, n, True).tolist() == [[1.0] * n]
+    x = np.arange(n, dtype=float)
+    e = api._design_matrix_t(x[:, None], n, True)                  # n x 1, R's orientation
+    assert e.shape == (2, n) and e[0].tolist() == [1.0] * n and np.array_equal(e[1], x)
+    assert api._design_matrix_t(x[None, :], n, False).shape == (1, n)
+    both = np.vstack([np.ones(n), x])
+    assert api._design_matrix_t(both, n, True).shape == (2, n)     # already has its intercept
 
 
 def test_no_gpu_means_error_not_fallback(small):

@@ -249,6 +249,44 @@ def test_user_supplied_fullalpha(engine):
     assert O.rel_frob(out["W"], ref2["W"]) < 1e-8
 
 
+@pytest.mark.parametrize("mode", ["ruvIII", "fastruvIII"])
+def test_eta_ruv1_prestep(engine, mode):
+    """eta != NULL (ruvIII.R:116, fastruvIII.R:133-134): ruv::RUV1 removes gene-wise covariates through the control genes
+    from every row of Y and replicate.data before anything else."""
+    p = make_problem(m1=150, n=1203, groups=20, rep=3, n_ctl=150, k=4, seed=611)
+    rng = np.random.default_rng(5)
+    eta = np.vstack([rng.normal(size=1203), np.linspace(-1, 1, 1203) ** 2])          # two gene-wise covariates (GC, length ...)
+    se = rv.SummarizedExperiment(assays={"logcounts": p.assay}, col_names=p.sample_names)
+    rd = rv.ReplicateData(p.replicate_data, p.replicate_names)
+    if mode == "ruvIII":
+        out = rv.ruvIII(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl, k=4, eta=eta.T, return_info=True,
+                        save_se_obj=False, verbose=False)
+        ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 4, apply_log=False, eta=eta)
+        plain = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 4, apply_log=False)
+    else:
+        out = rv.fastruvIII(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl, k=4, eta=eta.T, return_info=True,
+                            save_se_obj=False, verbose=False)
+        ref = O.fastruvIII_literal(p.assay, p.replicate_data, p.replicate_names, p.ctl, 4, apply_log=False, eta=eta)
+        plain = O.fastruvIII_literal(p.assay, p.replicate_data, p.replicate_names, p.ctl, 4, apply_log=False)
+    assert O.rel_frob(out["newY"], ref["newY"]) < TOL_NEWY
+    assert O.rel_frob(plain["newY"], ref["newY"]) > 1e-4                              # eta really changes the answer
+    assert O.rel_frob(out["W"] @ out["fullalpha"][:4], ref["W"] @ ref["fullalpha"][:4]) < TOL_NEWY * 10
+    # eta is cleared again: the next call without eta is the plain result
+    again = (rv.ruvIII if mode == "ruvIII" else rv.fastruvIII)(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl,
+                                                             k=4, return_info=True, save_se_obj=False, verbose=False)
+    assert O.rel_frob(again["newY"], plain["newY"]) < TOL_NEWY
+    # k = 0 still applies RUV1 (ruvIII.R:116 runs before :134-136); intercept only = eta given as a single number
+    k0 = rv.ruvIII(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl, k=0, eta=1, save_se_obj=False, verbose=False)
+    ref0 = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 0, apply_log=False,
+                            eta=np.zeros((0, 1203)))
+    assert O.rel_frob(k0.T, ref0["newY"]) < TOL_NEWY
+    # collinear covariates: solve() in RUV1 fails
+    with pytest.raises(rv.RuviiiError) as e:
+        rv.ruvIII(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl, k=2, eta=np.vstack([eta[0], eta[0]]).T,
+                  save_se_obj=False, verbose=False)
+    assert e.value.code == _cabi.ERR_SINGULAR
+
+
 def test_singular_control_block_is_an_error(engine):
     """solve(ac %*% t(ac)) fails in R when the control genes carry no unwanted variation (ruvIII.R:144)."""
     p = make_problem(m1=40, n=120, groups=4, rep=2, n_ctl=15, k=2, seed=11)
