@@ -17,6 +17,9 @@
 // start block, fixed summation orders, no atomics.
 #include "kernels.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace ruviii {
 
 namespace {
@@ -272,34 +275,43 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
     if (tid >= 32) return;
     const int lane = tid;
     int bad = 0;
-    for (int j = 0; j < B; ++j) {                       // right-looking Cholesky on the lower triangle
-        const double djj = L[j][j];
+    // Left-looking (Crout) Cholesky: column j of the factor is A[:, j] - L[:, :j] L[j, :j]' scaled by the pivot.  The
+    // inner product accumulates in registers and the loop only READS shared memory (own row: stride 33, conflict-free;
+    // row j: broadcast), so its loads pipeline; the right-looking form did a dependent shared-memory read-modify-write
+    // per term (~50 cycles each, 496 terms).
+    for (int j = 0; j < B; ++j) {
+        double v0 = L[lane][j], v1 = 0.0;
+        int q = 0;
+#pragma unroll 4
+        for (; q + 1 < j; q += 2) {
+            v0 = fma(-L[lane][q], L[j][q], v0);
+            v1 = fma(-L[lane][q + 1], L[j][q + 1], v1);
+        }
+        if (q < j) v0 = fma(-L[lane][q], L[j][q], v0);
+        const double v = v0 + v1;
+        const double djj = __shfl_sync(0xffffffffu, v, j);
         double rd = rsqrt(djj);
         if (!(djj > 1e-30)) { bad = j + 1; rd = 1.0; }
         __syncwarp();
-        const double lij = lane > j ? L[lane][j] * rd : (lane == j ? djj * rd : 0.0);
-        if (lane >= j) L[lane][j] = lij;
-        __syncwarp();
-#pragma unroll 4
-        for (int c = j + 1; c < B; ++c) {
-            const double lcj = L[c][j];                 // broadcast
-            if (lane >= c) L[lane][c] = fma(-lij, lcj, L[lane][c]);
-        }
+        L[lane][j] = lane > j ? v * rd : (lane == j ? djj * rd : 0.0);
+        if (lane == 0) W[0][j] = rd;                    // 1 / L[j][j], reused by the inversion (W is free by now)
         __syncwarp();
     }
-    // Li = L^-1: lane owns column `lane`; row i of L is read as a broadcast-free strided load (stride 33)
+    // Li = L^-1, lane owns column `lane` (Li[q][lane] = 0 for q < lane, so the sum needs no predicate); two accumulators
     for (int i = 0; i < B; ++i) {
-        double s = lane == i ? 1.0 : 0.0;
+        double s0 = lane == i ? 1.0 : 0.0, s1 = 0.0;
+        int q = 0;
 #pragma unroll 4
-        for (int q = 0; q < i; ++q) {
-            const double liq = L[i][q];                 // broadcast
-            if (q >= lane) s = fma(-liq, Li[q][lane], s);
+        for (; q + 1 < i; q += 2) {
+            s0 = fma(-L[i][q], Li[q][lane], s0);        // L[i][q]: broadcast
+            s1 = fma(-L[i][q + 1], Li[q + 1][lane], s1);
         }
-        if (lane <= i) Li[i][lane] = s / L[i][i];
+        if (q < i) s0 = fma(-L[i][q], Li[q][lane], s0);
+        if (lane <= i) Li[i][lane] = (s0 + s1) * W[0][i];
         __syncwarp();
     }
-    const double dl = dscale[lane];
-    for (int bcol = 0; bcol < B; ++bcol) M[lane * B + bcol] = lane <= bcol ? dl * Li[bcol][lane] : 0.0;   // M = D L^-T
+    // M = D L^-T, lane = column of M: coalesced stores, Li[lane][r] is a stride-33 (conflict-free) read
+    for (int r = 0; r < B; ++r) M[r * B + lane] = r <= lane ? dscale[r] * Li[lane][r] : 0.0;
     if (bad && lane == 0) state[2] = bad;
 }
 
@@ -411,7 +423,12 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     int splits = std::max(1, std::min(16, ceil_div(2 * n_sms, n_rb)));
     const int kchunk = (int)round_up(ceil_div(R, splits), 8);
     splits = ceil_div(R, kchunk);
+    // Rayleigh-Ritz + convergence check every T passes, the first one at `first` (default 2T): the span converges
+    // regardless of the basis, the check costs a 32 x 32 Jacobi (~0.1 ms, more than two plain passes), and no realistic
+    // spectrum converges to 1e-13 within three passes.
     const int T = 3;
+    static const int first_env = [] { const char* v = std::getenv("RUVIII_EIG_FIRST"); return v && *v ? std::atoi(v) : 0; }();
+    const int first = first_env > 0 ? (int)round_up(first_env, T) : 2 * T;
     int launches = 0;
     ek_init_kernel<B><<<ceil_div((int64_t)R * B, 256), 256, 0, s>>>(w.Zp, R, w.state);
     ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, 1, nullptr, R, w.Z, w.Sp, nullptr, w.state);
@@ -421,12 +438,12 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     TopkResult res;
     int it = 0;
     while (it < max_iter) {
-        const int batch_end = std::min(max_iter, it == 0 ? 2 * T : it + T);
+        const int batch_end = std::min(max_iter, it == 0 ? first : it + T);
         for (; it < batch_end;) {
             ++it;
             ek_gemm_kernel<B><<<dim3(n_rb, splits), 128, 0, s>>>(G, w.Q, R, kchunk, w.Zp, w.state);
             ++launches;
-            if (it % T == 0) {
+            if (it % T == 0 && it >= first) {
                 ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, w.Q, R, w.Z, w.Sp, w.Hp, w.state);
                 ek_rr_kernel<B><<<1, 512, 0, s>>>(w.Hp, n_rb, w.V, w.theta, w.state);
                 ek_rotate_kernel<B><<<n_rb, 256, 0, s>>>(w.Q, w.Z, w.V, w.theta, R, w.X, w.Rp, w.state);

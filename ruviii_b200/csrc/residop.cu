@@ -11,6 +11,9 @@
 // summation and the subtraction so every input byte is read once.
 #include "kernels.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace ruviii {
 
 namespace {
@@ -159,11 +162,27 @@ void launch_log2_inplace(double* Y, int64_t ld, int rows, int n, double pc, cuda
     RUVIII_LAUNCH_CHECK();
 }
 
+// grid.y of the segmented kernels.  One CTA per (gene strip, group) is 31,600 CTAs of ~1 us each at C3 -- bound by the
+// CTA launch rate, not by HBM (measured 0.63 of peak) -- so the groups are walked by a grid-stride loop instead and the
+// grid is sized to `waves` full waves of resident CTAs (16 CTAs of 128 threads per SM).
+static int seg_grid_y(int grid_x, int n_groups) {
+    static const int waves = [] { const char* v = std::getenv("RUVIII_SEG_WAVES"); return v && *v ? std::max(1, std::atoi(v)) : 2; }();
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    if (waves >= 1000) return std::min(n_groups, 65535);            // one CTA per group (the old launch shape)
+    const int target = sms * 16 * waves;
+    return std::max(1, std::min(std::min(n_groups, 65535), ceil_div(target, grid_x)));
+}
+
 void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int /*max_group*/,
                     int n, double* Y0, int64_t ldY0, cudaStream_t s) {
     if (n_groups <= 0 || n <= 0) return;
     const int n_pairs = (n + 1) / 2;          // pitches are even and zero padded, so the odd tail pair is safe
-    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), 1);
+    grid.y = seg_grid_y(grid.x, n_groups);
     residop_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Y0, ldY0);
     RUVIII_LAUNCH_CHECK();
 }
@@ -172,7 +191,8 @@ void launch_group_mean(RowSrc src, const int* all_start, const int* all_rows, in
                        cudaStream_t s) {
     if (n_groups <= 0 || n <= 0) return;
     const int n_pairs = (n + 1) / 2;
-    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), 1);
+    grid.y = seg_grid_y(grid.x, n_groups);
     group_mean_kernel<<<grid, kResidopThreads, 0, s>>>(src, all_start, all_rows, n_groups, n_pairs, out, ld);
     RUVIII_LAUNCH_CHECK();
 }
@@ -188,7 +208,8 @@ void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n
                     cudaStream_t s) {
     if (n_groups <= 0 || n <= 0) return;
     const int n_pairs = (n + 1) / 2;
-    dim3 grid(ceil_div(n_pairs, kResidopThreads), std::min(n_groups, 65535));
+    dim3 grid(ceil_div(n_pairs, kResidopThreads), 1);
+    grid.y = seg_grid_y(grid.x, n_groups);
     helmert_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Z, ldZ);
     RUVIII_LAUNCH_CHECK();
 }
