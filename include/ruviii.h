@@ -160,6 +160,22 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
  * it (the reference default eta = NULL: RUV1 is the identity).  q <= 32.  A singular eta_c eta_c' is RUVIII_ERR_SINGULAR. */
 int ruviii_set_eta(ruviii_handle* h, const double* eta, int32_t q, int32_t n);
 
+/* ---- PRPS construction (the step immediately before the path) -----------------------------------
+ * prpsForCategoricalUV.R:123-139 and prpsForContinuousUV.R:190-201 build every pseudo-sample as
+ *     rowMeans(expre.data[, index.sample])          with expre.data = log2(assay + pseudo.count) when apply.log.
+ * The index sets (which samples share a biology x batch cell, or sit at the top / bottom of a continuous variable) are
+ * host-side bookkeeping on colData and stay there; the means are this segmented kernel.  CSR: pseudo-sample j averages
+ * the samples set_rows[set_start[j] .. set_start[j+1]) (0-based rows of Y = columns of the assay).
+ *
+ * ruviii_prps: one shot, host buffers (only the member rows are uploaded).  PS_out is n_ps x n row-major, i.e. the bytes
+ * of the genes x pseudo-samples matrix the reference stores in metadata$PRPS. */
+int ruviii_prps(ruviii_handle* h, const double* Y, int64_t ldY, int32_t m1, int32_t n, int32_t apply_log, double pseudo_count,
+                const int32_t* set_start, const int32_t* set_rows, int32_t n_ps, double* PS_out, int64_t ldPS);
+/* Fused form: register the sets (sticky, like ruviii_set_eta; n_ps = 0 clears) and pass PS = NULL to ruviii_upload /
+ * ruviii_normalise with the same n_ps: replicate.data is then built on the device from the uploaded assay (after its
+ * log transform, before RUV1) and never crosses PCIe.  The group ids of the PRPS rows still come in group_of_row. */
+int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

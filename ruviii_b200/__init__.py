@@ -5,8 +5,10 @@ The product is ``lib/libruviii_b200.so`` (C ABI in ``include/ruviii.h``); this p
 and ``sharding`` (gene shards for one-process-per-GPU launches).  Importing the package never loads the
 library; the first compute call does, and raises if it is missing.
 """
-from .api import (ReplicateData, SummarizedExperiment, fastruvIII, get_engine, group_codes, ruvIII,  # noqa: F401
+from .api import (ReplicateData, SummarizedExperiment, fastruvIII, get_engine, group_codes, normalise, ruvIII,  # noqa: F401
                   ruvIIIMultipleK, set_engine)
+from .prps import (prpsForCategoricalUV, prpsForContinuousUV, supervisedPRPS,  # noqa: F401
+                   replicate_data_from_metadata)
 from ._cabi import Engine, RuviiiError, make_params, MODE_FAST, MODE_STACKED  # noqa: F401
 
 __version__ = "0.1.0"

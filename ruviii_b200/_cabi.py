@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets",
     "ruviii_fast_residop", "ruviii_probe",
 ]
 
@@ -94,6 +94,8 @@ def load_library():
     lib.ruviii_eigenvalues.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_fullalpha.argtypes = [H, vp, C.c_int32]
     lib.ruviii_set_eta.argtypes = [H, vp, C.c_int32, C.c_int32]
+    lib.ruviii_prps.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, C.c_int32, vp, C.c_int64]
+    lib.ruviii_set_prps_sets.argtypes = [H, vp, vp, C.c_int32]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
     lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     for name in SYMBOLS:
@@ -217,7 +219,11 @@ class Engine:
         self._plan = dict(params=params, m1=m1, n=n, n_ps=n_ps, ks=[int(k) for k in ks])
 
     def upload(self, Y, PS):
+        """PS = None: replicate.data is built on the device from Y (needs set_prps_sets with the plan's n_ps)."""
         Y = _rowmajor(Y, "Y")
+        if PS is None:
+            self._check(self._lib.ruviii_upload(self._h, _ptr(Y), Y.strides[0] // 8, None, 0))
+            return
         PS = _rowmajor(PS, "PS")
         self._check(self._lib.ruviii_upload(self._h, _ptr(Y), Y.strides[0] // 8, _ptr(PS), PS.strides[0] // 8))
 
@@ -241,6 +247,33 @@ class Engine:
             return
         e = _rowmajor(eta, "eta")
         self._check(self._lib.ruviii_set_eta(self._h, _ptr(e), e.shape[0], e.shape[1]))
+
+    @staticmethod
+    def _csr(sets):
+        """List of index lists -> (start int32[n+1], rows int32[total])."""
+        start = np.zeros(len(sets) + 1, dtype=np.int32)
+        start[1:] = np.cumsum([len(x) for x in sets])
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.int32) for x in sets]) if len(sets) else
+                                    np.zeros(0, dtype=np.int32), dtype=np.int32)
+        return start, rows
+
+    def prps(self, Y, sets, apply_log=False, pseudo_count=1.0):
+        """K0: pseudo-sample j = mean of the rows ``sets[j]`` of Y (samples x genes), after log2(Y + pseudo_count) when
+        ``apply_log`` (prpsForCategoricalUV.R:91,123-139).  Returns n_ps x n."""
+        Y = _rowmajor(Y, "Y")
+        start, rows = self._csr(sets)
+        out = np.empty((len(sets), Y.shape[1]), dtype=np.float64)
+        self._check(self._lib.ruviii_prps(self._h, _ptr(Y), Y.strides[0] // 8, Y.shape[0], Y.shape[1], int(bool(apply_log)),
+                                          float(pseudo_count), _ptr(start), _ptr(rows), len(sets), _ptr(out), out.shape[1]))
+        return out
+
+    def set_prps_sets(self, sets):
+        """Fused K0: the next plans with n_ps = len(sets) build replicate.data on the device when PS is None."""
+        if not sets:
+            self._check(self._lib.ruviii_set_prps_sets(self._h, None, None, 0))
+            return
+        start, rows = self._csr(sets)
+        self._check(self._lib.ruviii_set_prps_sets(self._h, _ptr(start), _ptr(rows), len(sets)))
 
     def eigenvalues(self, count):
         out = np.empty(count, dtype=np.float64)
@@ -278,9 +311,18 @@ class Engine:
 
     # ---- one shot ---------------------------------------------------------------------------------------
     def normalise(self, params, Y, PS, group_of_row, ctl, ks, want_fullalpha=False, want_W=False, want_ps=False,
-                  out=None):
-        """Host buffers in, host buffers out, through ``ruviii_normalise`` (what the R shim calls)."""
+                  out=None, ps_on_device=0):
+        """Host buffers in, host buffers out, through ``ruviii_normalise`` (what the R shim calls).
+        ``ps_on_device`` = n_ps > 0 with PS = None: the PRPS rows come from the sets given to ``set_prps_sets``."""
         Y = _rowmajor(Y, "Y")
+        if ps_on_device:
+            m1, n = Y.shape
+            group_of_row = np.ascontiguousarray(group_of_row, dtype=np.int32)
+            ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+            self.plan(params, m1, n, int(ps_on_device), group_of_row, np.asarray(ctl), ks_arr)
+            self.upload(Y, None)
+            self.run()
+            return self.download(want_fullalpha=want_fullalpha, want_W=want_W, want_ps=want_ps, out=out)
         PS = _rowmajor(PS, "PS") if PS is not None and np.size(PS) else np.zeros((0, Y.shape[1]))
         m1, n = Y.shape
         n_ps = PS.shape[0]

@@ -19,7 +19,7 @@ import numpy as np
 from . import _cabi
 from ._cabi import MODE_FAST, MODE_STACKED, Engine, RuviiiError, make_params
 
-__all__ = ["SummarizedExperiment", "ReplicateData", "ruvIII", "fastruvIII", "ruvIIIMultipleK", "get_engine",
+__all__ = ["SummarizedExperiment", "ReplicateData", "ruvIII", "fastruvIII", "ruvIIIMultipleK", "normalise", "get_engine",
            "set_engine", "group_codes"]
 
 
@@ -30,6 +30,7 @@ class SummarizedExperiment:
     col_names: list                  # sample ids  (colnames(se.obj))
     row_names: list | None = None    # gene ids
     metadata: dict = field(default_factory=dict)
+    col_data: dict = field(default_factory=dict)   # colData(se.obj): variable name -> one value per sample
 
     def assay(self, name):
         if name not in self.assays:
@@ -263,3 +264,38 @@ def ruvIIIMultipleK(se_obj, assay_name, apply_log=True, pseudo_count=1, replicat
             newY = res["averaged"][i]
         out.append(dict(newY=newY, fullalpha=res["fullalpha"], W=Ws[i]))
     return out
+
+
+def normalise(se_obj, assay_name, apply_log=True, pseudo_count=1, bio_variable_prps=None, uv_variables_prps=None,
+              batch_variable_prps=None, min_sample_for_prps=3, min_sample_per_batch_prps=6, assess_cor_variables_prps=False,
+              norm_assay_name_ncg=None, apply_normalization_ncg=False, normalization_ncg="CPM", bio_variables_ncg=None,
+              uv_variables_ncg=None, no_ncg=1000, regress_out_uv_variables_ncg=False, regress_out_bio_variables_ncg=False,
+              k=None, eta=None, include_intercept=True, apply_average_rep=False, fullalpha=None, inputcheck=True,
+              assess_se_obj=True, remove_na="both", verbose=True):
+    """R/normalise.R:61-167: supervisedPRPS -> supervisedFindNCG -> ruvIIIMultipleK.
+
+    The PRPS step runs on the device (:mod:`ruviii_b200.prps`); the RUV-III step is the engine.  Negative-control gene
+    selection (``supervisedFindNCG``, normalise.R:127-141) is outside the rebuilt path: the logical
+    vector it would leave in ``metadata$NCG`` must already be there."""
+    from . import prps
+    _printColoredMessage("------------The normalise function starts.", verbose)
+    if k is None:
+        raise ValueError("k cannot be 0. This means no adjustment will be made.")                     # normalise.R:95-96
+    if assay_name is None:
+        raise ValueError("No assay name has been provided.")
+    if isinstance(assay_name, (list, tuple)):
+        raise ValueError("The function can only take a single assay.name.")
+    se_obj = prps.supervisedPRPS(se_obj, assay_name, bio_variable_prps, uv_variables_prps, batch_variable_prps,
+                                 min_sample_for_prps, min_sample_per_batch_prps, apply_log, pseudo_count, assess_se_obj,
+                                 assess_cor_variables_prps, save_se_obj=True, verbose=verbose)          # :110-124
+    if "NCG" not in se_obj.metadata:
+        raise NotImplementedError("supervisedFindNCG (normalise.R:127-141) is not part of the CUDA path: put the negative "
+                                  "control genes (logical vector) into se_obj.metadata['NCG'] first")
+    replicate_data = prps.replicate_data_from_metadata(se_obj)                                        # :143
+    se_obj = ruvIIIMultipleK(se_obj, assay_name, apply_log=apply_log, pseudo_count=pseudo_count,
+                             replicate_data=replicate_data, ctl=se_obj.metadata["NCG"], k=k, eta=eta,
+                             include_intercept=include_intercept, apply_average_rep=apply_average_rep, fullalpha=fullalpha,
+                             return_info=False, inputcheck=inputcheck, assess_se_obj=assess_se_obj,
+                             remove_na="measurements", save_se_obj=True, verbose=verbose)                 # :144-161
+    _printColoredMessage("------------The normalise function finished.", verbose)
+    return se_obj

@@ -26,6 +26,32 @@ namespace {
 
 constexpr int kRowsPerCta = 32;
 
+// Programmatic dependent launch: the ~35 kernels of one solve are tiny and strictly dependent, so the launch gap
+// between them (~5 us each) is a quarter of the solve.  Launched with programmaticStreamSerialization the next kernel is
+// scheduled while its predecessor drains; every kernel executes griddepcontrol.wait before touching anything the
+// predecessor wrote (a no-op without the attribute).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool use_pdl() {
+    static const bool on = [] { const char* v = std::getenv("RUVIII_PDL"); return !(v && *v == '0'); }();
+    return on;
+}
+
+template <class... KArgs, class... Args>
+void launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RUVIII_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -35,6 +61,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ---- start block: a fixed hash of (row, column), uniform in (-1, 1) ------------------------------------------
 template <int B>
 __global__ void __launch_bounds__(256) ek_init_kernel(double* __restrict__ Z, int R, int* __restrict__ state) {
+    griddep_wait();
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e == 0) { state[0] = 0; state[1] = 0; state[2] = 0; }
     if (e >= R * B) return;
@@ -50,6 +77,7 @@ template <int B>
 __global__ void __launch_bounds__(128)
 ek_gemm_kernel(const double* __restrict__ G, const double* __restrict__ Q, int R, int kchunk,
                double* __restrict__ Zp, const int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
     constexpr int NT = B / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -90,6 +118,7 @@ template <int B>
 __global__ void __launch_bounds__(256)
 ek_ztz_kernel(const double* __restrict__ Zp, int nsplit, const double* __restrict__ Q, int R, double* __restrict__ Z,
               double* __restrict__ Sp, double* __restrict__ Hp, const int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
     __shared__ double sZ[kRowsPerCta][B + 1];
     __shared__ double sQ[kRowsPerCta][B + 1];
@@ -126,12 +155,13 @@ template <int B>
 __global__ void __launch_bounds__(512)
 ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, double* __restrict__ theta,
              const int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
     __shared__ double A[B][B + 1];
     __shared__ double W[B][B + 1];
     __shared__ double cs[B / 2][2];
     __shared__ int pr[B / 2][2];
-    __shared__ int flag;
+    __shared__ int flag, flag_big;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
@@ -149,7 +179,7 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
     __syncthreads();
     // parallel cyclic Jacobi, round-robin pairing: B/2 disjoint rotations per round, B-1 rounds per sweep
     for (int sweep = 0; sweep < 16; ++sweep) {
-        if (tid == 0) flag = 0;
+        if (tid == 0) { flag = 0; flag_big = 0; }
         __syncthreads();
         for (int round = 0; round < B - 1; ++round) {
             if (tid < B / 2) {
@@ -168,6 +198,7 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
                     c = rsqrt(fma(t, t, 1.0));
                     s = t * c;
                     flag = 1;
+                    if (apq * apq > 1e-20 * fabs(app * aqq)) flag_big = 1;
                 }
                 cs[tid][0] = c; cs[tid][1] = s;
                 pr[tid][0] = p; pr[tid][1] = q;
@@ -195,7 +226,9 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
             }
             __syncthreads();
         }
-        if (!flag) break;
+        // cyclic Jacobi converges quadratically: a sweep whose largest relative off-diagonal entry was below 1e-10
+        // leaves them below rounding, so the sweep that would only verify this is not run
+        if (!flag || !flag_big) break;
         __syncthreads();
     }
     // sort descending (rank sort), write V with permuted columns
@@ -216,21 +249,28 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
     }
 }
 
-// ORTHO: S = sum Sp, scale to unit diagonal, Cholesky, M = D L^-T  -> Q = Z M is orthonormal.
+// ORTHO: S = sum Sp, scale to unit diagonal, Cholesky S = L L'.  Q = Z D L^-T is then orthonormal; the triangular
+// solve itself is done row by row in ek_apply_kernel, so nothing is inverted here.  Output: Lf = L with its diagonal
+// replaced by 1 / L[j][j] (row-major B x B, upper part zero), Dv = the column scales.
 // With check != 0 it first turns the residual partials Rp into ||Z_j - theta_j X_j||, j < kk, and raises the
 // converged flag when all of them are <= tol * theta_0 (everything queued behind then exits at once).
+//
+// The factorisation is right-looking over the whole CTA with ONE barrier per column: in step j every thread updates its
+// trailing entries from column j of the previous state (A[r][c] -= A[r][j] A[c][j] / A[j][j]) and the owners of column j
+// write L[:, j]; step j only reads column j and only writes columns > j, so no second barrier is needed.
 template <int B>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restrict__ Rp, int n_part, int kk, double tol,
-                int iter, double* __restrict__ M, const double* __restrict__ theta, double* __restrict__ resid,
-                int* __restrict__ state) {
+                int iter, double* __restrict__ Lf, double* __restrict__ Dv, const double* __restrict__ theta,
+                double* __restrict__ resid, int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
-    __shared__ double W[B][B + 1];
+    __shared__ double A[B][B + 1];
+    __shared__ double L[B][B + 1];
     __shared__ double dscale[B];
     __shared__ int flag;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int mode = check ? 2 : 0;
-    if (mode == 2) {
+    if (check) {
         // ||Z_j - theta_j X_j||, j < kk, against tol * theta_0
         if (tid < B) {
             double s = 0.0;
@@ -250,92 +290,86 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
         __syncthreads();
         if (flag) return;
     }
-
-    // ---- ORTHO: one warp factors the scaled 32 x 32 matrix in shared memory (lane = row, row stride 33 keeps
-    // the lanes on distinct banks, pivot-column reads are broadcasts).  Compact loops on purpose: a fully unrolled
-    // register version is ~10k straight-line instructions that run once and stall on instruction fetch.
-    static_assert(B == 32, "the warp-level factorisation maps one matrix row to one lane");
-    __shared__ double L[B][B + 1];
-    __shared__ double Li[B][B + 1];
     for (int e = tid; e < B * B; e += nt) {
         double s = 0.0;
 #pragma unroll 8
         for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];      // unrolled: 8 loads in flight, fixed order
-        W[e / B][e % B] = s;
+        L[e / B][e % B] = s;
     }
     __syncthreads();
-    if (tid < B) dscale[tid] = W[tid][tid] > 0.0 ? rsqrt(W[tid][tid]) : 1.0;
+    if (tid < B) dscale[tid] = L[tid][tid] > 0.0 ? rsqrt(L[tid][tid]) : 1.0;
     __syncthreads();
     for (int e = tid; e < B * B; e += nt) {
         const int i = e / B, j = e % B;
-        L[i][j] = 0.5 * (W[i][j] + W[j][i]) * dscale[i] * dscale[j];
-        Li[i][j] = 0.0;
+        A[i][j] = 0.5 * (L[i][j] + L[j][i]) * dscale[i] * dscale[j];
     }
     __syncthreads();
-    if (tid >= 32) return;
-    const int lane = tid;
+    // thread t owns column c = t % B of rows r = t / B + (nt / B) u
+    const int c = tid % B, rbase = tid / B, rstep = nt / B;
     int bad = 0;
-    // Left-looking (Crout) Cholesky: column j of the factor is A[:, j] - L[:, :j] L[j, :j]' scaled by the pivot.  The
-    // inner product accumulates in registers and the loop only READS shared memory (own row: stride 33, conflict-free;
-    // row j: broadcast), so its loads pipeline; the right-looking form did a dependent shared-memory read-modify-write
-    // per term (~50 cycles each, 496 terms).
     for (int j = 0; j < B; ++j) {
-        double v0 = L[lane][j], v1 = 0.0;
-        int q = 0;
-#pragma unroll 4
-        for (; q + 1 < j; q += 2) {
-            v0 = fma(-L[lane][q], L[j][q], v0);
-            v1 = fma(-L[lane][q + 1], L[j][q + 1], v1);
+        const double pj = A[j][j];
+        double rd = rsqrt(pj);
+        if (!(pj > 1e-30)) { bad = j + 1; rd = 1.0; }
+        const double rd2 = rd * rd;
+        if (c > j) {
+            const double acj = A[c][j] * rd2;
+            for (int r = rbase; r < B; r += rstep)
+                if (r >= c) A[r][c] = fma(-A[r][j], acj, A[r][c]);
+        } else if (c == j) {
+            for (int r = rbase; r < B; r += rstep) L[r][j] = r > j ? A[r][j] * rd : (r == j ? rd : 0.0);   // diagonal: 1 / L[j][j]
         }
-        if (q < j) v0 = fma(-L[lane][q], L[j][q], v0);
-        const double v = v0 + v1;
-        const double djj = __shfl_sync(0xffffffffu, v, j);
-        double rd = rsqrt(djj);
-        if (!(djj > 1e-30)) { bad = j + 1; rd = 1.0; }
-        __syncwarp();
-        L[lane][j] = lane > j ? v * rd : (lane == j ? djj * rd : 0.0);
-        if (lane == 0) W[0][j] = rd;                    // 1 / L[j][j], reused by the inversion (W is free by now)
-        __syncwarp();
+        __syncthreads();
     }
-    // Li = L^-1, lane owns column `lane` (Li[q][lane] = 0 for q < lane, so the sum needs no predicate); two accumulators
-    for (int i = 0; i < B; ++i) {
-        double s0 = lane == i ? 1.0 : 0.0, s1 = 0.0;
-        int q = 0;
-#pragma unroll 4
-        for (; q + 1 < i; q += 2) {
-            s0 = fma(-L[i][q], Li[q][lane], s0);        // L[i][q]: broadcast
-            s1 = fma(-L[i][q + 1], Li[q + 1][lane], s1);
-        }
-        if (q < i) s0 = fma(-L[i][q], Li[q][lane], s0);
-        if (lane <= i) Li[i][lane] = (s0 + s1) * W[0][i];
-        __syncwarp();
+    for (int e = tid; e < B * B; e += nt) {
+        const int i = e / B, j = e % B;
+        Lf[e] = j <= i ? L[i][j] : 0.0;
     }
-    // M = D L^-T, lane = column of M: coalesced stores, Li[lane][r] is a stride-33 (conflict-free) read
-    for (int r = 0; r < B; ++r) M[r * B + lane] = r <= lane ? dscale[r] * Li[lane][r] : 0.0;
-    if (bad && lane == 0) state[2] = bad;
+    if (tid < B) Dv[tid] = dscale[tid];
+    if (bad && tid == 0) state[2] = bad;
 }
 
-// ---- out = in M  (R x B by B x B), rows blocked through shared memory ---------------------------------------
+// ---- out = in D L^-T: every row solves q L' = z D by forward substitution ---------------------------------------
+// One thread per row with the row in registers (right-looking: after q_c is known the remaining entries take their
+// q_c L[b][c] update as independent FMAs); L is read as warp-uniform shared-memory broadcasts.  Rows go through a
+// padded shared tile so that the global accesses stay coalesced.
 template <int B>
 __global__ void __launch_bounds__(256)
-ek_apply_kernel(const double* __restrict__ in, const double* __restrict__ M, int R, double* __restrict__ out,
-                const int* __restrict__ state) {
+ek_apply_kernel(const double* __restrict__ in, const double* __restrict__ Lf, const double* __restrict__ Dv, int R,
+                double* __restrict__ out, const int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
-    __shared__ double sM[B][B + 1];
+    __shared__ double sL[B][B + 1];
     __shared__ double sI[kRowsPerCta][B + 1];
+    __shared__ double sD[B];
     const int r0 = blockIdx.x * kRowsPerCta;
-    for (int e = threadIdx.x; e < B * B; e += 256) sM[e / B][e % B] = M[e];
+    for (int e = threadIdx.x; e < B * B; e += 256) sL[e / B][e % B] = Lf[e];
+    if (threadIdx.x < B) sD[threadIdx.x] = Dv[threadIdx.x];
+    __syncthreads();
     for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
         const int r = e / B, c = e % B;
-        sI[r][c] = (r0 + r < R) ? in[(int64_t)(r0 + r) * B + c] : 0.0;
+        sI[r][c] = (r0 + r < R) ? in[(int64_t)(r0 + r) * B + c] * sD[c] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < kRowsPerCta) {
+        const int r = threadIdx.x;
+        double z[B];
+#pragma unroll
+        for (int c = 0; c < B; ++c) z[c] = sI[r][c];
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+            const double q = z[c] * sL[c][c];          // sL[c][c] holds 1 / L[c][c]
+            z[c] = q;
+#pragma unroll
+            for (int b = c + 1; b < B; ++b) z[b] = fma(-q, sL[b][c], z[b]);
+        }
+#pragma unroll
+        for (int c = 0; c < B; ++c) sI[r][c] = z[c];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < kRowsPerCta * B; e += 256) {
         const int r = e / B, c = e % B;
-        double s = 0.0;
-#pragma unroll 8
-        for (int a = 0; a < B; ++a) s = fma(sI[r][a], sM[a][c], s);
-        if (r0 + r < R) out[(int64_t)(r0 + r) * B + c] = s;
+        if (r0 + r < R) out[(int64_t)(r0 + r) * B + c] = sI[r][c];
     }
 }
 
@@ -345,6 +379,7 @@ __global__ void __launch_bounds__(256)
 ek_rotate_kernel(const double* __restrict__ Q, double* __restrict__ Z, const double* __restrict__ V,
                  const double* __restrict__ theta, int R, double* __restrict__ X, double* __restrict__ Rp,
                  const int* __restrict__ state) {
+    griddep_wait();
     if (state[0]) return;
     __shared__ double sV[B][B + 1];
     __shared__ double sQ[kRowsPerCta][B + 1];
@@ -387,6 +422,7 @@ template <int B>
 __global__ void __launch_bounds__(256)
 ek_finalize_kernel(const double* __restrict__ X, const double* __restrict__ theta, int R, int n_keep, int kk, int kp,
                    double* __restrict__ U, double* __restrict__ evals) {
+    griddep_wait();
     const int j = blockIdx.x;
     __shared__ double s_abs[256];
     __shared__ double s_val[256];
@@ -430,10 +466,14 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     static const int first_env = [] { const char* v = std::getenv("RUVIII_EIG_FIRST"); return v && *v ? std::atoi(v) : 0; }();
     const int first = first_env > 0 ? (int)round_up(first_env, T) : 2 * T;
     int launches = 0;
-    ek_init_kernel<B><<<ceil_div((int64_t)R * B, 256), 256, 0, s>>>(w.Zp, R, w.state);
-    ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, 1, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-    ek_ortho_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, 0, w.M, w.theta, w.resid, w.state);
-    ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+    const dim3 g_rb(n_rb), one(1);
+    launch_dep(ek_init_kernel<B>, dim3(ceil_div((int64_t)R * B, 256)), dim3(256), s, w.Zp, R, w.state);
+    launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Zp, 1, (const double*)nullptr, R, w.Z, w.Sp, (double*)nullptr,
+               (const int*)w.state);
+    launch_dep(ek_ortho_kernel<B>, one, dim3(256), s, 0, (const double*)w.Sp, (const double*)nullptr, n_rb, kk, tol, 0, w.M, w.D,
+               (const double*)w.theta, w.resid, w.state);
+    launch_dep(ek_apply_kernel<B>, g_rb, dim3(256), s, (const double*)w.Z, (const double*)w.M, (const double*)w.D, R, w.Q,
+               (const int*)w.state);
     launches += 4;
     TopkResult res;
     int it = 0;
@@ -441,21 +481,29 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
         const int batch_end = std::min(max_iter, it == 0 ? first : it + T);
         for (; it < batch_end;) {
             ++it;
-            ek_gemm_kernel<B><<<dim3(n_rb, splits), 128, 0, s>>>(G, w.Q, R, kchunk, w.Zp, w.state);
+            launch_dep(ek_gemm_kernel<B>, dim3(n_rb, splits), dim3(128), s, G, (const double*)w.Q, R, kchunk, w.Zp, (const int*)w.state);
             ++launches;
             if (it % T == 0 && it >= first) {
-                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, w.Q, R, w.Z, w.Sp, w.Hp, w.state);
-                ek_rr_kernel<B><<<1, 512, 0, s>>>(w.Hp, n_rb, w.V, w.theta, w.state);
-                ek_rotate_kernel<B><<<n_rb, 256, 0, s>>>(w.Q, w.Z, w.V, w.theta, R, w.X, w.Rp, w.state);
-                // CHECK sets the flag; the ORTHO half of mode 2 needs S of the rotated block, so it is recomputed first
-                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, 1, nullptr, R, nullptr, w.Sp, nullptr, w.state);
-                ek_ortho_kernel<B><<<1, 1024, 0, s>>>(1, w.Sp, w.Rp, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
-                ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+                launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Zp, splits, (const double*)w.Q, R, w.Z, w.Sp, w.Hp,
+                           (const int*)w.state);
+                launch_dep(ek_rr_kernel<B>, one, dim3(512), s, (const double*)w.Hp, n_rb, w.V, w.theta, (const int*)w.state);
+                launch_dep(ek_rotate_kernel<B>, g_rb, dim3(256), s, (const double*)w.Q, w.Z, (const double*)w.V, (const double*)w.theta, R,
+                           w.X, w.Rp, (const int*)w.state);
+                // CHECK sets the flag; the ORTHO half needs S of the rotated block, so it is recomputed first
+                launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Z, 1, (const double*)nullptr, R, (double*)nullptr, w.Sp,
+                           (double*)nullptr, (const int*)w.state);
+                launch_dep(ek_ortho_kernel<B>, one, dim3(256), s, 1, (const double*)w.Sp, (const double*)w.Rp, n_rb, kk, tol, it, w.M, w.D,
+                           (const double*)w.theta, w.resid, w.state);
+                launch_dep(ek_apply_kernel<B>, g_rb, dim3(256), s, (const double*)w.Z, (const double*)w.M, (const double*)w.D, R, w.Q,
+                           (const int*)w.state);
                 launches += 6;
             } else {
-                ek_ztz_kernel<B><<<n_rb, 256, 0, s>>>(w.Zp, splits, nullptr, R, w.Z, w.Sp, nullptr, w.state);
-                ek_ortho_kernel<B><<<1, 1024, 0, s>>>(0, w.Sp, nullptr, n_rb, kk, tol, it, w.M, w.theta, w.resid, w.state);
-                ek_apply_kernel<B><<<n_rb, 256, 0, s>>>(w.Z, w.M, R, w.Q, w.state);
+                launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Zp, splits, (const double*)nullptr, R, w.Z, w.Sp,
+                           (double*)nullptr, (const int*)w.state);
+                launch_dep(ek_ortho_kernel<B>, one, dim3(256), s, 0, (const double*)w.Sp, (const double*)nullptr, n_rb, kk, tol, it, w.M,
+                           w.D, (const double*)w.theta, w.resid, w.state);
+                launch_dep(ek_apply_kernel<B>, g_rb, dim3(256), s, (const double*)w.Z, (const double*)w.M, (const double*)w.D, R, w.Q,
+                           (const int*)w.state);
                 launches += 3;
             }
         }
@@ -469,7 +517,8 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     res.iterations = h_state[1];
     res.launches = launches;
     if (res.converged) {
-        ek_finalize_kernel<B><<<std::max(std::max(n_keep, kp), kk), 256, 0, s>>>(w.X, w.theta, R, n_keep, kk, kp, U, evals);
+        launch_dep(ek_finalize_kernel<B>, dim3(std::max(std::max(n_keep, kp), kk)), dim3(256), s, (const double*)w.X,
+                   (const double*)w.theta, R, n_keep, kk, kp, U, evals);
         RUVIII_LAUNCH_CHECK();
         res.launches += 1;
     }
@@ -481,7 +530,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
 size_t topk_work_doubles(int R, int B) {
     const int n_rb = ceil_div(R, kRowsPerCta);
     // Q, X, Z, Zp (16 splits), Sp, Hp, Rp, M, V, theta, resid
-    return (size_t)R * B * (3 + 16) + (size_t)n_rb * B * B * 2 + (size_t)n_rb * B + (size_t)B * B * 2 + 4 * B;
+    return (size_t)R * B * (3 + 16) + (size_t)n_rb * B * B * 2 + (size_t)n_rb * B + (size_t)B * B * 2 + 5 * B;
 }
 
 void topk_bind(TopkWork& w, double* base, int* state, int R, int B) {
@@ -498,6 +547,7 @@ void topk_bind(TopkWork& w, double* base, int* state, int R, int B) {
     w.V = p; p += (size_t)B * B;
     w.theta = p; p += B;
     w.resid = p; p += B;
+    w.D = p; p += B;
     w.state = state;
 }
 

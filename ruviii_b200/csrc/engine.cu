@@ -141,7 +141,7 @@ struct Shard {
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
     DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
     DevBuf<int2> tile_map;
-    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1;
+    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1, set_start, set_rows;
     TopkWork topk{};
     alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
     alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
@@ -202,6 +202,11 @@ struct ruviii_handle {
     std::vector<double> eta_host;
     int eta_q = 0, eta_n = 0;
     bool eta_applied = false;           // once per upload, like the log transform
+    // PRPS construction on the device (prpsForCategoricalUV.R:123-139): CSR of the sample sets handed over by
+    // ruviii_set_prps_sets (sticky); replicate.data is then built from the uploaded assay when PS == NULL
+    std::vector<int> prps_start, prps_rows;
+    int prps_n = 0;
+    bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
     double eig_tol = 1e-13;
 
     ~ruviii_handle();
@@ -231,6 +236,8 @@ ruviii_handle::~ruviii_handle() {
         s.all_start.release();
         s.all_rows.release();
         s.status1.release();
+        s.set_start.release();
+        s.set_rows.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
@@ -341,7 +348,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
                                         "non-conformable arguments (fastruvIII.R:179-180)");
     if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
     h->prm = *prm;
-    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = false;
+    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = h->ps_pending = false;
     if (h->eta_q > 0 && h->eta_n != n)
         throw Error(RUVIII_ERR_INVALID, "eta has " + std::to_string(h->eta_n) + " columns, the assay has " + std::to_string(n) +
                                             " genes (ruviii_set_eta)");
@@ -502,6 +509,15 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (!cidx.empty())
                 RUVIII_CUDA_CHECK(cudaMemcpy(s.ctl_idx.p, cidx.data(), cidx.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
+        if (h->prps_n > 0 && h->prps_n == n_ps) {
+            for (int r : h->prps_rows)
+                if (r >= m1) throw Error(RUVIII_ERR_INVALID, "a PRPS set refers to sample " + std::to_string(r) + " but the assay has " +
+                                                                 std::to_string(m1) + " samples");
+            s.set_start.alloc(h->prps_start.size());
+            s.set_rows.alloc(std::max<size_t>(h->prps_rows.size(), 1));
+            RUVIII_CUDA_CHECK(cudaMemcpy(s.set_start.p, h->prps_start.data(), h->prps_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+            RUVIII_CUDA_CHECK(cudaMemcpy(s.set_rows.p, h->prps_rows.data(), h->prps_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
         if (h->eta_q > 0) {
             const int q = h->eta_q, qp = pad_k(q);
             s.eta.alloc((size_t)qp * s.ld);
@@ -605,12 +621,15 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
 
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS) {
     if (!h->planned) throw Error(RUVIII_ERR_STATE, "ruviii_upload before ruviii_plan");
-    if ((h->m1 > 0 && (!Y || ldY < h->n_local_total)) || (h->n_ps > 0 && (!PS || ldPS < h->n_local_total)))
+    // PS == NULL with registered PRPS sets: replicate.data is built on the device from the assay (K0, first run)
+    const bool build_ps = h->n_ps > 0 && !PS && h->prps_n == h->n_ps;
+    if ((h->m1 > 0 && (!Y || ldY < h->n_local_total)) || (h->n_ps > 0 && !build_ps && (!PS || ldPS < h->n_local_total)))
         throw Error(RUVIII_ERR_INVALID, "ruviii_upload: NULL matrix or row stride < n");
+    h->ps_pending = build_ps;
     for (auto& s : h->shards) {
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
-        if (h->n_ps > 0)
+        if (h->n_ps > 0 && !build_ps)
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
                                                 cudaMemcpyHostToDevice, s.stream));
         if (h->m1 > 0)
@@ -737,6 +756,16 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     if (h->prm.apply_log && !h->logged) {             // ruvIII.R:88-89, once per upload
         for_shards([&](Shard& s) { launch_log2_inplace(s.Y.p, s.ld, h->m1, s.n, h->prm.pseudo_count, s.stream); });
         h->logged = true;
+        h->launches += 1;
+    }
+    if (h->ps_pending) {
+        // K0  prpsForCategoricalUV.R:123-139 / prpsForContinuousUV.R:190-201: pseudo-sample j = rowMeans(expre.data[, set_j]),
+        // taken from the (already log-transformed) resident assay; replicate.data never crosses PCIe
+        for_shards([&](Shard& s) {
+            RowSrc src{s.Y.p, s.ld, nullptr, 0, h->m1};
+            launch_group_mean(src, s.set_start.p, s.set_rows.p, h->n_ps, s.n, s.PS.p, s.ld, s.stream);
+        });
+        h->ps_pending = false;
         h->launches += 1;
     }
     if (h->eta_q > 0 && !h->eta_applied) {
@@ -1066,7 +1095,8 @@ const void* host_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-bool can_pipeline(ruviii_handle* h, const double* Y, const double* newY_out, const double* newY_ps_out) {
+bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out) {
+    if (h->n_ps > 0 && !PS) return false;      // replicate.data is built on the device from the whole assay
     const int off = env_int("RUVIII_NO_PIPELINE", 0);
     const bool skip = h->no_replicates || h->kk == 0;
     return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
@@ -1419,6 +1449,83 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
     });
 }
 
+int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        h->planned = false;
+        if (!set_start || n_ps <= 0) {
+            h->prps_start.clear();
+            h->prps_rows.clear();
+            h->prps_n = 0;
+            return;
+        }
+        if (set_start[0] != 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: set_start[0] must be 0");
+        for (int j = 0; j < n_ps; ++j)
+            if (set_start[j + 1] <= set_start[j]) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: empty or unordered set");
+        if (!set_rows) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: set_rows is NULL");
+        for (int t = 0; t < set_start[n_ps]; ++t)
+            if (set_rows[t] < 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: negative sample index");
+        h->prps_start.assign(set_start, set_start + n_ps + 1);
+        h->prps_rows.assign(set_rows, set_rows + set_start[n_ps]);
+        h->prps_n = n_ps;
+    });
+}
+
+int ruviii_prps(ruviii_handle* h, const double* Y, int64_t ldY, int32_t m1, int32_t n, int32_t apply_log, double pseudo_count,
+                const int32_t* set_start, const int32_t* set_rows, int32_t n_ps, double* PS_out, int64_t ldPS) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!Y || !set_start || !set_rows || !PS_out || m1 <= 0 || n <= 0 || n_ps <= 0 || ldY < n || ldPS < n)
+            throw Error(RUVIII_ERR_INVALID, "ruviii_prps: bad arguments");
+        // only the member rows are needed on the device: upload each distinct one once, in ascending order
+        const int total = set_start[n_ps];
+        std::vector<int> uniq(set_rows, set_rows + total);
+        for (int r : uniq)
+            if (r < 0 || r >= m1) throw Error(RUVIII_ERR_INVALID, "ruviii_prps: sample index out of range");
+        for (int j = 0; j < n_ps; ++j)
+            if (set_start[j + 1] <= set_start[j]) throw Error(RUVIII_ERR_INVALID, "ruviii_prps: empty or unordered set");
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        std::vector<int> pos(m1, -1), rows(total);
+        for (size_t i = 0; i < uniq.size(); ++i) pos[uniq[i]] = (int)i;
+        for (int t = 0; t < total; ++t) rows[t] = pos[set_rows[t]];
+        const int nu = (int)uniq.size(), nsh = (int)h->shards.size();
+        std::vector<DevBuf<double>> dY(nsh), dP(nsh);
+        std::vector<DevBuf<int>> dS(nsh), dR(nsh);
+        for (int i = 0; i < nsh; ++i) {
+            Shard& s = h->shards[i];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            const int g0 = (int)((int64_t)n * i / nsh), ng = (int)((int64_t)n * (i + 1) / nsh) - g0;
+            if (ng <= 0) continue;
+            const int64_t ld = round_up(ng, kRowAlign);
+            dY[i].alloc((size_t)nu * ld);
+            dP[i].alloc((size_t)n_ps * ld, false);
+            dS[i].alloc(n_ps + 1);
+            dR[i].alloc(total);
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(dS[i].p, set_start, (size_t)(n_ps + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(dR[i].p, rows.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+            for (int a = 0; a < nu;) {                 // runs of consecutive samples go up as one 2-D copy
+                int b = a + 1;
+                while (b < nu && uniq[b] == uniq[b - 1] + 1) ++b;
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(dY[i].p + (size_t)a * ld, ld * 8, Y + (size_t)uniq[a] * ldY + g0, ldY * 8,
+                                                    (size_t)ng * 8, b - a, cudaMemcpyHostToDevice, s.stream));
+                a = b;
+            }
+            if (apply_log) launch_log2_inplace(dY[i].p, ld, nu, ng, pseudo_count, s.stream);   // prpsForCategoricalUV.R:91
+            RowSrc src{dY[i].p, ld, nullptr, 0, nu};
+            launch_group_mean(src, dS[i].p, dR[i].p, n_ps, ng, dP[i].p, ld, s.stream);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(PS_out + g0, ldPS * 8, dP[i].p, ld * 8, (size_t)ng * 8, n_ps, cudaMemcpyDeviceToHost,
+                                                s.stream));
+        }
+        sync_all(h);
+        h->launches = nsh * (apply_log ? 2 : 1);
+        for (int i = 0; i < nsh; ++i) {
+            cudaSetDevice(h->shards[i].device);
+            dY[i].release(); dP[i].release(); dS[i].release(); dR[i].release();
+        }
+    });
+}
+
 int ruviii_set_eta(ruviii_handle* h, const double* eta, int32_t q, int32_t n) {
     if (!h) return RUVIII_ERR_INVALID;
     return guarded(h, [&] {
@@ -1445,7 +1552,7 @@ int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double
         if (!newY_out) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
         do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk);
         h->pipelined_last = 0;
-        if (can_pipeline(h, Y, newY_out, newY_ps_out)) {
+        if (can_pipeline(h, Y, PS, newY_out, newY_ps_out)) {
             if ((m1 > 0 && ldY < n) || (n_ps > 0 && (!PS || ldPS < n))) throw Error(RUVIII_ERR_INVALID, "row stride < n");
             do_normalise_pipelined(h, Y, ldY, PS, ldPS, newY_out, fullalpha_out, W_out);
         } else {

@@ -70,7 +70,7 @@ void launch_pick_top(const double* evec_colmajor, int64_t ldv, const double* eva
 
 // K3  ruvIII.R:140  svd(Y0 %*% t(Y0))$u[, 1:k]: block subspace iteration + Rayleigh-Ritz (eigen_topk.cu).
 struct TopkWork {
-    double *Q, *X, *Z, *Zp, *Sp, *Hp, *Rp, *M, *V, *theta, *resid;
+    double *Q, *X, *Z, *Zp, *Sp, *Hp, *Rp, *M, *V, *theta, *resid, *D;
     int* state;                  // device: [0] converged, [1] iterations at the last check, [2] Cholesky breakdown
 };
 struct TopkResult {

@@ -328,8 +328,10 @@ chol_solve_kernel(const double* __restrict__ A, int rows_w, int mu_rows, const d
     __syncthreads();
     for (int j = 0; j < kk; ++j) {                    // right-looking Cholesky
         if (tid == 0) {
+            // R's solve() (dgesv + rcond check) stops on a computationally singular matrix; an exactly singular Gm leaves a
+            // pivot of a few ulps of its diagonal entry with either sign, so "not positive" alone would miss it
             const double d = L[j][j];
-            if (!(d > 0.0)) { bad = j + 1; L[j][j] = 1.0; } else L[j][j] = sqrt(d);
+            if (!(d > 16.0 * 2.220446049250313e-16 * Gm[j * kp + j])) { bad = j + 1; L[j][j] = 1.0; } else L[j][j] = sqrt(d);
         }
         __syncthreads();
         if (c == j && r > j && r < kk) L[r][j] /= L[j][j];
