@@ -176,6 +176,19 @@ int ruviii_prps(ruviii_handle* h, const double* Y, int64_t ldY, int32_t m1, int3
  * log transform, before RUV1) and never crosses PCIe.  The group ids of the PRPS rows still come in group_of_row. */
 int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps);
 
+/* ---- computePCA fast path (runs on every RUV_K* assay right after the path, normAssessment.R:113) ----------
+ * computePCA.R:120-134: runSVD(x = t(assay), k = nb.pcs, center, scale): top-k singular triplets of the samples x genes matrix
+ * after centring every gene over the samples (and dividing by its sd when scale, as base::scale does).
+ *   X != NULL : host matrix, m1 x n row-major (the assay bytes), log2(X + pseudo_count) first when apply_log (computePCA.R:124-127)
+ *   X == NULL : data already on the device -- slot >= 0: output block `slot` (the newY of ks[slot]) of the last ruviii_run;
+ *               slot == -1: the uploaded assay (after its own log transform).  m1, n, ldX are ignored.
+ *   u_out  m1 x k row-major (sing.val$u), d_out k (sing.val$d), v_out NULL or k x n row-major (= the bytes of R's n x k v).
+ *   Signs: each u_j has its largest-magnitude component positive; v_j follows.  k <= 32 and k < m1.
+ *   stage_ms6: NULL or 6 floats (device ms): upload+log, centre, Gram, allreduce+eigensolve, broadcast+projection, total. */
+int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+               double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,
+               float* stage_ms6);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca",
     "ruviii_fast_residop", "ruviii_probe",
 ]
 
@@ -96,6 +96,8 @@ def load_library():
     lib.ruviii_set_eta.argtypes = [H, vp, C.c_int32, C.c_int32]
     lib.ruviii_prps.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, C.c_int32, vp, C.c_int64]
     lib.ruviii_set_prps_sets.argtypes = [H, vp, vp, C.c_int32]
+    lib.ruviii_pca.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
+                               C.c_int32, vp, vp, vp, vp]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
     lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     for name in SYMBOLS:
@@ -266,6 +268,24 @@ class Engine:
         self._check(self._lib.ruviii_prps(self._h, _ptr(Y), Y.strides[0] // 8, Y.shape[0], Y.shape[1], int(bool(apply_log)),
                                           float(pseudo_count), _ptr(start), _ptr(rows), len(sets), _ptr(out), out.shape[1]))
         return out
+
+    def pca(self, X=None, k=10, slot=-1, apply_log=False, pseudo_count=1.0, center=True, scale=False, want_v=True):
+        """computePCA.R:120-134 fast path.  X: samples x genes host matrix, or None for data already on the device
+        (slot >= 0: output block of the last run, -1: the uploaded assay).  Returns dict(u m1 x k, d k, v n x k, stage_ms)."""
+        if X is not None:
+            X = _rowmajor(X, "X")
+            m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        else:
+            m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
+        u = np.empty((m1, k), dtype=np.float64)
+        d = np.empty(k, dtype=np.float64)
+        v = np.empty((k, n), dtype=np.float64) if want_v else None
+        ms = (C.c_float * 6)()
+        self._check(self._lib.ruviii_pca(self._h, ptr, ldx, m1, n, int(slot), int(bool(apply_log)), float(pseudo_count),
+                                         int(bool(center)), int(bool(scale)), int(k), _ptr(u), _ptr(d),
+                                         _ptr(v) if want_v else None, C.cast(ms, C.c_void_p)))
+        return dict(u=u, d=d, v=None if v is None else v.T, stage_ms=dict(zip(
+            ["upload_log", "center", "gram", "eigen", "project", "total"], [float(x) for x in ms])))
 
     def set_prps_sets(self, sets):
         """Fused K0: the next plans with n_ps = len(sets) build replicate.data on the device when PS is None."""

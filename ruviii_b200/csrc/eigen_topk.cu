@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace ruviii {
 
@@ -37,8 +39,41 @@ bool use_pdl() {
     return on;
 }
 
+// RUVIII_EIG_TRACE=1: an event after every kernel of the solve and a per-kernel table on stderr (in-situ, warm-cache times
+// including the launch gap; ncu flushes the caches between kernels, which inflates these latency-bound kernels 2-3x)
+struct EigTrace {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> name;
+    size_t used = 0;
+    void mark(const char* what, cudaStream_t s) {
+        if (!on) return;
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); name.push_back(what); }
+        name[used] = what;
+        cudaEventRecord(ev[used++], s);
+    }
+    void report() {
+        if (!on || used < 2) return;
+        cudaEventSynchronize(ev[used - 1]);
+        fprintf(stderr, "[eig trace]");
+        for (size_t i = 1; i < used; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s=%.1f", name[i], ms * 1e3f);
+        }
+        fprintf(stderr, " (us)\n");
+        used = 0;
+    }
+};
+EigTrace& eig_trace() {
+    static EigTrace t = [] { EigTrace x; const char* v = std::getenv("RUVIII_EIG_TRACE"); x.on = v && *v == '1'; return x; }();
+    return t;
+}
+#define EK_NAME(k) (strstr(#k, "init") ? "init" : strstr(#k, "gemm") ? "gemm" : strstr(#k, "ztz") ? "ztz" : strstr(#k, "ortho") ? "ortho" : \
+                    strstr(#k, "apply") ? "apply" : strstr(#k, "rr") ? "rr" : strstr(#k, "rotate") ? "rotate" : "finalize")
+
 template <class... KArgs, class... Args>
-void launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+void launch_dep_impl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -51,6 +86,11 @@ void launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, A
     cfg.numAttrs = 1;
     RUVIII_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
 }
+#define launch_dep(kern, grid, block, s, ...)              \
+    do {                                                   \
+        launch_dep_impl(kern, grid, block, s, __VA_ARGS__); \
+        eig_trace().mark(EK_NAME(kern), s);                \
+    } while (0)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -467,6 +507,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
     const int first = first_env > 0 ? (int)round_up(first_env, T) : 2 * T;
     int launches = 0;
     const dim3 g_rb(n_rb), one(1);
+    eig_trace().mark("start", s);
     launch_dep(ek_init_kernel<B>, dim3(ceil_div((int64_t)R * B, 256)), dim3(256), s, w.Zp, R, w.state);
     launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Zp, 1, (const double*)nullptr, R, w.Z, w.Sp, (double*)nullptr,
                (const int*)w.state);
@@ -522,6 +563,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
         RUVIII_LAUNCH_CHECK();
         res.launches += 1;
     }
+    eig_trace().report();
     return res;
 }
 

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -108,16 +109,22 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t count = 0;
+    // The clear runs on the legacy default stream, which does NOT order against the engine's non-blocking streams: wait for
+    // it, otherwise an asynchronous copy queued right after alloc() can be overwritten by the late memset.
+    static void clear(void* q, size_t bytes) {
+        RUVIII_CUDA_CHECK(cudaMemset(q, 0, bytes));
+        RUVIII_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     void alloc(size_t n, bool zero = true) {
         if (n <= count && p) {
-            if (zero) RUVIII_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+            if (zero) clear(p, n * sizeof(T));
             return;
         }
         release();
         if (n == 0) return;
         RUVIII_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
         count = n;
-        if (zero) RUVIII_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+        if (zero) clear(p, n * sizeof(T));
     }
     void release() {
         if (p) cudaFree(p);
@@ -140,6 +147,10 @@ struct Shard {
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
     DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
+    DevBuf<double> pX, pG, pWs, pU, pEv, pPart, pAlpha, pStat, pMean, pSd, pTopk, pEvAsc;   // computePCA fast path (ruviii_pca)
+    DevBuf<int2> pTiles;
+    DevBuf<int> pState;
+    TopkWork ptopk{};
     DevBuf<int2> tile_map;
     DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1, set_start, set_rows;
     TopkWork topk{};
@@ -225,7 +236,9 @@ ruviii_handle::~ruviii_handle() {
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
                                   &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
-                                  &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1};
+                                  &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1,
+                                  &s.pX, &s.pG, &s.pWs, &s.pU, &s.pEv, &s.pPart, &s.pAlpha, &s.pStat, &s.pMean, &s.pSd, &s.pTopk,
+                                  &s.pEvAsc};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -238,6 +251,8 @@ ruviii_handle::~ruviii_handle() {
         s.status1.release();
         s.set_start.release();
         s.set_rows.release();
+        s.pTiles.release();
+        s.pState.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
@@ -1260,6 +1275,164 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     h->pipelined_last = 1;
 }
 
+// ---- computePCA fast path --------------------------------------------------------------------------
+// computePCA.R:120-134: runSVD(t(assay), k = nb.pcs, center, scale) -- the top-k singular triplets of the centred samples x
+// genes matrix.  Sample-side route with the engine's own kernels: K10 centre -> K2 Gram Xc Xc' (genes sharded, allreduced)
+// -> K3 top-k eigenpairs (u, d^2) on rank 0 -> broadcast -> K4 projection t(u) Xc = diag(d) t(v).
+// source: X != NULL host matrix; X == NULL and slot >= 0: output block `slot` of the last run, already on the device
+// (normAssessment.R:113 runs computePCA on every RUV_K* assay right after normalise()); slot == -1: the resident input.
+void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
+            int center, int scale, int k, double* u_out, double* d_out, double* v_out, float* stage_ms) {
+    const bool resident = X == nullptr;
+    if (resident) {
+        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_pca on resident data needs a plan and an upload");
+        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_pca: no such output block");
+        m1 = h->m1;
+        n = h->n_local_total;
+    }
+    if (m1 < 2 || n <= 0 || k <= 0 || !u_out || !d_out) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: bad arguments");
+    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: row stride < n");
+    if (k > kMaxK || k >= m1) throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_pca: nb.pcs must be <= 32 and < the number of samples");
+    const int kp = pad_k(k), nsh = (int)h->shards.size();
+    const int n_keep = std::min(m1, k + 1);
+    const bool topk_ok = k <= kTopkBlock / 2 && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
+    h->launches = 0;
+    std::vector<GramPlan> gps(nsh);
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
+        const int blocks = colstat_blocks(m1, ng, h->n_sms);
+        s.pX.alloc((size_t)m1 * ld, !resident);
+        s.pStat.alloc((size_t)(blocks + 1) * ld, false);
+        s.pMean.alloc(ld);
+        s.pSd.alloc(ld);
+        GramPlan& gp = gps[i];
+        gp = plan_gram(m1, (int)ld, h->n_sms, h->gram_impl == 2 ? 1 : h->gram_impl);     // cp.async kernels (no tensor map to build)
+        s.pWs.alloc(gp.workspace_bytes / sizeof(double), false);
+        std::vector<int2> tm(gp.n_tiles);
+        fill_gram_tile_map(gp, tm.data());
+        s.pTiles.alloc(tm.size());
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.pTiles.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice, s.stream));
+        s.pG.alloc((size_t)m1 * m1, false);
+        s.pU.alloc((size_t)m1 * kp);
+        s.pEv.alloc(std::max(n_keep, kp) + 2);
+        const int rsplit = project_rsplit(m1, ng, h->n_sms);
+        s.pPart.alloc((size_t)rsplit * kp * ld, false);
+        s.pAlpha.alloc((size_t)kp * ld);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        const double* src = nullptr;
+        if (!resident) {
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.pX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
+            if (apply_log) { launch_log2_inplace(s.pX.p, ld, m1, ng, pseudo_count, s.stream); h->launches += 1; }   // computePCA.R:124-127
+            src = s.pX.p;
+        } else {
+            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+            if (apply_log) {                          // a resident block is copied before it is transformed: outputs stay intact
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.pX.p, src, (size_t)m1 * ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+                launch_log2_inplace(s.pX.p, ld, m1, ng, pseudo_count, s.stream);
+                h->launches += 1;
+                src = s.pX.p;
+            }
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+        // resident source: pX was not cleared, so the (zero) pitch padding is centred too and comes out as zeros
+        h->launches += launch_center_columns(src, ld, m1, resident ? (int)ld : ng, center, scale, blocks, s.pStat.p, s.pMean.p,
+                                             s.pSd.p, s.pX.p, ld, s.stream);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_RESIDOP], s.stream));
+        h->launches += launch_gram(gp, s.pX.p, ld, s.pTiles.p, s.pWs.p, s.pG.p, nullptr, s.stream);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_GRAM], s.stream));
+    }
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.pG.p);
+        allreduce_sum(h, b, (size_t)m1 * m1);
+    }
+    if (h->rank0 == 0) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        bool done = false;
+        if (topk_ok) {
+            s.pTopk.alloc(topk_work_doubles(m1, kTopkBlock), false);
+            s.pState.alloc(4);
+            topk_bind(s.ptopk, s.pTopk.p, s.pState.p, m1, kTopkBlock);
+            TopkResult tr = topk_eigen(s.pG.p, m1, k, kp, n_keep, kTopkBlock, s.ptopk, s.pU.p, s.pEv.p, h->eig_tol,
+                                       env_int("RUVIII_EIG_MAXIT", 150), h->n_sms, &h->h_flags[60], s.stream);
+            h->launches += tr.launches;
+            h->eig_iterations = tr.iterations;
+            done = tr.converged;
+        }
+        if (!done) {                                   // cuSOLVER: k > 16, small matrices, or no convergence
+            if (!h->solver) {
+                RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
+                RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
+            }
+            s.pEvAsc.alloc(m1);
+            int lwork = 0, meig = 0;
+            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                                             CUBLAS_FILL_MODE_UPPER, m1, s.pG.p, m1, 0.0, 0.0, m1 - n_keep + 1, m1,
+                                                             &meig, s.pEvAsc.p, &lwork));
+            h->solver_work.alloc((size_t)lwork, false);
+            h->solver_info.alloc(4);
+            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER,
+                                                  m1, s.pG.p, m1, 0.0, 0.0, m1 - n_keep + 1, m1, &meig, s.pEvAsc.p,
+                                                  h->solver_work.p, (int)h->solver_work.count, h->solver_info.p));
+            if (meig != n_keep) throw Error(RUVIII_ERR_SOLVER, "syevdx returned an unexpected number of eigenpairs");
+            launch_pick_top(s.pG.p, m1, s.pEvAsc.p, meig, m1, n_keep, k, kp, nullptr, s.pU.p, s.pEv.p, s.stream);
+            h->launches += 1;
+        }
+    }
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_EIG], s.stream));
+    }
+    {
+        std::vector<double*> b;
+        for (auto& s : h->shards) b.push_back(s.pU.p);
+        broadcast0(h, b, (size_t)m1 * kp);
+        b.clear();
+        for (auto& s : h->shards) b.push_back(s.pEv.p);
+        broadcast0(h, b, (size_t)std::max(n_keep, kp) + 2);
+    }
+    std::vector<double> ev(k);
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
+        const int rsplit = project_rsplit(m1, ng, h->n_sms);
+        launch_project(s.pX.p, ld, m1, ng, s.pU.p, kp, rsplit, s.pPart.p, ld, s.stream);
+        launch_alpha_finalize(s.pPart.p, rsplit, kp, ng, ld, s.pAlpha.p, nullptr, 0, nullptr, s.stream);
+        launch_v_from_alpha(s.pAlpha.p, s.pEv.p, k, ld, nullptr, s.stream);
+        h->launches += 3;
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_PROJECT], s.stream));
+        if (v_out)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(v_out + g0, (size_t)n * 8, s.pAlpha.p, ld * 8, (size_t)ng * 8, k, cudaMemcpyDeviceToHost,
+                                                s.stream));
+        if (i == 0) {
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(u_out, (size_t)k * 8, s.pU.p, (size_t)kp * 8, (size_t)k * 8, m1, cudaMemcpyDeviceToHost,
+                                                s.stream));
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(ev.data(), s.pEv.p, (size_t)k * 8, cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    sync_all(h);
+    for (int j = 0; j < k; ++j) d_out[j] = std::sqrt(std::max(ev[j], 0.0));
+    if (stage_ms) {
+        Shard& s = h->shards[0];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
+        stage_ms[0] = el(E_START, E_LOG);       // upload (+ log)
+        stage_ms[1] = el(E_LOG, E_RESIDOP);     // K10 centre / scale
+        stage_ms[2] = el(E_RESIDOP, E_GRAM);    // K2 Gram
+        stage_ms[3] = el(E_GRAM, E_EIG);        // allreduce + K3 eigensolve
+        stage_ms[4] = el(E_EIG, E_PROJECT);     // broadcast + K4 projection
+        stage_ms[5] = el(E_START, E_PROJECT);
+    }
+}
+
 template <class F>
 int guarded(ruviii_handle* h, F&& fn) {
     try {
@@ -1447,6 +1620,13 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
         for (int i = 0; i <= kMaxK; ++i) if (h->slot_of_k[i] < 0) h->slot_of_k[i] = 0;
         h->have_user_alpha = true;
     });
+}
+
+int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+               double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,
+               float* stage_ms6) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_pca(h, X, ldX, m1, n, slot, apply_log, pseudo_count, center, scale, k, u_out, d_out, v_out, stage_ms6); });
 }
 
 int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps) {

@@ -132,6 +132,12 @@ void launch_update_tma(const void* tmap_host, int rows, int n, const double* At_
                        int64_t ldat, int kk, uint64_t kmask, const int* out_slot_of_k, double* out, int64_t ldout,
                        int64_t out_stride, cudaStream_t s);
 
+// K10 computePCA.R:120-134  centre (and scale) the columns of a samples x genes matrix; v = t(alpha) / d  (pca.cu)
+int colstat_blocks(int rows, int n, int n_sms);
+int launch_center_columns(const double* X, int64_t ld, int rows, int n, int center, int scale, int blocks, double* part,
+                          double* mean, double* inv_sd, double* Xc, int64_t ldc, cudaStream_t s);   // returns kernels launched
+void launch_v_from_alpha(double* alpha, const double* evals, int kk, int64_t ld, double* d_out, cudaStream_t s);
+
 // micro-benchmarks (ceilings quoted beside the roofline)
 float probe_copy_gbs(size_t bytes, cudaStream_t s);
 float probe_dmma_tflops(int n_sms, cudaStream_t s);

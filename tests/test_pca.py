@@ -1,0 +1,67 @@
+"""computePCA fast path against the numpy oracle.  Singular vectors are sign-free: compared after
+aligning each component's sign; tolerance 1e-9 relative Frobenius like the rest of the path."""
+import numpy as np
+import pytest
+
+import ruviii_b200 as rv
+from oracle import pca_oracle as PCAO
+from oracle import ruviii_oracle as O
+from ruviii_b200 import _cabi, api
+from ruviii_b200.pca import computePCA
+from ruviii_b200.synth import make_problem
+
+
+def test_argument_errors_match_the_reference():
+    se = rv.SummarizedExperiment(assays={"a": np.ones((4, 3))}, col_names=["x", "y", "z"])
+    with pytest.raises(ValueError, match="number of PCs"):
+        computePCA(se, nb_pcs=0, verbose=False)
+    with pytest.raises(ValueError, match="at least an assay name"):
+        computePCA(se, assay_names=None, verbose=False)
+
+
+def _check(res, ref, k):
+    assert np.allclose(res["d"], ref["d"], rtol=1e-10, atol=0)
+    u = O.align_rows_sign(res["u"].T, ref["u"].T).T
+    v = O.align_rows_sign(res["v"].T, ref["v"].T).T
+    assert O.rel_frob(u, ref["u"]) < 1e-8 and O.rel_frob(v, ref["v"]) < 1e-8
+    # sign-free: the rank-k reconstruction
+    assert O.rel_frob((res["u"] * res["d"]) @ res["v"].T, (ref["u"] * ref["d"]) @ ref["v"].T) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,k,scale", [((300, 1203), 10, False), ((200, 515), 4, True), ((150, 90), 20, False)])
+def test_pca_matches_oracle(engine, shape, k, scale):
+    """k = 20 > 16 and the 150-sample case exercise the cuSOLVER route; the others the block subspace iteration."""
+    m1, n = shape
+    p = make_problem(m1=m1, n=n, groups=10, rep=3, n_ctl=40, k=3, seed=m1 + n, counts=True)
+    res = engine.pca(p.assay.T, k=k, apply_log=True, pseudo_count=1.0, center=True, scale=scale)
+    ref = PCAO.fast_pca(p.assay, k, True, 1.0, True, scale)
+    _check(res, ref, k)
+    assert res["u"].shape == (m1, k) and res["v"].shape == (n, k)
+
+
+@pytest.mark.gpu
+def test_pca_on_resident_outputs_and_r_api(engine):
+    """PCA of the normalised assays without leaving the device (slot = output block), and the computePCA mirror."""
+    p = make_problem(m1=260, n=1101, groups=20, rep=3, n_ctl=100, k=4, seed=77)
+    groups = api.group_codes(p.sample_names + p.replicate_names)
+    out = engine.normalise(_cabi.make_params(), p.Y, p.replicate_data, groups, p.ctl, [2, 4])
+    for slot in (0, 1):
+        res = engine.pca(None, k=6, slot=slot)
+        ref = PCAO.fast_pca(out["newY"][slot].T, 6, apply_log=False)
+        _check(res, ref, 6)
+    raw = engine.pca(None, k=6, slot=-1)                                   # the uploaded assay itself
+    _check(raw, PCAO.fast_pca(p.assay, 6, apply_log=False), 6)
+    again = engine.download()                                              # outputs are untouched by the PCA
+    assert np.array_equal(again["newY"][1], out["newY"][1])
+    se = rv.SummarizedExperiment(assays={"logcounts": p.assay, "RUV_K4_on_logcounts": out["newY"][1].T}, col_names=p.sample_names)
+    api.set_engine(engine)
+    try:
+        se = computePCA(se, "All", apply_log=False, nb_pcs=5, verbose=False)
+    finally:
+        api.set_engine(None)
+    for name in ("logcounts", "RUV_K4_on_logcounts"):
+        got = se.metadata["metric"][name]["fastPCA"]
+        ref = PCAO.fast_pca(se.assays[name], 5, apply_log=False)
+        assert np.array_equal(got["variation"], ref["variation"])
+        _check(got["sing_val"], ref, 5)
