@@ -230,13 +230,14 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
                 const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
                 double c = 1.0, s = 0.0;
                 if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
-                    // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written with one
-                    // sqrt, one division and one rsqrt (the rotation sits on the critical path of every round)
+                    // the rotation sits on the critical path of every round: cos(2 theta) = |zeta| / rr, |theta| <= pi / 4,
+                    // written with two rsqrt and no division:  c = sqrt((1 + cos 2theta) / 2),  s = sin 2theta / (2 c)
                     const double zeta = aqq - app, beta = 2.0 * apq;
-                    const double rr = sqrt(fma(zeta, zeta, beta * beta));
-                    const double t = beta / (zeta + (zeta >= 0.0 ? rr : -rr));
-                    c = rsqrt(fma(t, t, 1.0));
-                    s = t * c;
+                    const double irr = rsqrt(fma(zeta, zeta, beta * beta));
+                    const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
+                    const double ic = rsqrt(c2);
+                    c = c2 * ic;
+                    s = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
                     flag = 1;
                     if (apq * apq > 1e-20 * fabs(app * aqq)) flag_big = 1;
                 }
@@ -244,25 +245,28 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
                 pr[tid][0] = p; pr[tid][1] = q;
             }
             __syncthreads();
-            for (int e = tid; e < (B / 2) * B; e += nt) {         // rows p, q:  A <- J' A
-                const int i = e / B, j = e % B;
-                const int p = pr[i][0], q = pr[i][1];
-                const double c = cs[i][0], s = cs[i][1];
-                const double x = A[p][j], y = A[q][j];
-                A[p][j] = c * x - s * y;
-                A[q][j] = s * x + c * y;
-            }
-            __syncthreads();
-            for (int e = tid; e < (B / 2) * B; e += nt) {         // columns p, q:  A <- A J,  V <- V J
-                const int i = e / B, j = e % B;
-                const int p = pr[i][0], q = pr[i][1];
-                const double c = cs[i][0], s = cs[i][1];
-                const double x = A[j][p], y = A[j][q];
-                A[j][p] = c * x - s * y;
-                A[j][q] = s * x + c * y;
-                const double vx = W[j][p], vy = W[j][q];
-                W[j][p] = c * vx - s * vy;
-                W[j][q] = s * vx + c * vy;
+            if (tid < (B / 2) * (B / 2)) {
+                // A <- J' A J in one phase: thread (a, b) owns the 2 x 2 block rows (p, q) of pair a x columns (p', q') of pair b
+                const int a = tid / (B / 2), b2 = tid % (B / 2);
+                const int p = pr[a][0], q = pr[a][1], pp = pr[b2][0], qq = pr[b2][1];
+                const double c = cs[a][0], s = cs[a][1], cc = cs[b2][0], ss = cs[b2][1];
+                const double x00 = A[p][pp], x01 = A[p][qq], x10 = A[q][pp], x11 = A[q][qq];
+                const double r00 = c * x00 - s * x10, r01 = c * x01 - s * x11;      // rows:    J_a' X
+                const double r10 = s * x00 + c * x10, r11 = s * x01 + c * x11;
+                A[p][pp] = cc * r00 - ss * r01;                                      // columns: (.) J_b
+                A[p][qq] = ss * r00 + cc * r01;
+                A[q][pp] = cc * r10 - ss * r11;
+                A[q][qq] = ss * r10 + cc * r11;
+            } else {
+                // V <- V J: (row j, pair i) tasks for the other half of the CTA
+                for (int e = tid - (B / 2) * (B / 2); e < (B / 2) * B; e += nt - (B / 2) * (B / 2)) {
+                    const int i = e / B, j = e % B;
+                    const int p = pr[i][0], q = pr[i][1];
+                    const double c = cs[i][0], s = cs[i][1];
+                    const double vx = W[j][p], vy = W[j][q];
+                    W[j][p] = c * vx - s * vy;
+                    W[j][q] = s * vx + c * vy;
+                }
             }
             __syncthreads();
         }
@@ -330,11 +334,19 @@ ek_ortho_kernel(int check, const double* __restrict__ Sp, const double* __restri
         __syncthreads();
         if (flag) return;
     }
-    for (int e = tid; e < B * B; e += nt) {
-        double s = 0.0;
+    {
+        // S = sum of the row-block partials in a fixed order; the four elements of a thread are interleaved so that 32
+        // loads are in flight per thread (the kernel is one CTA: this phase is pure L2 latency)
+        constexpr int EPT = B * B / 256;
+        double acc[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) acc[u] = 0.0;
 #pragma unroll 8
-        for (int p = 0; p < n_part; ++p) s += Sp[(int64_t)p * B * B + e];      // unrolled: 8 loads in flight, fixed order
-        L[e / B][e % B] = s;
+        for (int p = 0; p < n_part; ++p)
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) acc[u] += Sp[(int64_t)p * B * B + tid + u * 256];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) L[(tid + u * 256) / B][(tid + u * 256) % B] = acc[u];
     }
     __syncthreads();
     if (tid < B) dscale[tid] = L[tid][tid] > 0.0 ? rsqrt(L[tid][tid]) : 1.0;

@@ -814,6 +814,8 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             });
             h->launches += 1;
         };
+        // RUVIII_GATHER_AT: 0 = fork after the Gram (default), 1 = after the residual (overlaps the Gram instead)
+        static const int gather_at = env_int("RUVIII_GATHER_AT", 0);
         if (h->have_user_alpha) fork_gather();
         if (!h->have_user_alpha) {
             for_shards([&](Shard& s) {
@@ -822,6 +824,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             });
             h->launches += 1;
             rec(E_RESIDOP);
+            if (gather_at == 1) fork_gather();
             const int GO = h->gorder;
             if (h->gene_side) {
                 // t(Z) restricted to the rows this shard contracts.  One shard: all of Z.  Several: all-to-all of row
@@ -871,7 +874,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 h->launches += 2;
             }
             rec(E_GRAM);
-            fork_gather();
+            if (gather_at == 0) fork_gather();
             {
                 std::vector<double*> b;
                 for (auto& s : h->shards) b.push_back(s.G.p);
@@ -1305,7 +1308,7 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
         const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
         const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
         const int blocks = colstat_blocks(m1, ng, h->n_sms);
-        s.pX.alloc((size_t)m1 * ld, !resident);
+        s.pX.alloc((size_t)m1 * ld, false);
         s.pStat.alloc((size_t)(blocks + 1) * ld, false);
         s.pMean.alloc(ld);
         s.pSd.alloc(ld);
@@ -1338,9 +1341,11 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
             }
         }
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
-        // resident source: pX was not cleared, so the (zero) pitch padding is centred too and comes out as zeros
-        h->launches += launch_center_columns(src, ld, m1, resident ? (int)ld : ng, center, scale, blocks, s.pStat.p, s.pMean.p,
-                                             s.pSd.p, s.pX.p, ld, s.stream);
+        h->launches += launch_center_columns(src, ld, m1, ng, center, scale, blocks, s.pStat.p, s.pMean.p, s.pSd.p, s.pX.p, ld, s.stream);
+        // the pitch padding takes part in the Gram's contraction: clear it after the centring (an output block's padding
+        // is never written by the update kernel, so what the centring read there is arbitrary)
+        if (ld > ng)
+            RUVIII_CUDA_CHECK(cudaMemset2DAsync(s.pX.p + ng, ld * 8, 0, (size_t)(ld - ng) * 8, m1, s.stream));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_RESIDOP], s.stream));
         h->launches += launch_gram(gp, s.pX.p, ld, s.pTiles.p, s.pWs.p, s.pG.p, nullptr, s.stream);
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_GRAM], s.stream));
