@@ -194,7 +194,7 @@ ek_ztz_kernel(const double* __restrict__ Zp, int nsplit, const double* __restric
 template <int B>
 __global__ void __launch_bounds__(512)
 ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, double* __restrict__ theta,
-             const int* __restrict__ state) {
+             int* __restrict__ state) {
     griddep_wait();
     if (state[0]) return;
     __shared__ double A[B][B + 1];
@@ -218,7 +218,9 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
     for (int e = tid; e < B * B; e += nt) W[e / B][e % B] = (e / B == e % B) ? 1.0 : 0.0;   // W = V
     __syncthreads();
     // parallel cyclic Jacobi, round-robin pairing: B/2 disjoint rotations per round, B-1 rounds per sweep
+    int sweeps_run = 0;
     for (int sweep = 0; sweep < 16; ++sweep) {
+        ++sweeps_run;
         if (tid == 0) { flag = 0; flag_big = 0; }
         __syncthreads();
         for (int round = 0; round < B - 1; ++round) {
@@ -275,6 +277,7 @@ ek_rr_kernel(const double* __restrict__ Hp, int n_part, double* __restrict__ V, 
         if (!flag || !flag_big) break;
         __syncthreads();
     }
+    if (tid == 0) state[3] = sweeps_run;          // reported by RUVIII_EIG_TRACE
     // sort descending (rank sort), write V with permuted columns
     if (tid < B) {
         const double t = A[tid][tid];
@@ -539,7 +542,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
             if (it % T == 0 && it >= first) {
                 launch_dep(ek_ztz_kernel<B>, g_rb, dim3(256), s, (const double*)w.Zp, splits, (const double*)w.Q, R, w.Z, w.Sp, w.Hp,
                            (const int*)w.state);
-                launch_dep(ek_rr_kernel<B>, one, dim3(512), s, (const double*)w.Hp, n_rb, w.V, w.theta, (const int*)w.state);
+                launch_dep(ek_rr_kernel<B>, one, dim3(512), s, (const double*)w.Hp, n_rb, w.V, w.theta, w.state);
                 launch_dep(ek_rotate_kernel<B>, g_rb, dim3(256), s, (const double*)w.Q, w.Z, (const double*)w.V, (const double*)w.theta, R,
                            w.X, w.Rp, (const int*)w.state);
                 // CHECK sets the flag; the ORTHO half needs S of the rotated block, so it is recomputed first
@@ -561,7 +564,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
             }
         }
         RUVIII_LAUNCH_CHECK();
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         for (int spin = 0; spin < (1 << 22) && cudaStreamQuery(s) == cudaErrorNotReady; ++spin) {}   // poll, do not sleep
         RUVIII_CUDA_CHECK(cudaStreamSynchronize(s));
         if (h_state[0]) break;
@@ -575,6 +578,7 @@ TopkResult run_topk(const double* G, int R, int kk, int kp, int n_keep, TopkWork
         RUVIII_LAUNCH_CHECK();
         res.launches += 1;
     }
+    if (eig_trace().on) fprintf(stderr, "[eig trace] jacobi sweeps in the last Rayleigh-Ritz: %d\n", h_state[3]);
     eig_trace().report();
     return res;
 }
