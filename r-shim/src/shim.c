@@ -111,10 +111,61 @@ SEXP _RUVIIIPRPS_fastResidop(SEXP A, SEXP B) {
 }
 SEXP _RUVIIIPRPS_fastResidop2(SEXP A, SEXP B) { return _RUVIIIPRPS_fastResidop(A, B); }
 
+/* ruvIII.R:116 / fastruvIII.R:133-134  RUV1(Y, eta, ctl): tEta = t(design.matrix(eta, include.intercept)) is q x n in R, whose
+ * column-major bytes are n x q row-major -- the engine wants q x n row-major, i.e. the bytes of the n x q design matrix
+ * itself, so the R side passes design.matrix(eta) (n x q) untransposed.  NULL clears. */
+SEXP _RUVIIIPRPS_setEta(SEXP design) {
+    ruviii_handle* h = engine();
+    int rc = Rf_isNull(design) ? ruviii_set_eta(h, NULL, 0, 0)
+                               : ruviii_set_eta(h, REAL(design), Rf_ncols(design), Rf_nrows(design));
+    if (rc != RUVIII_OK) Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    return R_NilValue;
+}
+
+/* prpsForCategoricalUV.R:123-139 / prpsForContinuousUV.R:190-201: every pseudo-sample is rowMeans(expre.data[, index]).
+ * setStart (length n_ps + 1, 0-based CSR offsets) and setRows (0-based column indices of the assay) come from the
+ * table() / dplyr bookkeeping that stays in R.  Returns genes x pseudo-samples, as metadata$PRPS stores it. */
+SEXP _RUVIIIPRPS_prpsMeans(SEXP assay, SEXP setStart, SEXP setRows, SEXP applyLog, SEXP pseudoCount) {
+    const int n = Rf_nrows(assay), m1 = Rf_ncols(assay), n_ps = LENGTH(setStart) - 1;
+    ruviii_handle* h = engine();
+    SEXP ps = PROTECT(Rf_allocMatrix(REALSXP, n, n_ps));
+    if (ruviii_prps(h, REAL(assay), n, m1, n, Rf_asLogical(applyLog), Rf_asReal(pseudoCount), INTEGER(setStart),
+                    INTEGER(setRows), n_ps, REAL(ps), n) != RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    }
+    UNPROTECT(1);
+    return ps;
+}
+
+/* computePCA.R:128-134  runSVD(x = transpose(temp.data), k = nb.pcs, center, scale): list(u = m1 x k, d, v = n x k).
+ * The engine returns u as m1 x k row-major = the bytes of a k x m1 R matrix (the R side applies t()); v comes back as
+ * k x n row-major = exactly R's n x k column-major v. */
+SEXP _RUVIIIPRPS_fastPCA(SEXP assay, SEXP k, SEXP applyLog, SEXP pseudoCount, SEXP center, SEXP scale) {
+    const int n = Rf_nrows(assay), m1 = Rf_ncols(assay), kk = Rf_asInteger(k);
+    ruviii_handle* h = engine();
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP tu = PROTECT(Rf_allocMatrix(REALSXP, kk, m1)), d = PROTECT(Rf_allocVector(REALSXP, kk)),
+         v = PROTECT(Rf_allocMatrix(REALSXP, n, kk));
+    if (ruviii_pca(h, REAL(assay), n, m1, n, -1, Rf_asLogical(applyLog), Rf_asReal(pseudoCount), Rf_asLogical(center),
+                   Rf_asLogical(scale), kk, REAL(tu), REAL(d), REAL(v), NULL) != RUVIII_OK) {
+        UNPROTECT(4);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    }
+    SET_VECTOR_ELT(out, 0, tu);
+    SET_VECTOR_ELT(out, 1, d);
+    SET_VECTOR_ELT(out, 2, v);
+    UNPROTECT(4);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"_RUVIIIPRPS_ruvIIICore", (DL_FUNC)&_RUVIIIPRPS_ruvIIICore, 9},
     {"_RUVIIIPRPS_fastResidop", (DL_FUNC)&_RUVIIIPRPS_fastResidop, 2},
     {"_RUVIIIPRPS_fastResidop2", (DL_FUNC)&_RUVIIIPRPS_fastResidop2, 2},
+    {"_RUVIIIPRPS_setEta", (DL_FUNC)&_RUVIIIPRPS_setEta, 1},
+    {"_RUVIIIPRPS_prpsMeans", (DL_FUNC)&_RUVIIIPRPS_prpsMeans, 5},
+    {"_RUVIIIPRPS_fastPCA", (DL_FUNC)&_RUVIIIPRPS_fastPCA, 6},
     {NULL, NULL, 0}};
 
 void R_init_RUVIIIPRPS(DllInfo* dll) {

@@ -1115,7 +1115,12 @@ const void* host_pinned(const void* p) {
 
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out) {
     if (h->n_ps > 0 && !PS) return false;      // replicate.data is built on the device from the whole assay
-    const int off = env_int("RUVIII_NO_PIPELINE", 0);
+    // RUVIII_PIPELINE: 0 = auto, 1 = always when eligible, 2 = never.  Auto takes the zero-copy pipeline on a single shard
+    // only: the scattered 8-byte reads of the control columns are bound by the HOST side of PCIe (request rate of the root
+    // complex: 19 ms for 11 M reads whether one GPU issues them or eight, r01p8), so with N shards the gather costs as much
+    // as at N = 1 while each shard's copies shrink by N -- 33 ms at N = 8 against ~10 ms for upload -> run -> download.
+    const int mode = env_int("RUVIII_PIPELINE", env_int("RUVIII_NO_PIPELINE", 0) ? 2 : 0);
+    const bool off = mode == 2 || (mode == 0 && h->world > 1);
     const bool skip = h->no_replicates || h->kk == 0;
     return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
            h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;
@@ -1137,6 +1142,11 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     // row chunks of ~1/12 of the assay (>= 256 rows, multiple of 64)
     const int chunk = (int)round_up(std::max(256, ceil_div(m1, 12)), 64);
     const int n_chunks = ceil_div(m1, chunk);
+    // RUVIII_ZC_PCT: share of the row chunks (the LAST ones in upload order) whose control columns come by zero-copy
+    const int zc_pct = std::max(0, std::min(100, env_int("RUVIII_ZC_PCT", 67)));
+    const int n_zc = std::min(n_chunks, (n_chunks * zc_pct + 50) / 100);
+    const int lead = n_chunks - n_zc;
+    const int row_zc0 = std::min(m1, lead * chunk);
     for_shards([&](Shard& s) {
         while ((int)s.ev_chunk.size() < n_chunks + 2) {
             cudaEvent_t e;
@@ -1151,17 +1161,33 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
                                                 cudaMemcpyHostToDevice, s.copy_stream));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[n_chunks], s.copy_stream));          // PS resident
+        // control columns of the PRPS rows (STACKED mode): from the device copy, right behind its upload
+        if (h->rows_w > m1 && s.n_ctl > 0) {
+            RowSrc ps_src{nullptr, 0, s.PS.p, s.ld, 0};
+            launch_ctl_gather(ps_src, h->rows_w - m1, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)m1 * s.ldc, s.ldc, 0, 0.0, s.copy_stream);
+        }
         for (int c = 0; c < n_chunks; ++c) {
             const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8,
                                                 (size_t)s.n * 8, rows, cudaMemcpyHostToDevice, s.copy_stream));
             RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
+            if (c < lead && s.n_ctl > 0) {
+                // leading chunks: their control columns are gathered on the device as soon as the chunk has landed
+                RowSrc dsrc{s.Y.p + (size_t)r0 * s.ld, s.ld, nullptr, 0, rows};
+                launch_ctl_gather(dsrc, rows, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)r0 * s.ldc, s.ldc, h->prm.apply_log ? rows : 0,
+                                  h->prm.pseudo_count, s.copy_stream);
+            }
+            if (c == lead - 1) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // device-side gathers complete
         }
-        // --- zero-copy gather of the control columns out of the pinned host assay (d2h stream, idle until K6) ---
-        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.d2h_stream, s.ev_chunk[n_chunks], 0));   // PS rows come from the device copy
-        RowSrc hsrc{static_cast<const double*>(host_pinned(Y)) + s.g0, ldY, s.PS.p, s.ld, m1};
-        launch_ctl_gather(hsrc, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, h->prm.apply_log ? m1 : 0,
-                          h->prm.pseudo_count, s.d2h_stream);
+        if (lead == 0) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));
+        // --- trailing chunks: zero-copy gather of their control columns out of the pinned host assay (d2h stream, idle
+        //     until K6).  It starts at once; the split between the two routes balances its ~19 ms per 11 M scattered reads
+        //     (bound by the host side of PCIe) against the upload time of the leading chunks. ---
+        if (row_zc0 < m1) {
+            RowSrc hsrc{static_cast<const double*>(host_pinned(Y)) + (size_t)row_zc0 * ldY + s.g0, ldY, nullptr, 0, m1 - row_zc0};
+            launch_ctl_gather(hsrc, m1 - row_zc0, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)row_zc0 * s.ldc, s.ldc,
+                              h->prm.apply_log ? m1 - row_zc0 : 0, h->prm.pseudo_count, s.d2h_stream);
+        }
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.d2h_stream));
         // --- K1, K2 on the PRPS rows ---
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[n_chunks], 0));
@@ -1189,10 +1215,11 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
         launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
         RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));
+        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_fork, 0));
         launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
                             s.n_ctl > 0 ? s.Yc.p : nullptr, s.ldc, s.stream);
     });
-    h->launches += 5;
+    h->launches += 5 + lead;
     {
         std::vector<double*> b;
         for (auto& s : h->shards) b.push_back(s.AG.p);
