@@ -338,6 +338,7 @@ def main():
     if args.probes and world == 1:
         probes = {"copy_gbs": eng.probe(0, 2048), "cublas_dgemm_tflops_8192": eng.probe(1, 8192),
                   "dmma_issue_tflops": eng.probe(2, 0), "host_gather_11000x1000_ms": eng.probe(3, 1000),
+                  "pcie_duplex_gbs_1GiB_each_way": eng.probe(6, 1024),
                   "copy_variants_gbs": dict(zip(["linear", "tiled_r4_plain", "tiled_r4_hint", "tiled_r8_hint", "tiled_r4_hint_16rows",
                                                  "tiled_r4_hint_1600rows", "tiled_r16_hint", "tiled_r2_plain"],
                                                 [round(eng.probe(4, i), 1) for i in range(8)]))}

@@ -209,7 +209,9 @@ int ruviii_barrier(ruviii_handle* h);
 /* which: 0 = device copy GB/s (bytes read+written), 1 = cuBLAS Dgemm TFLOP/s at size^3, 2 = DMMA issue peak TFLOP/s,
  *        3 = ms to gather 11,000 x `size` scattered doubles out of pinned host memory (zero-copy over PCIe),
  *        4 = GB/s of copy variant `size` (0 linear; 1..7 the update kernel's tiling with different rows in flight,
- *            rows per CTA and cache hints) over an 11,000 x 20,000 matrix */
+ *            rows per CTA and cache hints) over an 11,000 x 20,000 matrix,
+ *        5 = median us of an in-place FP64 allreduce of `size` KiB over all shards (every rank must call),
+ *        6 = aggregate GB/s of `size` MiB host->device plus `size` MiB device->host copied simultaneously (PCIe duplex) */
 int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_out);
 
 #ifdef __cplusplus

@@ -1166,6 +1166,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
             RowSrc ps_src{nullptr, 0, s.PS.p, s.ld, 0};
             launch_ctl_gather(ps_src, h->rows_w - m1, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)m1 * s.ldc, s.ldc, 0, 0.0, s.copy_stream);
         }
+        if (lead == 0) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // nothing but the PRPS rows is gathered here
         for (int c = 0; c < n_chunks; ++c) {
             const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8,
@@ -1179,7 +1180,6 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
             }
             if (c == lead - 1) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // device-side gathers complete
         }
-        if (lead == 0) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));
         // --- trailing chunks: zero-copy gather of their control columns out of the pinned host assay (d2h stream, idle
         //     until K6).  It starts at once; the split between the two routes balances its ~19 ms per 11 M scattered reads
         //     (bound by the host side of PCIe) against the upload time of the leading chunks. ---
@@ -1877,6 +1877,30 @@ int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_ou
             for (size_t i = 0; i < h->shards.size(); ++i) { cudaSetDevice(h->shards[i].device); bufs[i].release(); }
             std::sort(t.begin(), t.end());
             *value_out = 1e3 * t[t.size() / 2];
+        } else if (which == 6) {
+            // aggregate GB/s of `size` MiB host->device and `size` MiB device->host copied AT THE SAME TIME (pinned memory, two
+            // streams): what the overlapped part of ruviii_normalise can expect from the full-duplex link
+            const size_t bytes = (size_t)std::max(size, 16) << 20;
+            void *hin = nullptr, *hout = nullptr;
+            RUVIII_CUDA_CHECK(cudaHostAlloc(&hin, bytes, cudaHostAllocDefault));
+            RUVIII_CUDA_CHECK(cudaHostAlloc(&hout, bytes, cudaHostAllocDefault));
+            std::memset(hin, 1, bytes);
+            std::memset(hout, 0, bytes);
+            DevBuf<double> din, dout;
+            din.alloc(bytes / 8, false);
+            dout.alloc(bytes / 8);
+            double best = 1e30;
+            for (int it = 0; it < 3; ++it) {
+                sync_all(h);
+                const auto t0 = std::chrono::steady_clock::now();
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(din.p, hin, bytes, cudaMemcpyHostToDevice, s.copy_stream));
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(hout, dout.p, bytes, cudaMemcpyDeviceToHost, s.d2h_stream));
+                sync_all(h);
+                best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            }
+            din.release(); dout.release();
+            cudaFreeHost(hin); cudaFreeHost(hout);
+            *value_out = 2.0 * (double)bytes / best / 1e9;
         } else if (which == 4) {
             double r[8];
             probe_copy_variants(r, s.stream);
