@@ -1143,10 +1143,20 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     const int chunk = (int)round_up(std::max(256, ceil_div(m1, 12)), 64);
     const int n_chunks = ceil_div(m1, chunk);
     // RUVIII_ZC_PCT: share of the row chunks (the LAST ones in upload order) whose control columns come by zero-copy
-    const int zc_pct = std::max(0, std::min(100, env_int("RUVIII_ZC_PCT", 67)));
+    const int zc_pct = std::max(0, std::min(100, env_int("RUVIII_ZC_PCT", 83)));
     const int n_zc = std::min(n_chunks, (n_chunks * zc_pct + 50) / 100);
     const int lead = n_chunks - n_zc;
     const int row_zc0 = std::min(m1, lead * chunk);
+    // RUVIII_PIPE_TRACE=1: timestamps (ms after entry, shard 0) of the milestones of the overlapped pipeline on stderr
+    static const bool trace = env_int("RUVIII_PIPE_TRACE", 0) != 0;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* what, Shard& s, cudaStream_t st) {
+        if (!trace || &s != &h->shards[0]) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(what, e);
+    };
     for_shards([&](Shard& s) {
         while ((int)s.ev_chunk.size() < n_chunks + 2) {
             cudaEvent_t e;
@@ -1161,6 +1171,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
                                                 cudaMemcpyHostToDevice, s.copy_stream));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[n_chunks], s.copy_stream));          // PS resident
+        mark("ps_uploaded", s, s.copy_stream);
         // control columns of the PRPS rows (STACKED mode): from the device copy, right behind its upload
         if (h->rows_w > m1 && s.n_ctl > 0) {
             RowSrc ps_src{nullptr, 0, s.PS.p, s.ld, 0};
@@ -1178,8 +1189,12 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
                 launch_ctl_gather(dsrc, rows, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)r0 * s.ldc, s.ldc, h->prm.apply_log ? rows : 0,
                                   h->prm.pseudo_count, s.copy_stream);
             }
-            if (c == lead - 1) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // device-side gathers complete
+            if (c == lead - 1) {
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // device-side gathers complete
+                mark("lead_chunks_uploaded+gathered", s, s.copy_stream);
+            }
         }
+        mark("all_uploaded", s, s.copy_stream);
         // --- trailing chunks: zero-copy gather of their control columns out of the pinned host assay (d2h stream, idle
         //     until K6).  It starts at once; the split between the two routes balances its ~19 ms per 11 M scattered reads
         //     (bound by the host side of PCIe) against the upload time of the leading chunks. ---
@@ -1189,6 +1204,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
                               h->prm.apply_log ? m1 - row_zc0 : 0, h->prm.pseudo_count, s.d2h_stream);
         }
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.d2h_stream));
+        mark("zero_copy_gather_done", s, s.d2h_stream);
         // --- K1, K2 on the PRPS rows ---
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[n_chunks], 0));
         RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
@@ -1231,6 +1247,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
         launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
         launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
         launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
+        mark("W_known", s, s.stream);
         const int64_t stride = (int64_t)m1 * s.ld;
         // --- K6 per chunk as it lands, download right behind it ---
         for (int c = 0; c < n_chunks; ++c) {
@@ -1249,7 +1266,10 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
                 RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY_out + (size_t)i * m1 * n + (size_t)r0 * n + s.g0, n * 8,
                                                     s.out.p + (size_t)i * stride + (size_t)r0 * s.ld, s.ld * 8, (size_t)s.n * 8,
                                                     rows, cudaMemcpyDeviceToHost, s.d2h_stream));
+            if (c == 0) mark("first_chunk_downloaded", s, s.d2h_stream);
+            if (c == n_chunks / 2) mark("half_downloaded", s, s.d2h_stream);
         }
+        mark("all_downloaded", s, s.d2h_stream);
         size_t off = 0;
         for (int i = 0; i < nk; ++i) {
             launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
@@ -1275,6 +1295,16 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     }
     sync_all(h);
     const double t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (trace) {
+        fprintf(stderr, "[pipe trace] zc_pct=%d chunks=%d lead=%d:", zc_pct, n_chunks, lead);
+        for (auto& mk : marks) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->shards[0].ev[E_START], mk.second);
+            fprintf(stderr, " %s=%.2f", mk.first, ms);
+            cudaEventDestroy(mk.second);
+        }
+        fprintf(stderr, " host_total=%.2f (ms)\n", (t_done - t_enter) * 1e3);
+    }
     if (h->rank0 == 0 && h->h_flags[0] != 0)
         throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
     for (size_t i = 0; i < h->shards.size(); ++i)
@@ -1762,7 +1792,11 @@ int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double
     if (!h) return RUVIII_ERR_INVALID;
     return guarded(h, [&] {
         if (!newY_out) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
+        const auto tp0 = std::chrono::steady_clock::now();
         do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk);
+        if (env_int("RUVIII_PIPE_TRACE", 0))
+            fprintf(stderr, "[pipe trace] plan=%.2f ms\n",
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
         h->pipelined_last = 0;
         if (can_pipeline(h, Y, PS, newY_out, newY_ps_out)) {
             if ((m1 > 0 && ldY < n) || (n_ps > 0 && (!PS || ldPS < n))) throw Error(RUVIII_ERR_INVALID, "row stride < n");
