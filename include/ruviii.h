@@ -189,6 +189,19 @@ int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32
                double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,
                float* stage_ms6);
 
+/* ---- negative-control-gene statistics (the other step immediately before the path) ---------------------
+ * supervisedFindNCG.R:179-191,326-341: matrixTests::row_oneway_equalvar(x, g)$statistic -- the one-way ANOVA F statistic of
+ * every gene across the levels of a categorical variable; :214-229,270-285: Rfast::correls(y, x, type = "pearson") -- the
+ * Pearson correlation of every gene with a continuous variable.  Neither package is vendored in the reference; the
+ * definitions are the textbook ones (stats.cu).  Ranking, rounding and the rank product (:342-357) stay on the host.
+ *   X / slot         as in ruviii_pca (host matrix m1 x n row-major, or data resident on the device)
+ *   group_of_sample  NULL, or m1 ids; samples with id < 0 are left out (levels with < 3 samples, :183-185); needs F_out (n)
+ *   covariate        NULL, or m1 values; needs r_out (n).  With both, r is taken over the samples the ANOVA keeps.
+ *   ms_out           NULL or the device time of the pass */
+int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+                      double pseudo_count, const int32_t* group_of_sample, const double* covariate, double* F_out, double* r_out,
+                      float* ms_out);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

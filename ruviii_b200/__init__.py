@@ -9,6 +9,8 @@ from .api import (ReplicateData, SummarizedExperiment, fastruvIII, get_engine, g
                   ruvIIIMultipleK, set_engine)
 from .prps import (prpsForCategoricalUV, prpsForContinuousUV, supervisedPRPS,  # noqa: F401
                    replicate_data_from_metadata)
+from .pca import computePCA  # noqa: F401
+from .ncg import supervisedFindNCG  # noqa: F401
 from ._cabi import Engine, RuviiiError, make_params, MODE_FAST, MODE_STACKED  # noqa: F401
 
 __version__ = "0.1.0"

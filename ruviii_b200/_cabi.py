@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats",
     "ruviii_fast_residop", "ruviii_probe",
 ]
 
@@ -96,6 +96,7 @@ def load_library():
     lib.ruviii_set_eta.argtypes = [H, vp, C.c_int32, C.c_int32]
     lib.ruviii_prps.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, C.c_int32, vp, C.c_int64]
     lib.ruviii_set_prps_sets.argtypes = [H, vp, vp, C.c_int32]
+    lib.ruviii_gene_stats.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
     lib.ruviii_pca.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                C.c_int32, vp, vp, vp, vp]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
@@ -286,6 +287,27 @@ class Engine:
                                          _ptr(v) if want_v else None, C.cast(ms, C.c_void_p)))
         return dict(u=u, d=d, v=None if v is None else v.T, stage_ms=dict(zip(
             ["upload_log", "center", "gram", "eigen", "project", "total"], [float(x) for x in ms])))
+
+    def gene_stats(self, X=None, groups=None, covariate=None, slot=-1, apply_log=False, pseudo_count=1.0):
+        """K11: per-gene one-way ANOVA F across ``groups`` (ids < 0 are left out) and / or Pearson correlation with
+        ``covariate`` (supervisedFindNCG.R:179-191,214-229).  Returns dict(F, r, ms)."""
+        if X is not None:
+            X = _rowmajor(X, "X")
+            m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        else:
+            m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
+        g = None if groups is None else np.ascontiguousarray(groups, dtype=np.int32)
+        c = None if covariate is None else np.ascontiguousarray(covariate, dtype=np.float64)
+        if (g is not None and g.shape[0] != m1) or (c is not None and c.shape[0] != m1):
+            raise RuviiiError(ERR_INVALID, "groups / covariate need one entry per sample")
+        F = np.empty(n, dtype=np.float64) if g is not None else None
+        r = np.empty(n, dtype=np.float64) if c is not None else None
+        ms = C.c_float(0.0)
+        self._check(self._lib.ruviii_gene_stats(self._h, ptr, ldx, m1, n, int(slot), int(bool(apply_log)), float(pseudo_count),
+                                                None if g is None else _ptr(g), None if c is None else _ptr(c),
+                                                None if F is None else _ptr(F), None if r is None else _ptr(r),
+                                                C.cast(C.byref(ms), C.c_void_p)))
+        return dict(F=F, r=r, ms=float(ms.value))
 
     def set_prps_sets(self, sets):
         """Fused K0: the next plans with n_ps = len(sets) build replicate.data on the device when PS is None."""

@@ -274,9 +274,9 @@ def normalise(se_obj, assay_name, apply_log=True, pseudo_count=1, bio_variable_p
               assess_se_obj=True, remove_na="both", verbose=True):
     """R/normalise.R:61-167: supervisedPRPS -> supervisedFindNCG -> ruvIIIMultipleK.
 
-    The PRPS step runs on the device (:mod:`ruviii_b200.prps`); the RUV-III step is the engine.  Negative-control gene
-    selection (``supervisedFindNCG``, normalise.R:127-141) is outside the rebuilt path: the logical
-    vector it would leave in ``metadata$NCG`` must already be there."""
+    PRPS construction (:mod:`ruviii_b200.prps`), the negative-control gene statistics (:mod:`ruviii_b200.ncg`) and the
+    RUV-III step all run on the device.  ``norm_assay_name_ncg = None`` with ``metadata$NCG`` already present skips the
+    selection (an extension: the reference stops when the argument is missing, normalise.R:103-106)."""
     from . import prps
     _printColoredMessage("------------The normalise function starts.", verbose)
     if k is None:
@@ -288,9 +288,16 @@ def normalise(se_obj, assay_name, apply_log=True, pseudo_count=1, bio_variable_p
     se_obj = prps.supervisedPRPS(se_obj, assay_name, bio_variable_prps, uv_variables_prps, batch_variable_prps,
                                  min_sample_for_prps, min_sample_per_batch_prps, apply_log, pseudo_count, assess_se_obj,
                                  assess_cor_variables_prps, save_se_obj=True, verbose=verbose)          # :110-124
-    if "NCG" not in se_obj.metadata:
-        raise NotImplementedError("supervisedFindNCG (normalise.R:127-141) is not part of the CUDA path: put the negative "
-                                  "control genes (logical vector) into se_obj.metadata['NCG'] first")
+    if norm_assay_name_ncg is None and "NCG" not in se_obj.metadata:
+        raise ValueError("norm.assay.name.ncg is empty. Please select an assay to use for the Negative Control Genes selection")
+    if norm_assay_name_ncg is not None:                                                               # :127-141
+        from .ncg import supervisedFindNCG
+        se_obj = supervisedFindNCG(se_obj, norm_assay_name_ncg, bio_variables_ncg, uv_variables_ncg, no_ncg=no_ncg,
+                                   regress_out_uv_variables=regress_out_uv_variables_ncg,
+                                   regress_out_bio_variables=regress_out_bio_variables_ncg,
+                                   apply_normalization=apply_normalization_ncg, normalization=normalization_ncg,
+                                   apply_log=apply_log, pseudo_count=pseudo_count, assess_se_obj=assess_se_obj,
+                                   save_se_obj=True, verbose=verbose)
     replicate_data = prps.replicate_data_from_metadata(se_obj)                                        # :143
     se_obj = ruvIIIMultipleK(se_obj, assay_name, apply_log=apply_log, pseudo_count=pseudo_count,
                              replicate_data=replicate_data, ctl=se_obj.metadata["NCG"], k=k, eta=eta,

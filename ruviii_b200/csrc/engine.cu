@@ -148,6 +148,8 @@ struct Shard {
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
     DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
     DevBuf<double> pX, pG, pWs, pU, pEv, pPart, pAlpha, pStat, pMean, pSd, pTopk, pEvAsc;   // computePCA fast path (ruviii_pca)
+    DevBuf<double> gX, gPart, gCov, gF, gR;     // gene statistics (ruviii_gene_stats)
+    DevBuf<int> gStart, gRows, gGroup;
     DevBuf<int2> pTiles;
     DevBuf<int> pState;
     TopkWork ptopk{};
@@ -238,7 +240,7 @@ ruviii_handle::~ruviii_handle() {
                                   &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
                                   &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1,
                                   &s.pX, &s.pG, &s.pWs, &s.pU, &s.pEv, &s.pPart, &s.pAlpha, &s.pStat, &s.pMean, &s.pSd, &s.pTopk,
-                                  &s.pEvAsc};
+                                  &s.pEvAsc, &s.gX, &s.gPart, &s.gCov, &s.gF, &s.gR};
         for (auto b : bufs) b->release();
         s.tile_map.release();
         s.ctl_idx.release();
@@ -253,6 +255,9 @@ ruviii_handle::~ruviii_handle() {
         s.set_rows.release();
         s.pTiles.release();
         s.pState.release();
+        s.gStart.release();
+        s.gRows.release();
+        s.gGroup.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
@@ -1495,6 +1500,106 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
     }
 }
 
+// ---- negative-control-gene statistics ---------------------------------------------------------------
+// supervisedFindNCG.R:179-191,326-341 (row_oneway_equalvar(x, g)$statistic) and :214-229,270-285 (correls(y, x, "pearson")).
+// One streaming pass per call (K11, stats.cu).  Samples with group id < 0 are left out (the reference drops levels with
+// fewer than three samples, :183-185); without groups every sample takes part and only the correlation is produced.
+void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
+                   const int32_t* group, const double* covariate, double* F_out, double* r_out, float* ms_out) {
+    const bool resident = X == nullptr;
+    if (resident) {
+        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats on resident data needs a plan and an upload");
+        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats: no such output block");
+        m1 = h->m1;
+        n = h->n_local_total;
+    }
+    if (m1 < 2 || n <= 0 || (!group && !covariate) || (group && !F_out) || (covariate && !r_out))
+        throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: bad arguments");
+    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: row stride < n");
+    // ---- pieces: groups in ascending id order, each cut into runs of at most piece_rows samples ----
+    std::map<int32_t, std::vector<int>> groups;
+    if (group) {
+        for (int i = 0; i < m1; ++i)
+            if (group[i] >= 0) groups[group[i]].push_back(i);
+    } else {
+        for (int i = 0; i < m1; ++i) groups[0].push_back(i);
+    }
+    int n_rows = 0;
+    for (auto& kv : groups) n_rows += (int)kv.second.size();
+    const int n_groups = (int)groups.size();
+    if (group && (n_groups < 2 || n_rows <= n_groups)) throw Error(RUVIII_ERR_INVALID, "one-way ANOVA needs >= 2 groups and N > G");
+    if (n_rows < 2) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: fewer than two samples");
+    const int nsh = (int)h->shards.size();
+    const int piece_rows = gene_stats_piece_rows(std::max(1, n / nsh), n_rows, h->n_sms);
+    std::vector<int> pstart{0}, prow, pgroup;
+    int gi = 0;
+    for (auto& kv : groups) {
+        const std::vector<int>& rows = kv.second;
+        for (size_t a = 0; a < rows.size(); a += piece_rows) {
+            const size_t b = std::min(rows.size(), a + piece_rows);
+            prow.insert(prow.end(), rows.begin() + a, rows.begin() + b);
+            pstart.push_back((int)prow.size());
+            pgroup.push_back(gi);
+        }
+        ++gi;
+    }
+    const int n_pieces = (int)pgroup.size();
+    // centred covariate over the samples that take part (Pearson: sum c = 0)
+    std::vector<double> c(m1, 0.0);
+    double cov_ss = 1.0;
+    if (covariate) {
+        long double mean = 0.0L;
+        for (int r : prow) mean += covariate[r];
+        mean /= n_rows;
+        long double ss = 0.0L;
+        for (int r : prow) { c[r] = (double)(covariate[r] - mean); ss += (long double)c[r] * c[r]; }
+        cov_ss = (double)ss;
+    }
+    h->launches = 0;
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        if (ng <= 0) continue;
+        const int64_t ld = resident ? s.ld : round_up(ng, kRowAlign);
+        s.gStart.alloc(pstart.size(), false);
+        s.gRows.alloc(prow.size(), false);
+        s.gGroup.alloc(pgroup.size(), false);
+        s.gPart.alloc((size_t)n_pieces * 3 * ld, false);
+        s.gF.alloc(ld, false);
+        s.gR.alloc(ld, false);
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gStart.p, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gRows.p, prow.data(), prow.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gGroup.p, pgroup.data(), pgroup.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        if (covariate) {
+            s.gCov.alloc(m1, false);
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gCov.p, c.data(), (size_t)m1 * 8, cudaMemcpyHostToDevice, s.stream));
+        }
+        const double* src;
+        if (!resident) {
+            s.gX.alloc((size_t)m1 * ld, false);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
+            src = s.gX.p;
+        } else {
+            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        launch_gene_stats(src, ld, ng, s.gStart.p, s.gRows.p, s.gGroup.p, n_pieces, n_groups, n_rows, covariate ? s.gCov.p : nullptr,
+                          cov_ss, apply_log, pseudo_count, s.gPart.p, ld, group ? s.gF.p : nullptr, covariate ? s.gR.p : nullptr,
+                          s.stream);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+        h->launches += 2;
+        if (group) RUVIII_CUDA_CHECK(cudaMemcpyAsync(F_out + g0, s.gF.p, (size_t)ng * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (covariate) RUVIII_CUDA_CHECK(cudaMemcpyAsync(r_out + g0, s.gR.p, (size_t)ng * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    sync_all(h);
+    if (ms_out) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+        cudaEventElapsedTime(ms_out, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
+    }
+}
+
 template <class F>
 int guarded(ruviii_handle* h, F&& fn) {
     try {
@@ -1689,6 +1794,15 @@ int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32
                float* stage_ms6) {
     if (!h) return RUVIII_ERR_INVALID;
     return guarded(h, [&] { do_pca(h, X, ldX, m1, n, slot, apply_log, pseudo_count, center, scale, k, u_out, d_out, v_out, stage_ms6); });
+}
+
+int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+                      double pseudo_count, const int32_t* group_of_sample, const double* covariate, double* F_out, double* r_out,
+                      float* ms_out) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        do_gene_stats(h, X, ldX, m1, n, slot, apply_log, pseudo_count, group_of_sample, covariate, F_out, r_out, ms_out);
+    });
 }
 
 int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps) {

@@ -138,6 +138,12 @@ int launch_center_columns(const double* X, int64_t ld, int rows, int n, int cent
                           double* mean, double* inv_sd, double* Xc, int64_t ldc, cudaStream_t s);   // returns kernels launched
 void launch_v_from_alpha(double* alpha, const double* evals, int kk, int64_t ld, double* d_out, cudaStream_t s);
 
+// K11 supervisedFindNCG.R:179-191,214-229  per-gene one-way ANOVA F and Pearson correlation in one streaming pass (stats.cu)
+int gene_stats_piece_rows(int n, int n_rows, int n_sms);
+void launch_gene_stats(const double* X, int64_t ld, int n, const int* piece_start, const int* piece_rows, const int* piece_group,
+                       int n_pieces, int n_groups, int n_rows, const double* cov, double cov_ss, int log_first, double pseudo_count,
+                       double* part, int64_t ldp, double* F, double* r, cudaStream_t s);
+
 // micro-benchmarks (ceilings quoted beside the roofline)
 float probe_copy_gbs(size_t bytes, cudaStream_t s);
 float probe_dmma_tflops(int n_sms, cudaStream_t s);

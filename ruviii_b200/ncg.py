@@ -1,0 +1,103 @@
+"""Negative-control-gene selection -- the other step immediately before the RUV-III path.
+
+Host side of ``supervisedFindNCG`` (R/supervisedFindNCG.R:44-461) for its default configuration
+(``regress.out.* = FALSE``, ``apply.normalization = FALSE``, ``corr.method = "pearson"``): the same arguments, the same
+sequence of tests, ranks and rank product.  The per-gene statistics -- one-way ANOVA F across every categorical
+variable, Pearson correlation with every continuous one -- are the streaming kernel K11 through ``ruviii_gene_stats``;
+``rank()``, the ``round(., 2)`` the reference applies to the correlations, and the rank product are O(genes) host
+bookkeeping.  Plotting (:359-425) is not reproduced.
+
+Reference quirks kept or resolved (stated here because they change which genes come out):
+  * :183-187  levels of a categorical UV variable with fewer than three samples are dropped from the data, but the
+    grouping vector handed to row_oneway_equalvar is not subset (an error in R whenever a level is dropped).  Here
+    the samples of such levels are left out of both.
+  * :287-316  the biological ANOVA sits inside ``if (!is.null(continuous.uv))`` -- always true, since an empty
+    selection is ``character(0)``, not NULL -- and uses all samples.  Here it always runs, on all samples.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import _printColoredMessage, get_engine
+
+__all__ = ["supervisedFindNCG", "r_rank"]
+
+
+def r_rank(x):
+    """base::rank(x) with ties.method = "average"."""
+    x = np.asarray(x, dtype=np.float64)
+    order = np.argsort(x, kind="stable")
+    ranks = np.empty(x.shape[0], dtype=np.float64)
+    sx = x[order]
+    start = 0
+    n = x.shape[0]
+    while start < n:
+        end = start
+        while end + 1 < n and sx[end + 1] == sx[start]:
+            end += 1
+        ranks[order[start:end + 1]] = 0.5 * (start + end) + 1.0
+        start = end + 1
+    return ranks
+
+
+def _is_categorical(col):
+    return all(isinstance(v, str) for v in col)
+
+
+def _codes(col, min_count=1):
+    """Level codes in sorted level order; levels with fewer than ``min_count`` samples get -1 (left out)."""
+    col = np.asarray([str(v) for v in col], dtype=object)
+    levels, inv, counts = np.unique(col.astype(str), return_inverse=True, return_counts=True)
+    codes = inv.astype(np.int32)
+    codes[counts[inv] < min_count] = -1
+    return codes
+
+
+def supervisedFindNCG(se_obj, assay_name, bio_variables, uv_variables, no_ncg=1000, regress_out_uv_variables=False,
+                      regress_out_bio_variables=False, apply_normalization=False, normalization="CPM", apply_log=True,
+                      pseudo_count=1, corr_method="pearson", a=0.05, rho=0, anova_method="aov", assess_se_obj=True,
+                      assess_variables=False, remove_na="both", plot_output=False, fast_pca=True, save_se_obj=True, verbose=True):
+    _printColoredMessage("------------The supervisedFindNCG function starts:", verbose)
+    if regress_out_uv_variables or regress_out_bio_variables or apply_normalization:
+        raise NotImplementedError("regress.out.* / apply.normalization (supervisedFindNCG.R:111-146) are outside the CUDA path")
+    if corr_method != "pearson":
+        raise NotImplementedError("corr.method = '%s': only the default Pearson correlation is built" % corr_method)
+    bio_variables = [bio_variables] if isinstance(bio_variables, str) else list(bio_variables or [])
+    uv_variables = [uv_variables] if isinstance(uv_variables, str) else list(uv_variables or [])
+    assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)            # genes x samples
+    Y = np.ascontiguousarray(assay.T)
+    eng = get_engine()
+    cat_uv = [v for v in uv_variables if _is_categorical(se_obj.col_data[v])]            # :153-154
+    con_uv = [v for v in uv_variables if not _is_categorical(se_obj.col_data[v])]
+    cat_bio = [v for v in bio_variables if _is_categorical(se_obj.col_data[v])]          # :246-247
+    con_bio = [v for v in bio_variables if not _is_categorical(se_obj.col_data[v])]
+    kw = dict(apply_log=apply_log, pseudo_count=pseudo_count)
+    all_tests, ranks = {}, []
+    _printColoredMessage("### Finding genes that are highly affected by unwanted variation:", verbose)
+    for v in cat_uv:                                                                     # :179-191
+        F = eng.gene_stats(Y, groups=_codes(se_obj.col_data[v], min_count=3), **kw)["F"]
+        all_tests.setdefault("anova.gene.uv", {})[v] = dict(statistic=F, ranked_genes=r_rank(F))
+        ranks.append(all_tests["anova.gene.uv"][v]["ranked_genes"])
+    for v in con_uv:                                                                     # :214-229
+        r = np.round(eng.gene_stats(Y, covariate=np.asarray(se_obj.col_data[v], dtype=np.float64), **kw)["r"], 2)
+        all_tests.setdefault("corr.genes.uv", {})[v] = dict(correlation=r, ranked_genes=r_rank(np.abs(r)))
+        ranks.append(all_tests["corr.genes.uv"][v]["ranked_genes"])
+    _printColoredMessage("### Finding genes that are not highly affected by biology", verbose)
+    for v in con_bio:                                                                    # :270-285
+        r = np.round(eng.gene_stats(Y, covariate=np.asarray(se_obj.col_data[v], dtype=np.float64), **kw)["r"], 2)
+        all_tests.setdefault("corr.genes.bio", {})[v] = dict(correlation=r, ranked_genes=r_rank(-np.abs(r)))
+        ranks.append(all_tests["corr.genes.bio"][v]["ranked_genes"])
+    for v in cat_bio:                                                                    # :302-316
+        F = eng.gene_stats(Y, groups=_codes(se_obj.col_data[v]), **kw)["F"]
+        all_tests.setdefault("anova.gene.bio", {})[v] = dict(statistic=F, ranked_genes=r_rank(-F))
+        ranks.append(all_tests["anova.gene.bio"][v]["ranked_genes"])
+    if not ranks:
+        raise ValueError("no bio.variables / uv.variables to test")
+    prod = np.prod(np.stack(ranks, axis=1), axis=1)                                      # :342-356
+    ncg_selected = r_rank(-prod) < no_ncg + 1                                            # :357
+    if save_se_obj:
+        se_obj.metadata["NCG"] = ncg_selected                                            # :437
+        se_obj.metadata.setdefault("NCG.tests", all_tests)
+        _printColoredMessage("The NCG are saved to metadata@NCG.", verbose)
+        return se_obj
+    return ncg_selected

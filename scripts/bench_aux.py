@@ -46,6 +46,16 @@ def main():
                            "gram_tflops": gram_flops / (st["gram"] * 1e-3) / 1e12,
                            "center_gbs": 8.0 * m1 * n * 3 / (st["center"] * 1e-3) / 1e9,
                            "d": [float(x) for x in res["d"][:4]]}
+    # K11 gene statistics on the resident newY: ANOVA F over 73 batches and over 5 biologies, Pearson r with a covariate
+    batch = ((np.arange(m1) // 5) % 73).astype(np.int32)
+    bio = (np.arange(m1) % 5).astype(np.int32)
+    cov = np.random.default_rng(2).gamma(5.0, 1.0, m1)
+    gs = {}
+    for name, kw in (("anova_73_batches", dict(groups=batch)), ("anova_5_biologies", dict(groups=bio)), ("pearson", dict(covariate=cov)),
+                     ("anova+pearson", dict(groups=batch, covariate=cov))):
+        ms = [eng.gene_stats(None, slot=0, **kw)["ms"] for _ in range(args.steps + 1)][1:]
+        gs[name] = {"ms": float(np.median(ms)), "gbs": 8.0 * m1 * n / (float(np.median(ms)) * 1e-3) / 1e9}
+    out["gene_stats_resident"] = gs
     # K0 PRPS: 1,200 pseudo-samples of 3 samples each, host matrix in, host PS out (only member rows are uploaded)
     rng = np.random.default_rng(1)
     sets = [np.sort(rng.choice(m1, 3, replace=False)).astype(np.int32) for _ in range(n_ps)]
