@@ -611,7 +611,7 @@ void topk_bind(TopkWork& w, double* base, int* state, int R, int B) {
 
 TopkResult topk_eigen(const double* G, int R, int kk, int kp, int n_keep, int B, TopkWork& w, double* U, double* evals,
                       double tol, int max_iter, int n_sms, int* h_state, cudaStream_t s) {
-    if (B != 32 || kk > 16 || n_keep > B) throw Error(6, "topk_eigen: only B = 32 (k <= 16) is built");
+    if (B != 32 || kk > kTopkMaxK || n_keep > B) throw Error(6, "topk_eigen: only B = 32 (k <= 28) is built");
     return run_topk<32>(G, R, kk, kp, n_keep, w, U, evals, tol, max_iter, n_sms, h_state, s);
 }
 

@@ -610,7 +610,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         // block subspace iteration when only the leading kk rows of fullalpha are wanted and the block (32) leaves
         // room for oversampling; cuSOLVER otherwise and as the fallback
-        const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkBlock / 2 && GO >= 4 * kTopkBlock &&
+        const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkMaxK && GO >= 4 * kTopkBlock &&
                              h->rank_bound >= 2 * kTopkBlock;
         if (h->eig_impl == 3 && !topk_ok)
             throw Error(RUVIII_ERR_UNSUPPORTED, "RUVIII_EIG_IMPL=3 but the problem is outside the subspace-iteration range");
@@ -676,7 +676,8 @@ void eigensolve(ruviii_handle* h) {
     h->eig_iterations = 0;
     if (h->use_topk) {
         TopkResult tr = topk_eigen(s.G.p, R, h->kk, h->kp, h->n_keep, kTopkBlock, s.topk, s.U.p, s.evals.p, h->eig_tol,
-                                   env_int("RUVIII_EIG_MAXIT", 150), h->n_sms, &h->h_flags[60], s.stream);
+                                   env_int("RUVIII_EIG_MAXIT", h->kk > kTopkBlock / 2 ? kTopkPatience : 150), h->n_sms,
+                                   &h->h_flags[60], s.stream);
         h->launches += tr.launches;
         h->eig_iterations = tr.iterations;
         if (tr.converged) {
@@ -1360,7 +1361,7 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
     if (k > kMaxK || k >= m1) throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_pca: nb.pcs must be <= 32 and < the number of samples");
     const int kp = pad_k(k), nsh = (int)h->shards.size();
     const int n_keep = std::min(m1, k + 1);
-    const bool topk_ok = k <= kTopkBlock / 2 && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
+    const bool topk_ok = k <= kTopkMaxK && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
     h->launches = 0;
     std::vector<GramPlan> gps(nsh);
     for (int i = 0; i < nsh; ++i) {
@@ -1426,7 +1427,8 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
             s.pState.alloc(4);
             topk_bind(s.ptopk, s.pTopk.p, s.pState.p, m1, kTopkBlock);
             TopkResult tr = topk_eigen(s.pG.p, m1, k, kp, n_keep, kTopkBlock, s.ptopk, s.pU.p, s.pEv.p, h->eig_tol,
-                                       env_int("RUVIII_EIG_MAXIT", 150), h->n_sms, &h->h_flags[60], s.stream);
+                                       env_int("RUVIII_EIG_MAXIT", k > kTopkBlock / 2 ? kTopkPatience : 150), h->n_sms,
+                                       &h->h_flags[60], s.stream);
             h->launches += tr.launches;
             h->eig_iterations = tr.iterations;
             done = tr.converged;

@@ -77,7 +77,12 @@ struct TopkResult {
     bool converged = false;
     int iterations = 0, launches = 0;
 };
-constexpr int kTopkBlock = 32;   // block width B; serves k <= 16 (B >= 2k)
+constexpr int kTopkBlock = 32;   // block width B of the subspace iteration
+// Largest k the iteration is tried for: convergence of pair j goes with lambda_{B+1} / lambda_j, so what matters is a gap
+// below the block, not B >= 2k; beyond kTopkMaxK (or without convergence in kTopkPatience passes when k > B / 2) cuSOLVER
+// takes over.
+constexpr int kTopkMaxK = 28;
+constexpr int kTopkPatience = 45;
 size_t topk_work_doubles(int R, int B);
 void topk_bind(TopkWork& w, double* base, int* state, int R, int B);
 // U: row-major R x kp (first kk columns, sign fixed); evals: n_keep descending Ritz values (only the first kk converged)
