@@ -1121,12 +1121,9 @@ const void* host_pinned(const void* p) {
 
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out) {
     if (h->n_ps > 0 && !PS) return false;      // replicate.data is built on the device from the whole assay
-    // RUVIII_PIPELINE: 0 = auto, 1 = always when eligible, 2 = never.  Auto takes the zero-copy pipeline on a single shard
-    // only: the scattered 8-byte reads of the control columns are bound by the HOST side of PCIe (request rate of the root
-    // complex: 19 ms for 11 M reads whether one GPU issues them or eight, r01p8), so with N shards the gather costs as much
-    // as at N = 1 while each shard's copies shrink by N -- 33 ms at N = 8 against ~10 ms for upload -> run -> download.
+    // RUVIII_PIPELINE: 0 / 1 = pipeline whenever eligible, 2 = never (upload -> run -> download in sequence)
     const int mode = env_int("RUVIII_PIPELINE", env_int("RUVIII_NO_PIPELINE", 0) ? 2 : 0);
-    const bool off = mode == 2 || (mode == 0 && h->world > 1);
+    const bool off = mode == 2;
     const bool skip = h->no_replicates || h->kk == 0;
     return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
            h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;
@@ -1148,8 +1145,19 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     // row chunks of ~1/12 of the assay (>= 256 rows, multiple of 64)
     const int chunk = (int)round_up(std::max(256, ceil_div(m1, 12)), 64);
     const int n_chunks = ceil_div(m1, chunk);
-    // RUVIII_ZC_PCT: share of the row chunks (the LAST ones in upload order) whose control columns come by zero-copy
-    const int zc_pct = std::max(0, std::min(100, env_int("RUVIII_ZC_PCT", 83)));
+    // Share of the row chunks (the LAST ones in upload order) whose control columns come by zero-copy.  The scattered reads
+    // cost ~1.7 ns each however many GPUs issue them (a request-rate limit on the host side of PCIe: 18-19 ms for the
+    // 11 M reads of C3 on one GPU, and the same total on eight), the bulk upload of a shard runs at ~55 GB/s; W is known
+    // when both the zero-copy share and the upload of the leading chunks are done, so the share that balances the two is
+    // (t_ps + t_upload) / (t_zero_copy_all + t_upload); a factor 1.2 leans towards zero-copy because it starts at t = 0
+    // while the leading chunks also wait for the PRPS block (measured optimum 75-100 % at N = 1).  RUVIII_ZC_PCT overrides.
+    int zc_pct = env_int("RUVIII_ZC_PCT", -1);
+    if (zc_pct < 0) {
+        const double t_zc = (double)m1 * (double)h->n_ctl_global * 1.7e-9;
+        const double t_up = (double)m1 * (double)h->shards[0].n * 8.0 / 55e9, t_ps = (double)h->n_ps * (double)h->shards[0].n * 8.0 / 55e9;
+        zc_pct = (int)(100.0 * std::min(1.0, 1.2 * (t_ps + t_up) / (t_zc + t_up)) + 0.5);
+    }
+    zc_pct = std::max(0, std::min(100, zc_pct));
     const int n_zc = std::min(n_chunks, (n_chunks * zc_pct + 50) / 100);
     const int lead = n_chunks - n_zc;
     const int row_zc0 = std::min(m1, lead * chunk);
