@@ -187,6 +187,18 @@ def main():
 
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
+    # Bind this rank to the CPUs next to its GPU before any pinned buffer is touched (first touch decides the NUMA node):
+    # the end-to-end leg is PCIe-bound and, with several ranks, host-memory-bound (r01w: 19 GB/s per GPU with 4 unbound ranks).
+    numa = "unbound"
+    try:
+        if world == 1:                # one rank: leave the process alone (the CPU-baseline leg below wants every core)
+            raise RuntimeError("single rank")
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = "cpus of GPU %d: %d" % (local_rank, len(os.sched_getaffinity(0)))
+    except Exception as e:            # not fatal: the numbers are then simply those of an unbound process
+        numa = "unbound (%s)" % type(e).__name__
     p, ks, sliced = workload_problem(args.workload, rank, world)
     m1, n, n_ps = p.meta["m1"], p.meta["n"], p.meta["n_ps"]
     g0, g1 = n * rank // world, n * (rank + 1) // world
@@ -361,6 +373,7 @@ def main():
                                "semantics, genes sharded over %d GPU(s)" % (args.workload, m1, n, n_ps, p.meta["groups"],
                                                                           int(p.meta["n_ctl"]), ks if nk > 1 else ks[0], world),
                    "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % ((Y_h.nbytes + PS_h.nbytes) / 1e9),
+                   "host_affinity": numa,
                    "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next},
                    "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(
                        info.eig_solver, "none"), "eig_iterations": info.eig_iterations,
