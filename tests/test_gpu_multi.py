@@ -63,6 +63,32 @@ def test_gene_side_gram_over_shards(ndev):
     assert O.rel_frob(O.align_rows_sign(many["fullalpha"], one["fullalpha"]), one["fullalpha"]) < 1e-8
 
 
+def test_aux_entry_points_over_two_shards():
+    """The 8f entry points (PRPS means, gene statistics, fast PCA) shard the genes like the path itself: two shards must
+    reproduce one (PCA: the Gram partials are allreduced; statistics and means are per gene)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = make_problem(m1=300, n=1501, groups=20, rep=3, n_ctl=100, k=3, seed=91)                 # odd n: ragged shards
+    rng = np.random.default_rng(3)
+    sets = [np.sort(rng.choice(300, 3, replace=False)) for _ in range(40)]
+    batch = (np.arange(300) % 7).astype(np.int32)
+    cov = rng.gamma(4.0, 1.0, 300)
+    with rv.Engine(devices=[0]) as e1:
+        ps1 = e1.prps(p.Y, sets)
+        gs1 = e1.gene_stats(p.Y, groups=batch, covariate=cov)
+        pc1 = e1.pca(p.Y, k=5)
+    with rv.Engine(devices=[0, 1]) as e2:
+        ps2 = e2.prps(p.Y, sets)
+        gs2 = e2.gene_stats(p.Y, groups=batch, covariate=cov)
+        pc2 = e2.pca(p.Y, k=5)
+    assert np.array_equal(ps1, ps2)                                     # per-gene arithmetic: identical bits
+    assert np.array_equal(gs1["F"], gs2["F"]) and np.array_equal(gs1["r"], gs2["r"])
+    assert np.allclose(pc1["d"], pc2["d"], rtol=1e-12, atol=0)
+    assert O.rel_frob(O.align_rows_sign(pc2["u"].T, pc1["u"].T), pc1["u"].T) < 1e-9
+    assert O.rel_frob(O.align_rows_sign(pc2["v"].T, pc1["v"].T), pc1["v"].T) < 1e-9
+    assert O.rel_frob(ps1, np.stack([p.Y[s].mean(axis=0) for s in sets])) < 1e-14
+
+
 def test_torchrun_two_ranks_gene_side(tmp_path):
     """One process per GPU: the per-rank gene counts travel through the plan-time allreduce."""
     if _ngpu() < 2:
