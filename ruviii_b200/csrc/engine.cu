@@ -826,7 +826,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         if (!h->have_user_alpha) {
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
-                launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, s.n, s.Y0.p, s.ld, s.stream);
+                launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld, s.stream);
             });
             h->launches += 1;
             rec(E_RESIDOP);
@@ -1222,7 +1222,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
         // --- K1, K2 on the PRPS rows ---
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[n_chunks], 0));
         RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
-        launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, s.n, s.Y0.p, s.ld, s.stream);
+        launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld, s.stream);
         launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
     });
     h->launches += 4;

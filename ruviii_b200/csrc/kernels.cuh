@@ -33,7 +33,7 @@ void launch_residop(RowSrc src, const int* grp_start, const int* grp_rows, int n
 // t(U) %*% Y0 = t(U_z) %*% Z for the left singular vectors U_z of Z: Gram, eigensolve and projection all run on
 // the smaller Z (800 instead of 1,200 rows at C3: 2.25x fewer Gram flops).  Row (grp_start[g] - g + j - 1) of Z
 // is contrast j of group g.
-void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int n, double* Z,
+void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int max_group, int n, double* Z,
                     int64_t ldZ, cudaStream_t s);
 
 // K9  ruvIII.R:148-149  apply.average.rep: out[g, ] = mean of the rows of newY in replicate group g (all p groups).

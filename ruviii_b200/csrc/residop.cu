@@ -67,6 +67,9 @@ residop_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restr
 // Helmert contrasts of every replicate group (see kernels.cuh): one pass, 8 B read per member cell and 8 B written
 // per contrast cell.  Groups of up to kRegGroup members are loaded in one batch (all loads in flight before the
 // first use); larger groups stream with a running sum.
+// RG = members held in registers: PRPS sets have 2-4 members, and the 4-member instance needs half the registers of
+// the 8-member one (80 -> occupancy 6 CTAs of 128 threads per SM), i.e. twice the loads in flight per SM.
+template <int RG>
 __global__ void __launch_bounds__(kResidopThreads)
 helmert_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restrict__ grp_rows, int n_groups,
                int n_pairs, double* __restrict__ Z, int64_t ldZ) {
@@ -77,14 +80,14 @@ helmert_kernel(RowSrc src, const int* __restrict__ grp_start, const int* __restr
         const int s = grp_start[g];
         const int sz = grp_start[g + 1] - s;
         double* out = Z + (int64_t)(s - g) * ldZ + col;        // every earlier group contributed (size - 1) rows
-        if (sz <= kRegGroup) {
-            double2 v[kRegGroup];
+        if (sz <= RG) {
+            double2 v[RG];
 #pragma unroll
-            for (int t = 0; t < kRegGroup; ++t)
+            for (int t = 0; t < RG; ++t)
                 if (t < sz) v[t] = ld_stream(src.row(grp_rows[s + t]) + col);
             double2 run = v[0];
 #pragma unroll
-            for (int j = 1; j < kRegGroup; ++j) {
+            for (int j = 1; j < RG; ++j) {
                 if (j < sz) {
                     const double c = sqrt((double)j / (double)(j + 1)), inv = 1.0 / (double)j;
                     st_stream(out + (int64_t)(j - 1) * ldZ, make_double2(c * (run.x * inv - v[j].x), c * (run.y * inv - v[j].y)));
@@ -204,13 +207,16 @@ void launch_transpose(const double* in, int64_t ld_in, int rows, int cols, doubl
     RUVIII_LAUNCH_CHECK();
 }
 
-void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int n, double* Z, int64_t ldZ,
-                    cudaStream_t s) {
+void launch_helmert(RowSrc src, const int* grp_start, const int* grp_rows, int n_groups, int max_group, int n, double* Z,
+                    int64_t ldZ, cudaStream_t s) {
     if (n_groups <= 0 || n <= 0) return;
     const int n_pairs = (n + 1) / 2;
     dim3 grid(ceil_div(n_pairs, kResidopThreads), 1);
     grid.y = seg_grid_y(grid.x, n_groups);
-    helmert_kernel<<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Z, ldZ);
+    if (max_group > 0 && max_group <= 4)
+        helmert_kernel<4><<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Z, ldZ);
+    else
+        helmert_kernel<kRegGroup><<<grid, kResidopThreads, 0, s>>>(src, grp_start, grp_rows, n_groups, n_pairs, Z, ldZ);
     RUVIII_LAUNCH_CHECK();
 }
 
