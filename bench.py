@@ -34,9 +34,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C1", "C3", "C4", "C3d", "C5", "tiny"],
+    ap.add_argument("--workload", default="C3", choices=["C1", "C3", "C4", "C3d", "C5", "C5p", "tiny"],
                     help="C3 = the BASELINE metric's configuration (default); C3d / C5 = dense replicate designs "
-                         "(12,200 / 60,000 rows in groups of 3, no PRPS rows; C5 takes the gene-side Gram), 1 GPU only")
+                         "(12,200 / 60,000 rows in groups of 3, no PRPS rows; C5 takes the gene-side Gram); C5p = 60,000 samples with "
+                         "2,000 PRPS sets (the PRPS-shaped large-sample case of SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--probes", action="store_true", help="also measure copy / cuBLAS Dgemm / DMMA ceilings")
@@ -148,7 +149,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         args.gpus = world
-    if args.workload in ("C3d", "C5"):          # evidence runs for the dense designs: no CPU arm (a 60,000^2 SVD)
+    if args.workload in ("C3d", "C5", "C5p"):   # evidence runs for the large designs: no CPU arm (a 60,000^2 SVD)
         args.no_cpu_baseline = True
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
