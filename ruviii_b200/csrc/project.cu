@@ -8,6 +8,8 @@
 // All of these are skinny (k <= 32 rows), so they are bandwidth problems, not tensor problems.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace ruviii {
 
 namespace {
@@ -261,6 +263,95 @@ ctl_products_kernel(RowSrc src, int rows_w, const int* __restrict__ ctl_idx, int
     }
 }
 
+// K5 on the pre-gathered block: A (rows x kp) = Yc (rows x c, dense) . acT (c x kp) as a skinny FP64 GEMM on DMMA.
+// The DFMA kernel above spends 1.5 shared-memory loads per FMA (0.09 ms for 98 MB at C3 -- bound by shared-memory
+// bandwidth, not by HBM); one m8n8k4 DMMA takes two 8-byte fragment loads per lane for 256 FMAs.  A CTA owns 32 rows,
+// tiles of 128 control genes arrive by 16-byte cp.async (double buffered, zero-filled past rows_w / n_ctl), warp w
+// owns row tile w % 4 and the column tiles (w / 4) + 2u.  Row stride 132 and acT stride KPE + 4 make the fragment loads
+// of a half-warp hit 16 distinct 8-byte banks.
+constexpr int kCtlYStrideMma = kCtlTile + 4;
+
+__device__ __forceinline__ void dmma884p(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16z(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kCtlThreads)
+ctl_products_mma_kernel(const double* __restrict__ Yc, int64_t ldc, int rows_w, int n_ctl, const double* __restrict__ acT,
+                        double* __restrict__ A) {
+    constexpr int KPE = KP < 8 ? 8 : KP;             // column extent in whole 8-wide DMMA tiles
+    constexpr int AS = KPE + 4;
+    constexpr int NCT = KPE / 8;                     // column tiles
+    constexpr int NU = NCT >= 2 ? NCT / 2 : 1;       // column tiles per warp
+    extern __shared__ __align__(16) double ctl_smem[];
+    double* sY = ctl_smem;                                          // [2][32][132]
+    double* sAc = ctl_smem + 2 * kCtlRowsPerCta * kCtlYStrideMma;   // [2][128][AS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * kCtlRowsPerCta;
+    const int n_tiles = (n_ctl + kCtlTile - 1) / kCtlTile;
+    for (int e = tid; e < 2 * kCtlTile * AS; e += kCtlThreads) sAc[e] = 0.0;     // columns >= KP stay zero
+    __syncthreads();
+    auto issue_tile = [&](int t, int buf) {
+        double* dY = sY + buf * kCtlRowsPerCta * kCtlYStrideMma;
+#pragma unroll
+        for (int i = 0; i < kCtlRowsPerCta * (kCtlTile / 2) / kCtlThreads; ++i) {
+            const int e = tid + i * kCtlThreads;
+            const int r = e / (kCtlTile / 2), c2 = (e % (kCtlTile / 2)) * 2;
+            const int c = t * kCtlTile + c2;
+            const int left = (row0 + r < rows_w) ? min(2, max(0, n_ctl - c)) : 0;       // valid doubles of this chunk
+            cp_async16z(dY + r * kCtlYStrideMma + c2, Yc + (int64_t)min(row0 + r, rows_w - 1) * ldc + (left ? c : 0), left * 8);
+        }
+        double* dA = sAc + buf * kCtlTile * AS;
+        for (int e = tid; e < kCtlTile * (KP / 2); e += kCtlThreads) {
+            const int cc = e / (KP / 2), j = (e - cc * (KP / 2)) * 2;
+            const bool ok = t * kCtlTile + cc < n_ctl;
+            cp_async16z(dA + cc * AS + j, acT + (int64_t)(ok ? t * kCtlTile + cc : 0) * KP + j, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int rt = warp & 3, ct0 = warp >> 2;
+    const bool active = ct0 < NCT;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[NU][2];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u][0] = acc[u][1] = 0.0;
+    issue_tile(0, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) {
+            issue_tile(t + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (active) {
+            const double* y = sY + buf * kCtlRowsPerCta * kCtlYStrideMma + (rt * 8 + fr) * kCtlYStrideMma + fk;
+            const double* a = sAc + buf * kCtlTile * AS + fk * AS + ct0 * 8 + fr;
+#pragma unroll 8
+            for (int kk = 0; kk < kCtlTile; kk += 4) {
+                const double av = y[kk];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) dmma884p(acc[u][0], acc[u][1], av, a[kk * AS + u * 16]);
+            }
+        }
+        __syncthreads();                              // the buffer is refilled by the next iteration's issue_tile
+    }
+    const int row = row0 + rt * 8 + fr;
+    if (active && row < rows_w) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int col = (ct0 + 2 * u) * 8 + fk * 2;
+            if (col < KP) A[(int64_t)row * KP + col] = acc[u][0];
+            if (col + 1 < KP) A[(int64_t)row * KP + col + 1] = acc[u][1];
+        }
+    }
+}
+
 // Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA: acT is streamed through shared memory in coalesced
 // chunks of 64 control genes; thread (pair e, quarter s) sums rows s, s+4, ... of every chunk and the four
 // quarters are added in a fixed order, so the result is bitwise reproducible.
@@ -449,12 +540,19 @@ void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, do
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
                          double* A, double* Gm, const double* Yc, int64_t ldc, cudaStream_t s) {
     const int blocks = ceil_div(rows_w, kCtlRowsPerCta);
+    static const bool use_mma = [] { const char* v = std::getenv("RUVIII_CTL_MMA"); return !(v && *v == '0'); }();
     if (n_ctl > 0) {
 #define RUVIII_CTL(KP)                                                                                                   \
     do {                                                                                                                 \
-        const int smem = (2 * kCtlRowsPerCta * kCtlYStride + 2 * kCtlTile * (KP + 4)) * 8;                               \
-        RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ctl_products_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        ctl_products_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A, Yc, ldc);         \
+        if (Yc && use_mma) {                                                                                             \
+            const int smem = (2 * kCtlRowsPerCta * kCtlYStrideMma + 2 * kCtlTile * ((KP < 8 ? 8 : KP) + 4)) * 8;         \
+            RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ctl_products_mma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            ctl_products_mma_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(Yc, ldc, rows_w, n_ctl, acT, A);               \
+        } else {                                                                                                         \
+            const int smem = (2 * kCtlRowsPerCta * kCtlYStride + 2 * kCtlTile * (KP + 4)) * 8;                           \
+            RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ctl_products_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            ctl_products_kernel<KP><<<blocks, kCtlThreads, smem, s>>>(src, rows_w, ctl_idx, n_ctl, acT, A, Yc, ldc);     \
+        }                                                                                                                \
     } while (0)
         switch (kp) {
             case 4: RUVIII_CTL(4); break;
