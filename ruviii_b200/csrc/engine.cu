@@ -143,6 +143,7 @@ struct Shard {
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
+    cudaEvent_t ev_acgram = nullptr;                      // aux -> main join of ac %*% t(ac)
     int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
@@ -235,6 +236,7 @@ ruviii_handle::~ruviii_handle() {
         for (auto e : s.ev) cudaEventDestroy(e);
         if (s.ev_fork) cudaEventDestroy(s.ev_fork);
         if (s.ev_gather) cudaEventDestroy(s.ev_gather);
+        if (s.ev_acgram) cudaEventDestroy(s.ev_acgram);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
                                   &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
@@ -299,6 +301,7 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
     for (auto& e : s.ev) RUVIII_CUDA_CHECK(cudaEventCreate(&e));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_gather, cudaEventDisableTiming));
+    RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_acgram, cudaEventDisableTiming));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     h->n_sms = sms;
@@ -939,9 +942,15 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         rec(E_PROJECT);
         for_shards([&](Shard& s) {
             RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
+            // ac %*% t(ac) (one latency-bound CTA) runs on the auxiliary stream beside the products
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
+            launch_ac_gram(s.acT.p, s.n_ctl, kp, s.AG.p + (size_t)h->rows_w * kp, s.copy_stream);
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_acgram, s.copy_stream));
             RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));
-            launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
-                                s.n_ctl > 0 ? s.Yc.p : nullptr, s.ldc, s.stream);
+            launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, nullptr, s.n_ctl > 0 ? s.Yc.p : nullptr,
+                                s.ldc, s.stream);
+            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_acgram, 0));
         });
         h->launches += 2;
         rec(E_CTL);

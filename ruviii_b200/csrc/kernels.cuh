@@ -104,7 +104,9 @@ void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_
 void launch_ctl_gather(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, double* Yc, int64_t ldc, int log_rows,
                        double pseudo_count, cudaStream_t s);
 void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, const double* acT, int kp,
-                         double* A, double* Gm, const double* Yc, int64_t ldc, cudaStream_t s);
+                         double* A, double* Gm, const double* Yc, int64_t ldc, cudaStream_t s);   // Gm == NULL: A only
+// Gm = ac %*% t(ac) alone (one latency-bound CTA): the engine runs it beside the products on the auxiliary stream
+void launch_ac_gram(const double* acT, int n_ctl, int kp, double* Gm, cudaStream_t s);
 
 // K5c ruvIII.R:144  solve(ac %*% t(ac)) via Cholesky Gm[:kk,:kk] = L L'.  Produces Linv (kp x kp, lower), the
 // column means of A over the first mu_rows rows, and a status word (nonzero = not positive definite).

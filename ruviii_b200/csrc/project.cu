@@ -565,6 +565,10 @@ void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, 
         RUVIII_CUDA_CHECK(cudaMemsetAsync(A, 0, (size_t)rows_w * kp * sizeof(double), s));
     }
     RUVIII_LAUNCH_CHECK();
+    if (Gm) launch_ac_gram(acT, n_ctl, kp, Gm, s);
+}
+
+void launch_ac_gram(const double* acT, int n_ctl, int kp, double* Gm, cudaStream_t s) {
     ac_gram_kernel<<<1, 1024, 0, s>>>(acT, n_ctl, kp, Gm);
     RUVIII_LAUNCH_CHECK();
 }
