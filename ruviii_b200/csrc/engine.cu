@@ -6,227 +6,13 @@
 //   -> K4 projection -> K5 control-gene products -> allreduce([A | Gm]) -> Cholesky -> K6 update.
 // One process may drive several shards (an R session: ruviii_create) or exactly one (torchrun:
 // ruviii_create_rank); the code below is the same loop over `shards_` in both cases.
-#include "../../include/ruviii.h"
-#include "kernels.cuh"
-
-#include <cublas_v2.h>
-#include <cuda.h>
-#include <cusolverDn.h>
-#include <dlfcn.h>
-#include <nccl.h>   // types only: the library is dlopen()ed, see NcclApi
-
-#include <algorithm>
-#include <chrono>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <vector>
-
-namespace ruviii {
-
-int launch_gram_tma_prepare(const GramPlan& gp, const double* Y0, int64_t ldY0, void* desc_out);  // gram_tma.cu
-
-// NCCL entry points, resolved at run time.  If the process already holds a libnccl.so.2 (torch imports its own
-// 2.28 build) that one is reused; otherwise the system library is loaded.  Linking libnccl directly would let
-// whichever of the two builds is loaded first shadow the other under the shared soname.
-struct NcclApi {
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    static NcclApi& get() {
-        static NcclApi api;
-        static std::once_flag once;
-        static std::string err;
-        std::call_once(once, [] {
-            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
-            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-            if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
-            auto sym = [&](const char* name) {
-                void* p = dlsym(lib, name);
-                if (!p && err.empty()) err = std::string("libnccl lacks ") + name;
-                return p;
-            };
-            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
-            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
-            api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
-            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
-            api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
-            api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
-            api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
-            api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
-            api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
-            api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
-            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
-        });
-        if (!err.empty()) throw ::ruviii::Error(3, err);
-        return api;
-    }
-};
-#define ncclGetUniqueId ::ruviii::NcclApi::get().GetUniqueId
-#define ncclCommInitRank ::ruviii::NcclApi::get().CommInitRank
-#define ncclCommInitAll ::ruviii::NcclApi::get().CommInitAll
-#define ncclCommDestroy ::ruviii::NcclApi::get().CommDestroy
-#define ncclAllReduce ::ruviii::NcclApi::get().AllReduce
-#define ncclBroadcast ::ruviii::NcclApi::get().Broadcast
-#define ncclSend ::ruviii::NcclApi::get().Send
-#define ncclRecv ::ruviii::NcclApi::get().Recv
-#define ncclGroupStart ::ruviii::NcclApi::get().GroupStart
-#define ncclGroupEnd ::ruviii::NcclApi::get().GroupEnd
-#define ncclGetErrorString ::ruviii::NcclApi::get().GetErrorString
-
-#define RUVIII_NCCL_CHECK(expr)                                                                         \
-    do {                                                                                                \
-        ncclResult_t _r = (expr);                                                                       \
-        if (_r != ncclSuccess)                                                                          \
-            throw ::ruviii::Error(RUVIII_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(_r)); \
-    } while (0)
-#define RUVIII_SOLVER_CHECK(expr)                                                                        \
-    do {                                                                                                 \
-        cusolverStatus_t _r = (expr);                                                                    \
-        if (_r != CUSOLVER_STATUS_SUCCESS)                                                               \
-            throw ::ruviii::Error(RUVIII_ERR_SOLVER, std::string(#expr) + ": cusolver status " +         \
-                                                         std::to_string((int)_r));                       \
-    } while (0)
-
-static int env_int(const char* name, int dflt) {
-    const char* v = std::getenv(name);
-    return v && *v ? std::atoi(v) : dflt;
-}
-
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t count = 0;
-    // The clear runs on the legacy default stream, which does NOT order against the engine's non-blocking streams: wait for
-    // it, otherwise an asynchronous copy queued right after alloc() can be overwritten by the late memset.
-    static void clear(void* q, size_t bytes) {
-        RUVIII_CUDA_CHECK(cudaMemset(q, 0, bytes));
-        RUVIII_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
-    }
-    void alloc(size_t n, bool zero = true) {
-        if (n <= count && p) {
-            if (zero) clear(p, n * sizeof(T));
-            return;
-        }
-        release();
-        if (n == 0) return;
-        RUVIII_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
-        count = n;
-        if (zero) clear(p, n * sizeof(T));
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        count = 0;
-    }
-};
-
-struct Shard {
-    int device = 0;
-    int g0 = 0, n = 0;            // first gene (in the caller's matrix) and gene count of this shard
-    int64_t ld = 0;               // device row pitch (doubles) of every genes-contiguous matrix
-    int n_ctl = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
-    std::vector<cudaEvent_t> ev_chunk, ev_upd;   // pipelined host path: chunk uploaded / chunk updated
-    ncclComm_t comm = nullptr;
-    std::vector<cudaEvent_t> ev;
-    cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
-    cudaEvent_t ev_acgram = nullptr;                      // aux -> main join of ac %*% t(ac)
-    int64_t ldc = 0;
-    DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
-        evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
-    DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
-    DevBuf<double> pX, pG, pWs, pU, pEv, pPart, pAlpha, pStat, pMean, pSd, pTopk, pEvAsc;   // computePCA fast path (ruviii_pca)
-    DevBuf<double> gX, gPart, gCov, gF, gR;     // gene statistics (ruviii_gene_stats)
-    DevBuf<int> gStart, gRows, gGroup;
-    DevBuf<int2> pTiles;
-    DevBuf<int> pState;
-    TopkWork ptopk{};
-    DevBuf<int2> tile_map;
-    DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1, set_start, set_rows;
-    TopkWork topk{};
-    alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
-    alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
-    GramPlan gp;
-    int rsplit = 1;
-};
-
-enum Ev { E_START, E_LOG, E_RESIDOP, E_GRAM, E_AR1, E_EIG, E_BCAST, E_PROJECT, E_CTL, E_AR2, E_SOLVE, E_UPDATE, E_COUNT };
-
-}  // namespace ruviii
+// Companion translation units: engine_pipeline.cu (overlapped host-to-host path of ruviii_normalise), engine_aux.cu (RUV1
+// pre-step, PRPS construction, gene statistics, fast PCA, probes); shared definitions in engine_internal.cuh.
+#include "engine_internal.cuh"
 
 using namespace ruviii;
 
-struct ruviii_handle {
-    std::vector<Shard> shards;
-    int rank0 = 0, world = 1;           // global rank of shards[0], total shards over all processes
-    bool multi_process = false;
-    std::string err;
-    int n_sms = 148;
-
-    // solver state lives on the device of shards[0] (used only when rank0 == 0)
-    cusolverDnHandle_t solver = nullptr;
-    cublasHandle_t blas = nullptr;
-    DevBuf<double> solver_work;
-    DevBuf<int> solver_info;
-    int* h_flags = nullptr;             // pinned: [0] cusolver devInfo, [1..] cholesky status per shard
-
-    // plan
-    bool planned = false, uploaded = false, ran = false, logged = false, have_user_alpha = false;
-    ruviii_params prm{};
-    int m1 = 0, n_ps = 0, m = 0, n_local_total = 0;
-    int p = 0, R = 0, r = 0, n_groups_active = 0, max_group = 0;
-    int active_rows = 0;                // rows in non-singleton groups; R = active_rows - n_groups_active (Helmert rows)
-    int64_t n_ctl_global = 0;
-    std::vector<int> ks, k_eff;
-    int kmax = 0, kk = 0, kp = 4;       // kk = min(kmax, r); kp = padded register extent
-    int n_alpha_rows = 0, n_keep = 0;   // rows of fullalpha produced / eigenvectors kept
-    int rows_w = 0, mu_rows = 0;
-    bool no_replicates = false;
-    uint64_t kmask = 0;
-    int slot_of_k[kMaxK + 1];
-    std::vector<std::pair<int, int>> dup_slots;   // (dst slot, src slot) for k values with the same effective k
-    int launches = 0;
-    ruviii_info info{};
-    int upd_impl = 3;
-    int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
-    int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
-    bool use_topk = false;
-    bool active_all_ps = false;         // every non-singleton row is a PRPS row (the PRPS regime)
-    int pipelined_last = 0;             // 1 when the last ruviii_normalise took the pipelined host path
-    bool gene_side = false;             // Gram = Z'Z (n x n) instead of Z Z' (R x R): taken when R > n
-    int gorder = 0;                     // order of the Gram that is formed and decomposed
-    // gene-side Gram over several shards: gene count / first gene of every GLOBAL rank, and the split of
-    // the R Helmert rows over the ranks after the all-to-all (rank j contracts rows [zrow[j], zrow[j+1]))
-    std::vector<int> gn, goff, zrow;
-    int n_total = 0;                    // genes over all shards of all processes
-    // ruv::RUV1 pre-step (ruvIII.R:116): eta as handed over by ruviii_set_eta (q x n row-major, host copy), sticky
-    std::vector<double> eta_host;
-    int eta_q = 0, eta_n = 0;
-    bool eta_applied = false;           // once per upload, like the log transform
-    // PRPS construction on the device (prpsForCategoricalUV.R:123-139): CSR of the sample sets handed over by
-    // ruviii_set_prps_sets (sticky); replicate.data is then built from the uploaded assay when PS == NULL
-    std::vector<int> prps_start, prps_rows;
-    int prps_n = 0;
-    bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
-    double eig_tol = 1e-13;
-
-    ~ruviii_handle();
-};
-
-static thread_local std::string g_create_error;
+thread_local std::string g_create_error;
 
 ruviii_handle::~ruviii_handle() {
     for (auto& s : shards) {
@@ -274,6 +60,8 @@ ruviii_handle::~ruviii_handle() {
     if (h_flags) cudaFreeHost(h_flags);
 }
 
+namespace ruviii {
+
 namespace {
 
 void check_device(int dev) {
@@ -316,6 +104,8 @@ void finish_create(ruviii_handle* h) {
     h->upd_impl = env_int("RUVIII_UPD_IMPL", 3);   // 1 a~ in registers, 2 TMA ring, 3 a~ in shared memory (default)
     if (const char* t = std::getenv("RUVIII_EIG_TOL")) h->eig_tol = std::atof(t);
 }
+
+}  // namespace
 
 // ---- collectives over all shards of all processes ------------------------------------------------------
 void allreduce_sum(ruviii_handle* h, std::vector<double*> bufs, size_t count) {
@@ -712,50 +502,6 @@ void eigensolve(ruviii_handle* h) {
     h->launches += 1;
 }
 
-// ruv::RUV1 (ruvIII.R:116; fastruvIII.R:133-134 applies it to Y and to replicate.data): every row y of the stacked matrix
-// becomes y - y[ctl] eta_c' (eta_c eta_c')^-1 eta.  Same shape as the RUV-III update itself with eta in the role of alpha
-// and no centring, so it reuses K5/K6: A1 = Y[, ctl] eta_c' and eta_c eta_c' (allreduced over gene shards), Cholesky,
-// then an in-place rank-q update of the device copies of Y and replicate.data.
-void apply_ruv1(ruviii_handle* h) {
-    const int q = h->eta_q, qp = pad_k(q), m = h->m, m1 = h->m1;
-    int slot0[kMaxK + 1] = {0};
-    for (auto& s : h->shards) {
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
-        launch_alpha_finalize(s.eta.p, 1, qp, s.n, s.ld, s.eta.p, s.ctl_idx.p, s.n_ctl, s.etacT.p, s.stream);
-        launch_ctl_gather(src, m, s.ctl_idx.p, s.n_ctl, s.Yc1.p, s.ldc, 0, 0.0, s.stream);
-        launch_ctl_products(src, m, s.ctl_idx.p, s.n_ctl, s.etacT.p, qp, s.AG1.p, s.AG1.p + (size_t)m * qp,
-                            s.n_ctl > 0 ? s.Yc1.p : nullptr, s.ldc, s.stream);
-    }
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.AG1.p);
-        allreduce_sum(h, b, (size_t)m * qp + (size_t)qp * qp);
-    }
-    for (size_t i = 0; i < h->shards.size(); ++i) {
-        Shard& s = h->shards[i];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const double* A = s.AG1.p;
-        launch_chol_solve(A, m, 0, s.AG1.p + (size_t)m * qp, q, qp, s.Linv1.p, s.cm1.p, s.status1.p, s.stream);   // mu_rows = 0: no centring
-        launch_atilde(A, m, s.cm1.p, s.Linv1.p, q, qp, s.At1.p, s.stream);
-        launch_alpha_tilde(s.eta.p, s.Linv1.p, q, qp, s.n, s.ld, s.eta_t.p, s.stream);
-        if (m1 > 0)
-            launch_update_smem(s.Y.p, s.ld, m1, s.n, s.At1.p, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.Y.p, s.ld, 0, s.stream);
-        if (h->n_ps > 0)
-            launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At1.p + (size_t)m1 * qp, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.PS.p,
-                          s.ld, 0, s.stream);
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[32 + i], s.status1.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    }
-    h->launches += 8 + (h->n_ps > 0 ? 1 : 0);
-    for (size_t i = 0; i < h->shards.size(); ++i) {
-        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[i].device));
-        spin_sync(h->shards[i].stream);
-        if (h->h_flags[32 + i] != 0)
-            throw Error(RUVIII_ERR_SINGULAR, "etac %*% t(etac) is not positive definite at pivot " +
-                                                 std::to_string(h->h_flags[32 + i]) + " (solve() in ruv::RUV1 would fail)");
-    }
-}
-
 void do_run(ruviii_handle* h, ruviii_info* info_out) {
     if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_run needs ruviii_plan and ruviii_upload first");
     const bool fast = h->prm.mode == RUVIII_MODE_FAST;
@@ -1110,531 +856,7 @@ void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullal
     h->info.ms_d2h = ms;
 }
 
-// ---- pipelined host-to-host path of ruviii_normalise -----------------------------------------------------------
-// The one-shot call is PCIe-bound (C3: 1.95 GB in, 1.76 GB out, ~35 ms each way at ~55 GB/s against ~2 ms of
-// kernels), and the link is full duplex, so the only real lever is to start the download before the upload has
-// finished.  W needs the control columns of EVERY row of Y, which would serialise the two directions; so those
-// columns (m1 x c doubles, 5 % of Y) are gathered straight out of the pinned host buffer by a zero-copy kernel while
-// the bulk DMA is still streaming Y in row chunks.  Timeline per shard:
-//   copy stream : PS -> Y chunk 0 -> Y chunk 1 -> ...                              (H2D DMA)
-//   d2h stream  : zero-copy gather of Y[, ctl]  ....  newY chunk 0 -> newY chunk 1 -> ...   (D2H DMA)
-//   main stream : K1 K2 [allreduce] K3 [bcast] K4 | wait gather | K5 [allreduce] solve | per chunk: wait upload, K6
-// Taken when the host buffers are pinned, every replicate row is a PRPS row (the PRPS regime: residop/Gram/eigen
-// need PS only), the sample-side Gram is used and nothing but newY / W / the leading rows of fullalpha is wanted.
-// Device-visible alias of a pinned (cudaHostAlloc'ed / registered) host pointer, or nullptr for pageable memory.
-const void* host_pinned(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-}
-
-bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out) {
-    if (h->n_ps > 0 && !PS) return false;      // replicate.data is built on the device from the whole assay
-    // RUVIII_PIPELINE: 0 / 1 = pipeline whenever eligible, 2 = never (upload -> run -> download in sequence)
-    const int mode = env_int("RUVIII_PIPELINE", env_int("RUVIII_NO_PIPELINE", 0) ? 2 : 0);
-    const bool off = mode == 2;
-    const bool skip = h->no_replicates || h->kk == 0;
-    return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
-           h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;
-}
-
-void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* newY_out,
-                            double* fullalpha_out, double* W_out) {
-    const bool fast = h->prm.mode == RUVIII_MODE_FAST;
-    const int kp = h->kp, kk = h->kk, R = h->R, nk = (int)h->ks.size(), m1 = h->m1;
-    const int64_t n = h->n_local_total;
-    const double t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    h->launches = 0;
-    auto for_shards = [&](auto&& fn) {
-        for (auto& s : h->shards) {
-            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-            fn(s);
-        }
-    };
-    // row chunks of ~1/12 of the assay (>= 256 rows, multiple of 64)
-    const int chunk = (int)round_up(std::max(256, ceil_div(m1, 12)), 64);
-    const int n_chunks = ceil_div(m1, chunk);
-    // Share of the row chunks (the LAST ones in upload order) whose control columns come by zero-copy.  The scattered reads
-    // cost ~1.7 ns each however many GPUs issue them (a request-rate limit on the host side of PCIe: 18-19 ms for the
-    // 11 M reads of C3 on one GPU, and the same total on eight), the bulk upload of a shard runs at ~55 GB/s; W is known
-    // when both the zero-copy share and the upload of the leading chunks are done, so the share that balances the two is
-    // (t_ps + t_upload) / (t_zero_copy_all + t_upload); a factor 1.2 leans towards zero-copy because it starts at t = 0
-    // while the leading chunks also wait for the PRPS block (measured optimum 75-100 % at N = 1).  RUVIII_ZC_PCT overrides.
-    int zc_pct = env_int("RUVIII_ZC_PCT", -1);
-    if (zc_pct < 0) {
-        const double t_zc = (double)m1 * (double)h->n_ctl_global * 1.7e-9;
-        const double t_up = (double)m1 * (double)h->shards[0].n * 8.0 / 55e9, t_ps = (double)h->n_ps * (double)h->shards[0].n * 8.0 / 55e9;
-        zc_pct = (int)(100.0 * std::min(1.0, 1.2 * (t_ps + t_up) / (t_zc + t_up)) + 0.5);
-    }
-    zc_pct = std::max(0, std::min(100, zc_pct));
-    const int n_zc = std::min(n_chunks, (n_chunks * zc_pct + 50) / 100);
-    const int lead = n_chunks - n_zc;
-    const int row_zc0 = std::min(m1, lead * chunk);
-    // RUVIII_PIPE_TRACE=1: timestamps (ms after entry, shard 0) of the milestones of the overlapped pipeline on stderr
-    static const bool trace = env_int("RUVIII_PIPE_TRACE", 0) != 0;
-    std::vector<std::pair<const char*, cudaEvent_t>> marks;
-    auto mark = [&](const char* what, Shard& s, cudaStream_t st) {
-        if (!trace || &s != &h->shards[0]) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        marks.emplace_back(what, e);
-    };
-    for_shards([&](Shard& s) {
-        while ((int)s.ev_chunk.size() < n_chunks + 2) {
-            cudaEvent_t e;
-            RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            s.ev_chunk.push_back(e);
-            RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            s.ev_upd.push_back(e);
-        }
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
-        // --- uploads: PS first, then Y in row chunks (copy stream) ---
-        if (h->n_ps > 0)
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.PS.p, s.ld * 8, PS + s.g0, ldPS * 8, (size_t)s.n * 8, h->n_ps,
-                                                cudaMemcpyHostToDevice, s.copy_stream));
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[n_chunks], s.copy_stream));          // PS resident
-        mark("ps_uploaded", s, s.copy_stream);
-        // control columns of the PRPS rows (STACKED mode): from the device copy, right behind its upload
-        if (h->rows_w > m1 && s.n_ctl > 0) {
-            RowSrc ps_src{nullptr, 0, s.PS.p, s.ld, 0};
-            launch_ctl_gather(ps_src, h->rows_w - m1, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)m1 * s.ldc, s.ldc, 0, 0.0, s.copy_stream);
-        }
-        if (lead == 0) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // nothing but the PRPS rows is gathered here
-        for (int c = 0; c < n_chunks; ++c) {
-            const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8,
-                                                (size_t)s.n * 8, rows, cudaMemcpyHostToDevice, s.copy_stream));
-            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
-            if (c < lead && s.n_ctl > 0) {
-                // leading chunks: their control columns are gathered on the device as soon as the chunk has landed
-                RowSrc dsrc{s.Y.p + (size_t)r0 * s.ld, s.ld, nullptr, 0, rows};
-                launch_ctl_gather(dsrc, rows, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)r0 * s.ldc, s.ldc, h->prm.apply_log ? rows : 0,
-                                  h->prm.pseudo_count, s.copy_stream);
-            }
-            if (c == lead - 1) {
-                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.copy_stream));   // device-side gathers complete
-                mark("lead_chunks_uploaded+gathered", s, s.copy_stream);
-            }
-        }
-        mark("all_uploaded", s, s.copy_stream);
-        // --- trailing chunks: zero-copy gather of their control columns out of the pinned host assay (d2h stream, idle
-        //     until K6).  It starts at once; the split between the two routes balances its ~19 ms per 11 M scattered reads
-        //     (bound by the host side of PCIe) against the upload time of the leading chunks. ---
-        if (row_zc0 < m1) {
-            RowSrc hsrc{static_cast<const double*>(host_pinned(Y)) + (size_t)row_zc0 * ldY + s.g0, ldY, nullptr, 0, m1 - row_zc0};
-            launch_ctl_gather(hsrc, m1 - row_zc0, s.ctl_idx.p, s.n_ctl, s.Yc.p + (size_t)row_zc0 * s.ldc, s.ldc,
-                              h->prm.apply_log ? m1 - row_zc0 : 0, h->prm.pseudo_count, s.d2h_stream);
-        }
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.d2h_stream));
-        mark("zero_copy_gather_done", s, s.d2h_stream);
-        // --- K1, K2 on the PRPS rows ---
-        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[n_chunks], 0));
-        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
-        launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld, s.stream);
-        launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
-    });
-    h->launches += 4;
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.G.p);
-        allreduce_sum(h, b, (size_t)R * R);
-    }
-    if (h->rank0 == 0) eigensolve(h);
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.U.p);
-        broadcast0(h, b, (size_t)R * kp);
-        b.clear();
-        for (auto& s : h->shards) b.push_back(s.evals.p);
-        broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
-    }
-    for_shards([&](Shard& s) {
-        launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
-        launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
-        RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
-        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));
-        RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_fork, 0));
-        launch_ctl_products(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.acT.p, kp, s.AG.p, s.AG.p + (size_t)h->rows_w * kp,
-                            s.n_ctl > 0 ? s.Yc.p : nullptr, s.ldc, s.stream);
-    });
-    h->launches += 5 + lead;
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.AG.p);
-        allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
-    }
-    for_shards([&](Shard& s) {
-        const double* A = s.AG.p;
-        const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
-        launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
-        launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
-        launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
-        mark("W_known", s, s.stream);
-        const int64_t stride = (int64_t)m1 * s.ld;
-        // --- K6 per chunk as it lands, download right behind it ---
-        for (int c = 0; c < n_chunks; ++c) {
-            const int r0 = c * chunk, rows = std::min(chunk, m1 - r0);
-            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[c], 0));
-            if (h->prm.apply_log) launch_log2_inplace(s.Y.p + (size_t)r0 * s.ld, s.ld, rows, s.n, h->prm.pseudo_count, s.stream);
-            launch_update_smem(s.Y.p + (size_t)r0 * s.ld, s.ld, rows, s.n, s.At.p + (size_t)r0 * kp, kp, s.at.p, s.ld, kk,
-                               h->kmask, h->slot_of_k, s.out.p + (size_t)r0 * s.ld, s.ld, stride, s.stream);
-            for (auto& d : h->dup_slots)
-                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.out.p + (size_t)d.first * stride + (size_t)r0 * s.ld, s.ld * 8,
-                                                    s.out.p + (size_t)d.second * stride + (size_t)r0 * s.ld, s.ld * 8,
-                                                    (size_t)s.n * 8, rows, cudaMemcpyDeviceToDevice, s.stream));
-            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_upd[c], s.stream));
-            RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.d2h_stream, s.ev_upd[c], 0));
-            for (int i = 0; i < nk; ++i)
-                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY_out + (size_t)i * m1 * n + (size_t)r0 * n + s.g0, n * 8,
-                                                    s.out.p + (size_t)i * stride + (size_t)r0 * s.ld, s.ld * 8, (size_t)s.n * 8,
-                                                    rows, cudaMemcpyDeviceToHost, s.d2h_stream));
-            if (c == 0) mark("first_chunk_downloaded", s, s.d2h_stream);
-            if (c == n_chunks / 2) mark("half_downloaded", s, s.d2h_stream);
-        }
-        mark("all_downloaded", s, s.d2h_stream);
-        size_t off = 0;
-        for (int i = 0; i < nk; ++i) {
-            launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
-            off += (size_t)h->rows_w * h->k_eff[i];
-        }
-        if (fullalpha_out)
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(fullalpha_out + s.g0, n * 8, s.alpha.p, s.ld * 8, (size_t)s.n * 8, h->n_alpha_rows,
-                                                cudaMemcpyDeviceToHost, s.stream));
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_UPDATE], s.stream));
-    });
-    h->launches += 3 + n_chunks * (h->prm.apply_log ? 2 : 1) + nk;
-    if (W_out) {
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        size_t w_total = 0;
-        for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(W_out, s.W.p, w_total * 8, cudaMemcpyDeviceToHost, s.stream));
-    }
-    for (size_t i = 0; i < h->shards.size(); ++i) {
-        Shard& s = h->shards[i];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[1 + i], s.status.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    }
-    sync_all(h);
-    const double t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    if (trace) {
-        fprintf(stderr, "[pipe trace] zc_pct=%d chunks=%d lead=%d:", zc_pct, n_chunks, lead);
-        for (auto& mk : marks) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->shards[0].ev[E_START], mk.second);
-            fprintf(stderr, " %s=%.2f", mk.first, ms);
-            cudaEventDestroy(mk.second);
-        }
-        fprintf(stderr, " host_total=%.2f (ms)\n", (t_done - t_enter) * 1e3);
-    }
-    if (h->rank0 == 0 && h->h_flags[0] != 0)
-        throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
-    for (size_t i = 0; i < h->shards.size(); ++i)
-        if (h->h_flags[1 + i] != 0)
-            throw Error(RUVIII_ERR_SINGULAR, "ac %*% t(ac) is not positive definite at pivot " + std::to_string(h->h_flags[1 + i]) +
-                                                 " (solve() in ruvIII.R:144 would fail)");
-    ruviii_info& I = h->info;
-    std::memset(&I, 0, sizeof(I));
-    I.struct_size = sizeof(ruviii_info);
-    I.m = h->m; I.m1 = m1; I.n_ps = h->n_ps; I.n = (int)n; I.p = h->p; I.active_rows = h->active_rows; I.r = h->r;
-    I.gram_order = h->gorder; I.n_ctl = (int)h->n_ctl_global; I.kmax_eff = kk; I.gram_side = 1;
-    I.n_shards = (int)h->shards.size(); I.kernel_launches = h->launches;
-    I.eig_solver = h->eig_solver_used; I.eig_iterations = h->eig_iterations; I.pipelined = 1;
-    I.host_t_enter = t_enter; I.host_t_done = t_done;
-    I.ms_total = (float)((t_done - t_enter) * 1e3);          // host wall time of the overlapped copy + compute pipeline
-    {
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        std::vector<double> ev(kk + 1, 0.0);
-        const int have = std::min(kk + 1, h->n_keep);
-        RUVIII_CUDA_CHECK(cudaMemcpy(ev.data(), s.evals.p, have * sizeof(double), cudaMemcpyDeviceToHost));
-        I.eig_top = ev[0]; I.eig_kmax = ev[kk - 1]; I.eig_next = have > kk ? ev[kk] : 0.0;
-    }
-    (void)fast;
-    h->uploaded = true;
-    h->logged = h->prm.apply_log != 0;
-    h->ran = true;
-    h->pipelined_last = 1;
-}
-
-// ---- computePCA fast path --------------------------------------------------------------------------
-// computePCA.R:120-134: runSVD(t(assay), k = nb.pcs, center, scale) -- the top-k singular triplets of the centred samples x
-// genes matrix.  Sample-side route with the engine's own kernels: K10 centre -> K2 Gram Xc Xc' (genes sharded, allreduced)
-// -> K3 top-k eigenpairs (u, d^2) on rank 0 -> broadcast -> K4 projection t(u) Xc = diag(d) t(v).
-// source: X != NULL host matrix; X == NULL and slot >= 0: output block `slot` of the last run, already on the device
-// (normAssessment.R:113 runs computePCA on every RUV_K* assay right after normalise()); slot == -1: the resident input.
-void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
-            int center, int scale, int k, double* u_out, double* d_out, double* v_out, float* stage_ms) {
-    const bool resident = X == nullptr;
-    if (resident) {
-        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_pca on resident data needs a plan and an upload");
-        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_pca: no such output block");
-        m1 = h->m1;
-        n = h->n_local_total;
-    }
-    if (m1 < 2 || n <= 0 || k <= 0 || !u_out || !d_out) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: bad arguments");
-    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: row stride < n");
-    if (k > kMaxK || k >= m1) throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_pca: nb.pcs must be <= 32 and < the number of samples");
-    const int kp = pad_k(k), nsh = (int)h->shards.size();
-    const int n_keep = std::min(m1, k + 1);
-    const bool topk_ok = k <= kTopkMaxK && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
-    h->launches = 0;
-    std::vector<GramPlan> gps(nsh);
-    for (int i = 0; i < nsh; ++i) {
-        Shard& s = h->shards[i];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
-        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
-        const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
-        const int blocks = colstat_blocks(m1, ng, h->n_sms);
-        s.pX.alloc((size_t)m1 * ld, false);
-        s.pStat.alloc((size_t)(blocks + 1) * ld, false);
-        s.pMean.alloc(ld);
-        s.pSd.alloc(ld);
-        GramPlan& gp = gps[i];
-        gp = plan_gram(m1, (int)ld, h->n_sms, h->gram_impl == 2 ? 1 : h->gram_impl);     // cp.async kernels (no tensor map to build)
-        s.pWs.alloc(gp.workspace_bytes / sizeof(double), false);
-        std::vector<int2> tm(gp.n_tiles);
-        fill_gram_tile_map(gp, tm.data());
-        s.pTiles.alloc(tm.size());
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.pTiles.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice, s.stream));
-        s.pG.alloc((size_t)m1 * m1, false);
-        s.pU.alloc((size_t)m1 * kp);
-        s.pEv.alloc(std::max(n_keep, kp) + 2);
-        const int rsplit = project_rsplit(m1, ng, h->n_sms);
-        s.pPart.alloc((size_t)rsplit * kp * ld, false);
-        s.pAlpha.alloc((size_t)kp * ld);
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
-        const double* src = nullptr;
-        if (!resident) {
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.pX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
-            if (apply_log) { launch_log2_inplace(s.pX.p, ld, m1, ng, pseudo_count, s.stream); h->launches += 1; }   // computePCA.R:124-127
-            src = s.pX.p;
-        } else {
-            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
-            if (apply_log) {                          // a resident block is copied before it is transformed: outputs stay intact
-                RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.pX.p, src, (size_t)m1 * ld * 8, cudaMemcpyDeviceToDevice, s.stream));
-                launch_log2_inplace(s.pX.p, ld, m1, ng, pseudo_count, s.stream);
-                h->launches += 1;
-                src = s.pX.p;
-            }
-        }
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
-        h->launches += launch_center_columns(src, ld, m1, ng, center, scale, blocks, s.pStat.p, s.pMean.p, s.pSd.p, s.pX.p, ld, s.stream);
-        // the pitch padding takes part in the Gram's contraction: clear it after the centring (an output block's padding
-        // is never written by the update kernel, so what the centring read there is arbitrary)
-        if (ld > ng)
-            RUVIII_CUDA_CHECK(cudaMemset2DAsync(s.pX.p + ng, ld * 8, 0, (size_t)(ld - ng) * 8, m1, s.stream));
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_RESIDOP], s.stream));
-        h->launches += launch_gram(gp, s.pX.p, ld, s.pTiles.p, s.pWs.p, s.pG.p, nullptr, s.stream);
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_GRAM], s.stream));
-    }
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.pG.p);
-        allreduce_sum(h, b, (size_t)m1 * m1);
-    }
-    if (h->rank0 == 0) {
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        bool done = false;
-        if (topk_ok) {
-            s.pTopk.alloc(topk_work_doubles(m1, kTopkBlock), false);
-            s.pState.alloc(4);
-            topk_bind(s.ptopk, s.pTopk.p, s.pState.p, m1, kTopkBlock);
-            TopkResult tr = topk_eigen(s.pG.p, m1, k, kp, n_keep, kTopkBlock, s.ptopk, s.pU.p, s.pEv.p, h->eig_tol,
-                                       env_int("RUVIII_EIG_MAXIT", k > kTopkBlock / 2 ? kTopkPatience : 150), h->n_sms,
-                                       &h->h_flags[60], s.stream);
-            h->launches += tr.launches;
-            h->eig_iterations = tr.iterations;
-            done = tr.converged;
-        }
-        if (!done) {                                   // cuSOLVER: k > 16, small matrices, or no convergence
-            if (!h->solver) {
-                RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
-                RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
-            }
-            s.pEvAsc.alloc(m1);
-            int lwork = 0, meig = 0;
-            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
-                                                             CUBLAS_FILL_MODE_UPPER, m1, s.pG.p, m1, 0.0, 0.0, m1 - n_keep + 1, m1,
-                                                             &meig, s.pEvAsc.p, &lwork));
-            h->solver_work.alloc((size_t)lwork, false);
-            h->solver_info.alloc(4);
-            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER,
-                                                  m1, s.pG.p, m1, 0.0, 0.0, m1 - n_keep + 1, m1, &meig, s.pEvAsc.p,
-                                                  h->solver_work.p, (int)h->solver_work.count, h->solver_info.p));
-            if (meig != n_keep) throw Error(RUVIII_ERR_SOLVER, "syevdx returned an unexpected number of eigenpairs");
-            launch_pick_top(s.pG.p, m1, s.pEvAsc.p, meig, m1, n_keep, k, kp, nullptr, s.pU.p, s.pEv.p, s.stream);
-            h->launches += 1;
-        }
-    }
-    for (auto& s : h->shards) {
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_EIG], s.stream));
-    }
-    {
-        std::vector<double*> b;
-        for (auto& s : h->shards) b.push_back(s.pU.p);
-        broadcast0(h, b, (size_t)m1 * kp);
-        b.clear();
-        for (auto& s : h->shards) b.push_back(s.pEv.p);
-        broadcast0(h, b, (size_t)std::max(n_keep, kp) + 2);
-    }
-    std::vector<double> ev(k);
-    for (int i = 0; i < nsh; ++i) {
-        Shard& s = h->shards[i];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
-        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
-        const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
-        const int rsplit = project_rsplit(m1, ng, h->n_sms);
-        launch_project(s.pX.p, ld, m1, ng, s.pU.p, kp, rsplit, s.pPart.p, ld, s.stream);
-        launch_alpha_finalize(s.pPart.p, rsplit, kp, ng, ld, s.pAlpha.p, nullptr, 0, nullptr, s.stream);
-        launch_v_from_alpha(s.pAlpha.p, s.pEv.p, k, ld, nullptr, s.stream);
-        h->launches += 3;
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_PROJECT], s.stream));
-        if (v_out)
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(v_out + g0, (size_t)n * 8, s.pAlpha.p, ld * 8, (size_t)ng * 8, k, cudaMemcpyDeviceToHost,
-                                                s.stream));
-        if (i == 0) {
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(u_out, (size_t)k * 8, s.pU.p, (size_t)kp * 8, (size_t)k * 8, m1, cudaMemcpyDeviceToHost,
-                                                s.stream));
-            RUVIII_CUDA_CHECK(cudaMemcpyAsync(ev.data(), s.pEv.p, (size_t)k * 8, cudaMemcpyDeviceToHost, s.stream));
-        }
-    }
-    sync_all(h);
-    for (int j = 0; j < k; ++j) d_out[j] = std::sqrt(std::max(ev[j], 0.0));
-    if (stage_ms) {
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
-        stage_ms[0] = el(E_START, E_LOG);       // upload (+ log)
-        stage_ms[1] = el(E_LOG, E_RESIDOP);     // K10 centre / scale
-        stage_ms[2] = el(E_RESIDOP, E_GRAM);    // K2 Gram
-        stage_ms[3] = el(E_GRAM, E_EIG);        // allreduce + K3 eigensolve
-        stage_ms[4] = el(E_EIG, E_PROJECT);     // broadcast + K4 projection
-        stage_ms[5] = el(E_START, E_PROJECT);
-    }
-}
-
-// ---- negative-control-gene statistics ---------------------------------------------------------------
-// supervisedFindNCG.R:179-191,326-341 (row_oneway_equalvar(x, g)$statistic) and :214-229,270-285 (correls(y, x, "pearson")).
-// One streaming pass per call (K11, stats.cu).  Samples with group id < 0 are left out (the reference drops levels with
-// fewer than three samples, :183-185); without groups every sample takes part and only the correlation is produced.
-void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
-                   const int32_t* group, const double* covariate, double* F_out, double* r_out, float* ms_out) {
-    const bool resident = X == nullptr;
-    if (resident) {
-        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats on resident data needs a plan and an upload");
-        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats: no such output block");
-        m1 = h->m1;
-        n = h->n_local_total;
-    }
-    if (m1 < 2 || n <= 0 || (!group && !covariate) || (group && !F_out) || (covariate && !r_out))
-        throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: bad arguments");
-    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: row stride < n");
-    // ---- pieces: groups in ascending id order, each cut into runs of at most piece_rows samples ----
-    std::map<int32_t, std::vector<int>> groups;
-    if (group) {
-        for (int i = 0; i < m1; ++i)
-            if (group[i] >= 0) groups[group[i]].push_back(i);
-    } else {
-        for (int i = 0; i < m1; ++i) groups[0].push_back(i);
-    }
-    int n_rows = 0;
-    for (auto& kv : groups) n_rows += (int)kv.second.size();
-    const int n_groups = (int)groups.size();
-    if (group && (n_groups < 2 || n_rows <= n_groups)) throw Error(RUVIII_ERR_INVALID, "one-way ANOVA needs >= 2 groups and N > G");
-    if (n_rows < 2) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: fewer than two samples");
-    const int nsh = (int)h->shards.size();
-    const int piece_rows = gene_stats_piece_rows(std::max(1, n / nsh), n_rows, h->n_sms);
-    std::vector<int> pstart{0}, prow, pgroup;
-    int gi = 0;
-    for (auto& kv : groups) {
-        const std::vector<int>& rows = kv.second;
-        for (size_t a = 0; a < rows.size(); a += piece_rows) {
-            const size_t b = std::min(rows.size(), a + piece_rows);
-            prow.insert(prow.end(), rows.begin() + a, rows.begin() + b);
-            pstart.push_back((int)prow.size());
-            pgroup.push_back(gi);
-        }
-        ++gi;
-    }
-    const int n_pieces = (int)pgroup.size();
-    // centred covariate over the samples that take part (Pearson: sum c = 0)
-    std::vector<double> c(m1, 0.0);
-    double cov_ss = 1.0;
-    if (covariate) {
-        long double mean = 0.0L;
-        for (int r : prow) mean += covariate[r];
-        mean /= n_rows;
-        long double ss = 0.0L;
-        for (int r : prow) { c[r] = (double)(covariate[r] - mean); ss += (long double)c[r] * c[r]; }
-        cov_ss = (double)ss;
-    }
-    h->launches = 0;
-    for (int i = 0; i < nsh; ++i) {
-        Shard& s = h->shards[i];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
-        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
-        if (ng <= 0) continue;
-        const int64_t ld = resident ? s.ld : round_up(ng, kRowAlign);
-        s.gStart.alloc(pstart.size(), false);
-        s.gRows.alloc(prow.size(), false);
-        s.gGroup.alloc(pgroup.size(), false);
-        s.gPart.alloc((size_t)n_pieces * 3 * ld, false);
-        s.gF.alloc(ld, false);
-        s.gR.alloc(ld, false);
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gStart.p, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gRows.p, prow.data(), prow.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gGroup.p, pgroup.data(), pgroup.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-        if (covariate) {
-            s.gCov.alloc(m1, false);
-            RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gCov.p, c.data(), (size_t)m1 * 8, cudaMemcpyHostToDevice, s.stream));
-        }
-        const double* src;
-        if (!resident) {
-            s.gX.alloc((size_t)m1 * ld, false);
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
-            src = s.gX.p;
-        } else {
-            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
-        }
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
-        launch_gene_stats(src, ld, ng, s.gStart.p, s.gRows.p, s.gGroup.p, n_pieces, n_groups, n_rows, covariate ? s.gCov.p : nullptr,
-                          cov_ss, apply_log, pseudo_count, s.gPart.p, ld, group ? s.gF.p : nullptr, covariate ? s.gR.p : nullptr,
-                          s.stream);
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
-        h->launches += 2;
-        if (group) RUVIII_CUDA_CHECK(cudaMemcpyAsync(F_out + g0, s.gF.p, (size_t)ng * 8, cudaMemcpyDeviceToHost, s.stream));
-        if (covariate) RUVIII_CUDA_CHECK(cudaMemcpyAsync(r_out + g0, s.gR.p, (size_t)ng * 8, cudaMemcpyDeviceToHost, s.stream));
-    }
-    sync_all(h);
-    if (ms_out) {
-        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
-        cudaEventElapsedTime(ms_out, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
-    }
-}
-
-template <class F>
-int guarded(ruviii_handle* h, F&& fn) {
-    try {
-        fn();
-        return RUVIII_OK;
-    } catch (const Error& e) {
-        if (h) h->err = e.what(); else g_create_error = e.what();
-        cudaGetLastError();
-        return e.code;
-    } catch (const std::exception& e) {
-        if (h) h->err = e.what(); else g_create_error = e.what();
-        return RUVIII_ERR_INVALID;
-    }
-}
-
-}  // namespace
+}  // namespace ruviii
 
 // ======================================== C ABI ==========================================================
 #pragma GCC visibility push(default)
@@ -1808,116 +1030,6 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
     });
 }
 
-int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
-               double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,
-               float* stage_ms6) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] { do_pca(h, X, ldX, m1, n, slot, apply_log, pseudo_count, center, scale, k, u_out, d_out, v_out, stage_ms6); });
-}
-
-int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
-                      double pseudo_count, const int32_t* group_of_sample, const double* covariate, double* F_out, double* r_out,
-                      float* ms_out) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        do_gene_stats(h, X, ldX, m1, n, slot, apply_log, pseudo_count, group_of_sample, covariate, F_out, r_out, ms_out);
-    });
-}
-
-int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32_t* set_rows, int32_t n_ps) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        h->planned = false;
-        if (!set_start || n_ps <= 0) {
-            h->prps_start.clear();
-            h->prps_rows.clear();
-            h->prps_n = 0;
-            return;
-        }
-        if (set_start[0] != 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: set_start[0] must be 0");
-        for (int j = 0; j < n_ps; ++j)
-            if (set_start[j + 1] <= set_start[j]) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: empty or unordered set");
-        if (!set_rows) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: set_rows is NULL");
-        for (int t = 0; t < set_start[n_ps]; ++t)
-            if (set_rows[t] < 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_prps_sets: negative sample index");
-        h->prps_start.assign(set_start, set_start + n_ps + 1);
-        h->prps_rows.assign(set_rows, set_rows + set_start[n_ps]);
-        h->prps_n = n_ps;
-    });
-}
-
-int ruviii_prps(ruviii_handle* h, const double* Y, int64_t ldY, int32_t m1, int32_t n, int32_t apply_log, double pseudo_count,
-                const int32_t* set_start, const int32_t* set_rows, int32_t n_ps, double* PS_out, int64_t ldPS) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        if (!Y || !set_start || !set_rows || !PS_out || m1 <= 0 || n <= 0 || n_ps <= 0 || ldY < n || ldPS < n)
-            throw Error(RUVIII_ERR_INVALID, "ruviii_prps: bad arguments");
-        // only the member rows are needed on the device: upload each distinct one once, in ascending order
-        const int total = set_start[n_ps];
-        std::vector<int> uniq(set_rows, set_rows + total);
-        for (int r : uniq)
-            if (r < 0 || r >= m1) throw Error(RUVIII_ERR_INVALID, "ruviii_prps: sample index out of range");
-        for (int j = 0; j < n_ps; ++j)
-            if (set_start[j + 1] <= set_start[j]) throw Error(RUVIII_ERR_INVALID, "ruviii_prps: empty or unordered set");
-        std::sort(uniq.begin(), uniq.end());
-        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-        std::vector<int> pos(m1, -1), rows(total);
-        for (size_t i = 0; i < uniq.size(); ++i) pos[uniq[i]] = (int)i;
-        for (int t = 0; t < total; ++t) rows[t] = pos[set_rows[t]];
-        const int nu = (int)uniq.size(), nsh = (int)h->shards.size();
-        std::vector<DevBuf<double>> dY(nsh), dP(nsh);
-        std::vector<DevBuf<int>> dS(nsh), dR(nsh);
-        for (int i = 0; i < nsh; ++i) {
-            Shard& s = h->shards[i];
-            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-            const int g0 = (int)((int64_t)n * i / nsh), ng = (int)((int64_t)n * (i + 1) / nsh) - g0;
-            if (ng <= 0) continue;
-            const int64_t ld = round_up(ng, kRowAlign);
-            dY[i].alloc((size_t)nu * ld);
-            dP[i].alloc((size_t)n_ps * ld, false);
-            dS[i].alloc(n_ps + 1);
-            dR[i].alloc(total);
-            RUVIII_CUDA_CHECK(cudaMemcpyAsync(dS[i].p, set_start, (size_t)(n_ps + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-            RUVIII_CUDA_CHECK(cudaMemcpyAsync(dR[i].p, rows.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-            for (int a = 0; a < nu;) {                 // runs of consecutive samples go up as one 2-D copy
-                int b = a + 1;
-                while (b < nu && uniq[b] == uniq[b - 1] + 1) ++b;
-                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(dY[i].p + (size_t)a * ld, ld * 8, Y + (size_t)uniq[a] * ldY + g0, ldY * 8,
-                                                    (size_t)ng * 8, b - a, cudaMemcpyHostToDevice, s.stream));
-                a = b;
-            }
-            if (apply_log) launch_log2_inplace(dY[i].p, ld, nu, ng, pseudo_count, s.stream);   // prpsForCategoricalUV.R:91
-            RowSrc src{dY[i].p, ld, nullptr, 0, nu};
-            launch_group_mean(src, dS[i].p, dR[i].p, n_ps, ng, dP[i].p, ld, s.stream);
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(PS_out + g0, ldPS * 8, dP[i].p, ld * 8, (size_t)ng * 8, n_ps, cudaMemcpyDeviceToHost,
-                                                s.stream));
-        }
-        sync_all(h);
-        h->launches = nsh * (apply_log ? 2 : 1);
-        for (int i = 0; i < nsh; ++i) {
-            cudaSetDevice(h->shards[i].device);
-            dY[i].release(); dP[i].release(); dS[i].release(); dR[i].release();
-        }
-    });
-}
-
-int ruviii_set_eta(ruviii_handle* h, const double* eta, int32_t q, int32_t n) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        if (!eta || q <= 0) {
-            h->eta_host.clear();
-            h->eta_q = h->eta_n = 0;
-        } else {
-            if (n <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_set_eta: n <= 0");
-            if (q > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "eta with more than 32 rows is not supported");
-            h->eta_host.assign(eta, eta + (size_t)q * n);
-            h->eta_q = q;
-            h->eta_n = n;
-        }
-        h->planned = false;                 // the plan sizes the RUV1 buffers
-    });
-}
-
 int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
                      const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
                      const int32_t* ks, int32_t nk, double* newY_out, double* newY_ps_out, double* fullalpha_out,
@@ -1940,41 +1052,6 @@ int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double
             do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out);
         }
         if (info) *info = h->info;
-    });
-}
-
-int ruviii_fast_residop(ruviii_handle* h, const double* A, int32_t rows, int32_t n, const int32_t* group_of_row,
-                        double* out) {
-    if (!h) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        if (!A || !out || !group_of_row || rows <= 0 || n <= 0) throw Error(RUVIII_ERR_INVALID, "fast_residop: bad arguments");
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        std::map<int32_t, std::vector<int>> groups;
-        for (int i = 0; i < rows; ++i) groups[group_of_row[i]].push_back(i);
-        std::vector<int> gs{0}, gr;
-        for (auto& kv : groups) {           // singletons included here: their residual rows are written as zeros
-            for (int r : kv.second) gr.push_back(r);
-            gs.push_back((int)gr.size());
-        }
-        const int64_t ld = round_up(n, kRowAlign);
-        DevBuf<double> dA, dO;
-        DevBuf<int> dgs, dgr;
-        dA.alloc((size_t)rows * ld);
-        dO.alloc((size_t)rows * ld);
-        dgs.alloc(gs.size());
-        dgr.alloc(gr.size());
-        RUVIII_CUDA_CHECK(cudaMemcpy(dgs.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice));
-        RUVIII_CUDA_CHECK(cudaMemcpy(dgr.p, gr.data(), gr.size() * 4, cudaMemcpyHostToDevice));
-        RUVIII_CUDA_CHECK(cudaMemcpy2D(dA.p, ld * 8, A, (size_t)n * 8, (size_t)n * 8, rows, cudaMemcpyHostToDevice));
-        RowSrc src{dA.p, ld, dA.p, ld, rows};
-        launch_residop(src, dgs.p, dgr.p, (int)gs.size() - 1, 0, n, dO.p, ld, s.stream);
-        RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        // compact row t of the kernel output is the residual of input row gr[t]
-        std::vector<double> tmp((size_t)rows * n);
-        RUVIII_CUDA_CHECK(cudaMemcpy2D(tmp.data(), (size_t)n * 8, dO.p, ld * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost));
-        for (int t = 0; t < rows; ++t) std::memcpy(out + (size_t)gr[t] * n, tmp.data() + (size_t)t * n, (size_t)n * 8);
-        dA.release(); dO.release(); dgs.release(); dgr.release();
     });
 }
 
@@ -2004,103 +1081,6 @@ int ruviii_barrier(ruviii_handle* h) {
     });
 }
 
-int ruviii_probe(ruviii_handle* h, int32_t which, int32_t size, double* value_out) {
-    if (!h || !value_out) return RUVIII_ERR_INVALID;
-    return guarded(h, [&] {
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        if (which == 0) {
-            *value_out = probe_copy_gbs((size_t)std::max(size, 64) << 20, s.stream);
-        } else if (which == 2) {
-            *value_out = probe_dmma_tflops(h->n_sms, s.stream);
-        } else if (which == 5) {
-            // median microseconds of an in-place FP64 sum-allreduce of `size` KiB over all shards (every rank must call)
-            const size_t count = (size_t)std::max(size, 1) * 128;
-            std::vector<DevBuf<double>> bufs(h->shards.size());
-            std::vector<double*> ptrs;
-            for (size_t i = 0; i < h->shards.size(); ++i) {
-                RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[i].device));
-                bufs[i].alloc(count);
-                ptrs.push_back(bufs[i].p);
-            }
-            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-            cudaEvent_t e0, e1;
-            cudaEventCreate(&e0); cudaEventCreate(&e1);
-            std::vector<float> t;
-            for (int it = 0; it < 25; ++it) {
-                sync_all(h);
-                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-                cudaEventRecord(e0, s.stream);
-                allreduce_sum(h, ptrs, count);
-                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-                cudaEventRecord(e1, s.stream);
-                cudaEventSynchronize(e1);
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, e0, e1);
-                if (it >= 5) t.push_back(ms);
-            }
-            sync_all(h);
-            cudaEventDestroy(e0); cudaEventDestroy(e1);
-            for (size_t i = 0; i < h->shards.size(); ++i) { cudaSetDevice(h->shards[i].device); bufs[i].release(); }
-            std::sort(t.begin(), t.end());
-            *value_out = 1e3 * t[t.size() / 2];
-        } else if (which == 6) {
-            // aggregate GB/s of `size` MiB host->device and `size` MiB device->host copied AT THE SAME TIME (pinned memory, two
-            // streams): what the overlapped part of ruviii_normalise can expect from the full-duplex link
-            const size_t bytes = (size_t)std::max(size, 16) << 20;
-            void *hin = nullptr, *hout = nullptr;
-            RUVIII_CUDA_CHECK(cudaHostAlloc(&hin, bytes, cudaHostAllocDefault));
-            RUVIII_CUDA_CHECK(cudaHostAlloc(&hout, bytes, cudaHostAllocDefault));
-            std::memset(hin, 1, bytes);
-            std::memset(hout, 0, bytes);
-            DevBuf<double> din, dout;
-            din.alloc(bytes / 8, false);
-            dout.alloc(bytes / 8);
-            double best = 1e30;
-            for (int it = 0; it < 3; ++it) {
-                sync_all(h);
-                const auto t0 = std::chrono::steady_clock::now();
-                RUVIII_CUDA_CHECK(cudaMemcpyAsync(din.p, hin, bytes, cudaMemcpyHostToDevice, s.copy_stream));
-                RUVIII_CUDA_CHECK(cudaMemcpyAsync(hout, dout.p, bytes, cudaMemcpyDeviceToHost, s.d2h_stream));
-                sync_all(h);
-                best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-            }
-            din.release(); dout.release();
-            cudaFreeHost(hin); cudaFreeHost(hout);
-            *value_out = 2.0 * (double)bytes / best / 1e9;
-        } else if (which == 4) {
-            double r[8];
-            probe_copy_variants(r, s.stream);
-            *value_out = r[std::min(std::max(size, 0), 7)];
-        } else if (which == 3) {
-            *value_out = probe_host_gather_ms(11000, 20000, std::max(size, 1), s.stream);
-        } else if (which == 1) {
-            if (!h->blas && cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) throw Error(RUVIII_ERR_CUDA, "cublasCreate failed");
-            cublasSetStream(h->blas, s.stream);
-            const int N = std::max(size, 256);
-            DevBuf<double> a, b, c;
-            a.alloc((size_t)N * N); b.alloc((size_t)N * N); c.alloc((size_t)N * N);
-            const double one = 1.0, zero = 0.0;
-            cudaEvent_t e0, e1;
-            cudaEventCreate(&e0); cudaEventCreate(&e1);
-            float best = 1e30f;
-            for (int it = 0; it < 4; ++it) {
-                cudaEventRecord(e0, s.stream);
-                cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, N, N, N, &one, a.p, N, b.p, N, &zero, c.p, N);
-                cudaEventRecord(e1, s.stream);
-                cudaEventSynchronize(e1);
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, e0, e1);
-                if (it >= 1) best = std::min(best, ms);
-            }
-            cudaEventDestroy(e0); cudaEventDestroy(e1);
-            a.release(); b.release(); c.release();
-            *value_out = 2.0 * N * (double)N * N / (best * 1e-3) / 1e12;
-        } else {
-            throw Error(RUVIII_ERR_INVALID, "unknown probe");
-        }
-    });
-}
-
 }  // extern "C"
 #pragma GCC visibility pop
+
