@@ -300,11 +300,24 @@ def main():
             eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
         barrier()
         te = max_over_ranks((time.perf_counter() - te0) / n_e2e)
-        e2e = {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3,
+        # the overlapped one-shot path must return exactly what upload -> run -> download returns (same kernels, same order):
+        # recompute this rank's shard through the sequential path and compare bit for bit
+        pipelined = int(eng._info.pipelined)
+        check = None
+        if pipelined:
+            ref_h = pinned((len(ks), m1, n_loc))
+            os.environ["RUVIII_PIPELINE"] = "2"
+            try:
+                eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, ref_h)
+            finally:
+                os.environ.pop("RUVIII_PIPELINE", None)
+            check = bool(np.array_equal(ref_h, out_h))
+            del ref_h
+        e2e = {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3, "bit_identical_to_sequential_path": check,
                "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world,
                "d2h_bytes_per_step": int(out_h.nbytes) * world, "steps": n_e2e,
                "api": "ruviii_normalise (C ABI) with pinned host buffers, copies inside the timed region",
-               "pipelined": int(eng._info.pipelined)}
+               "pipelined": pipelined}
 
     if rank != 0:
         eng.close()

@@ -370,9 +370,13 @@ def test_tma_kernel_variants_match(env):
 
 
 @pytest.mark.parametrize("apply_log", [False, True], ids=["log2_input", "counts_apply_log"])
-def test_pipelined_host_path_matches_sequential(engine, apply_log):
-    """ruviii_normalise with page-locked buffers overlaps upload / compute / download (zero-copy gather of the control
-    columns, chunked update); it must return exactly what the sequential upload -> run -> download path returns."""
+@pytest.mark.parametrize("zc_pct", ["", "0", "40", "100"])
+def test_pipelined_host_path_matches_sequential(engine, apply_log, zc_pct, monkeypatch):
+    """ruviii_normalise with page-locked buffers overlaps upload / compute / download (control columns gathered on the
+    device for the leading row chunks and by zero-copy for the trailing ones, chunked update); whatever the split, it
+    must return exactly what the sequential upload -> run -> download path returns."""
+    if zc_pct:
+        monkeypatch.setenv("RUVIII_ZC_PCT", zc_pct)
     p = make_problem(m1=700, n=3001, groups=60, rep=3, n_ctl=200, k=7, seed=20, counts=apply_log)
     ks = [0, 3, 7]
     groups = api.group_codes(p.sample_names + p.replicate_names)
