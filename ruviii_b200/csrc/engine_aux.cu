@@ -139,7 +139,7 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
             h->eig_iterations = tr.iterations;
             done = tr.converged;
         }
-        if (!done) {                                   // cuSOLVER: k > 16, small matrices, or no convergence
+        if (!done) {                                   // cuSOLVER: k > 28, small matrices, or no convergence
             if (!h->solver) {
                 RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
                 RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
