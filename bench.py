@@ -121,6 +121,15 @@ def cpu_reference_run(sample, ks, threads_note=True):
     return cells / dt, dt
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core it may run on."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -156,6 +165,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        use_all_host_threads()
         sample, desc = reference_sample(args.workload)
         ks = list(range(1, 21)) if args.workload == "C4" else [sample.k]
         if args.workload == "C4":
@@ -372,6 +382,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
+        use_all_host_threads()
         sample, desc = reference_sample(args.workload)
         ks_cpu = ks if args.workload != "C4" else ks[:2]
         v, dt = cpu_reference_run(sample, ks_cpu)
