@@ -159,6 +159,51 @@ def test_gene_side_row_resplit_matches_unsharded_oracle(tmp_path, world):
     assert O.rel_frob(newY, ref["newY"]) < 1e-10
 
 
+def _worker_pca(rank, world, port, outdir):
+    """computePCA's fast path over gene shards as ruviii_pca does it: centre per gene (local), partial sample-side Gram,
+    allreduce, eigensolve on rank 0, broadcast of u and d^2, local projection v = t(Xc) u / d."""
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.default_rng(12)
+    X = rng.normal(size=(40, 97)) @ np.diag(np.linspace(3, 0.2, 97)) + rng.normal(size=(40, 1))
+    k = 4
+    Xs = shard_columns(X, rank, world)
+    Xc = Xs - Xs.mean(axis=0, keepdims=True)
+    G = torch.from_numpy(Xc @ Xc.T)
+    dist.all_reduce(G)
+    U = torch.zeros((40, k), dtype=torch.float64)
+    lam = torch.zeros(k, dtype=torch.float64)
+    if rank == 0:
+        w, Q = np.linalg.eigh(G.numpy())
+        top = np.argsort(w)[::-1][:k]
+        U, lam = torch.from_numpy(np.ascontiguousarray(Q[:, top])), torch.from_numpy(np.ascontiguousarray(w[top]))
+    dist.broadcast(U, src=0)
+    dist.broadcast(lam, src=0)
+    d = np.sqrt(lam.numpy())
+    np.save(os.path.join(outdir, "v_%d.npy" % rank), (Xc.T @ U.numpy()) / d)
+    if rank == 0:
+        np.save(os.path.join(outdir, "u.npy"), U.numpy())
+        np.save(os.path.join(outdir, "d.npy"), d)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pca_matches_unsharded_oracle(tmp_path, world):
+    import torch.multiprocessing as mp
+    from oracle import pca_oracle as PCAO
+    from oracle import ruviii_oracle as O
+    mp.spawn(_worker_pca, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(12)
+    X = rng.normal(size=(40, 97)) @ np.diag(np.linspace(3, 0.2, 97)) + rng.normal(size=(40, 1))
+    ref = PCAO.fast_pca(X.T, 4, apply_log=False)
+    v = np.concatenate([np.load(tmp_path / ("v_%d.npy" % r)) for r in range(world)], axis=0)
+    u, d = np.load(tmp_path / "u.npy"), np.load(tmp_path / "d.npy")
+    assert np.allclose(d, ref["d"], rtol=1e-12, atol=0)
+    assert O.rel_frob((u * d) @ v.T, (ref["u"] * ref["d"]) @ ref["v"].T) < 1e-11
+
+
 def test_gene_ranges_tile_the_genome():
     for n in (1, 7, 403, 20000):
         for world in (1, 2, 3, 4, 8):
