@@ -245,6 +245,17 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
 void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
                    const int32_t* group, const double* covariate, double* F_out, double* r_out, float* ms_out);
 
+// After a failure nothing of this handle may still be running when the caller touches (or frees) its buffers again.  Only
+// for handles that own all their shards: with one process per GPU a peer may be sitting in a collective this rank never
+// reached, and waiting for the device would turn an error return into a hang.
+inline void quiesce(ruviii_handle* h) {
+    if (!h || h->multi_process) return;
+    for (auto& s : h->shards) {
+        if (cudaSetDevice(s.device) == cudaSuccess) cudaDeviceSynchronize();
+        cudaGetLastError();
+    }
+}
+
 template <class F>
 int guarded(ruviii_handle* h, F&& fn) {
     try {
@@ -253,9 +264,11 @@ int guarded(ruviii_handle* h, F&& fn) {
     } catch (const Error& e) {
         if (h) h->err = e.what(); else g_create_error = e.what();
         cudaGetLastError();
+        quiesce(h);
         return e.code;
     } catch (const std::exception& e) {
         if (h) h->err = e.what(); else g_create_error = e.what();
+        quiesce(h);
         return RUVIII_ERR_INVALID;
     }
 }
