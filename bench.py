@@ -402,6 +402,8 @@ def main():
                    "eigen_gap": {"lambda_1": info.eig_top, "lambda_k": info.eig_kmax, "lambda_k+1": info.eig_next},
                    "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration (own kernels)"}.get(
                        info.eig_solver, "none"), "eig_iterations": info.eig_iterations,
+                   "eig_rayleigh_ritz_steps": info.eig_rr, "eig_filter_products": info.eig_filter_products,
+                   "eig_second_cholqr_rounds": info.eig_chol2,
                    "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1")), "gram_order": info.gram_order,
                    "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "3"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,

@@ -85,6 +85,10 @@ typedef struct ruviii_info {
     int32_t gram_order;                /* order of the Gram actually formed: active_rows - #non-singleton groups    */
     int32_t pipelined;                 /* 1 when ruviii_normalise overlapped upload, compute and download (pinned buffers) */
     double host_t_enter, host_t_done;  /* CLOCK_MONOTONIC seconds at ruviii_run entry and when its last stream drained */
+    float ms_gather;                   /* control-gene gather on its own stream (overlaps the eigensolve; not part of the sum) */
+    int32_t eig_rr;                    /* solver 3, persistent form: Rayleigh-Ritz steps                                      */
+    int32_t eig_filter_products;       /*   products spent inside Chebyshev filter rounds (part of eig_iterations)             */
+    int32_t eig_chol2;                 /*   Cholesky-QR rounds that needed a second pass                                      */
 } ruviii_info;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */

@@ -43,7 +43,8 @@ class Info(C.Structure):
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
                 ("eig_top", C.c_double), ("eig_kmax", C.c_double), ("eig_next", C.c_double),
                 ("eig_solver", C.c_int32), ("eig_iterations", C.c_int32), ("gram_order", C.c_int32),
-                ("pipelined", C.c_int32), ("host_t_enter", C.c_double), ("host_t_done", C.c_double)]
+                ("pipelined", C.c_int32), ("host_t_enter", C.c_double), ("host_t_done", C.c_double),
+                ("ms_gather", C.c_float), ("eig_rr", C.c_int32), ("eig_filter_products", C.c_int32), ("eig_chol2", C.c_int32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

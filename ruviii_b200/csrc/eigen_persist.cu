@@ -1,0 +1,724 @@
+// K3, persistent form: the whole top-k eigensolve of the small Gram in ONE cooperative kernel.
+//
+// Reference: ruvIII.R:140 `svd(Y0 %*% t(Y0))$u[, 1:r]`; the update (ruvIII.R:142-145) uses the first k <= 32 columns.
+// eigen_topk.cu runs the same block subspace iteration as ~35 strictly dependent launches with a host poll every three
+// passes; at the PRPS orders (R ~ 10^3) every one of those kernels is a few microseconds of latency, so launch gaps, the
+// one-CTA phases and the host round trip ARE the solve (0.41 ms at C3, half of the 8-GPU pass).  Here one grid of
+// P = ceil(R / RB) CTAs (RB = 8, 16 or 32 rows of G per CTA, P <= #SMs, all co-resident: cooperative launch) keeps its
+// rows of the iterate in shared memory for the whole solve and meets the other CTAs only at grid barriers:
+//
+//   pass:  Z_blk = G[rows, :] Q              DMMA m8n8k4, K split over the warps of the CTA, Q read from L2 (ld.cg)
+//          S_c = Z_blk' Z_blk (H_c = Q_blk' Z_blk on Rayleigh-Ritz passes)          -> global partials
+//          -- barrier --  every CTA reduces a slice of the P partials in a fixed order  -- barrier --
+//          [Rayleigh-Ritz pass: CTA 0: H = V diag(theta) V' (parallel cyclic Jacobi) -- barrier --
+//           X_blk = Q_blk V, Z_blk = Z_blk V, residual / sign partials -- barrier -- converged?  -> U, eigenvalues, exit
+//           S <- V' S V]
+//          every CTA: column-scaled Cholesky S = L L' (redundantly), Q_blk = Z_blk D L^-T, rows -> global Q' -- barrier --
+//   [Chebyshev continuation when the first check fails: Y <- p_d(G) X with the degree-d Chebyshev polynomial that damps
+//    [0, theta_min]: d products with ONE barrier each and no orthogonalisation in between (three-term recurrence on
+//    the CTA's own rows), the degree chosen on the device from the Ritz values and residuals]
+//
+// Convergence is decided on the device; the host never waits inside the solve.  Deterministic: fixed start block, fixed
+// summation orders, no floating-point atomics (the barrier counter is the only atomic).
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace ruviii {
+
+namespace {
+
+constexpr int PB = 32;            // block width of the subspace iteration
+constexpr int PT = 256;           // threads per CTA (8 warps)
+constexpr int PS = PB + 1;        // shared-memory row stride (doubles)
+constexpr int kMaxTrace = 1024;
+
+struct PersistArgs {
+    const double* G;
+    int R, RB, P;
+    double *Q0, *Q1;              // ping-pong iterate, R x 32 row-major
+    double* Pp;                   // P x 2048: per-CTA partials [S | H]
+    double* Pr;                   // P x 64:   per-CTA [residual^2 partial | largest-|x| candidate] per column
+    double* Pred;                 // 2048: reduced [S | H]
+    double* Vm;                   // 32 x 32 Ritz rotation (row-major, columns sorted by descending theta)
+    double* theta;                // 32 Ritz values, descending
+    double* U;                    // out: R x kp row-major, first kk columns
+    double* evals;                // out: n_keep leading Ritz values
+    double* flag_out;             // optional: 0.0 when converged, 1.0 otherwise (summed by the next allreduce)
+    int kk, kp, n_keep;
+    double tol;
+    int max_iter, first, period, cheb;
+    unsigned* bar;                // [0] barrier counter, [1] exit counter
+    int* state;                   // [0] converged, [1] G products, [2] Cholesky breakdown, [3] Jacobi sweeps, [4] RR count,
+                                  // [5] second CholQR rounds, [6] Chebyshev products
+    long long* trace;             // optional: (phase << 48 | clock) marks of CTA 0
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// Grid barrier: one monotone counter; release/acquire at GPU scope by thread 0, CTA barriers on both sides.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target, unsigned P) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += P;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct Smem {
+    double Z[PB][PS];        // this CTA's rows of Z = G Q (rows >= RB unused)
+    double Q[PB][PS];        // this CTA's rows of the current orthonormal block
+    double X[PB][PS];        // Ritz vectors (rows) / previous Chebyshev iterate
+    double A[PB][PS];        // Cholesky / Jacobi work
+    double L[PB][PS];        // Cholesky factor (diagonal holds 1 / L[j][j]) / Jacobi vectors
+    double S[PB][PS];        // reduced Z'Z
+    double V[PB][PS];        // Ritz rotation
+    double part[2304];       // K-split partials of the product (64 rows x stride 34) / reduction scratch
+    double dscale[PB];
+    double th[PB];
+    double cs[PB / 2][2];
+    int pr[PB / 2][2];
+    double red[PB];
+    int flag, flag_big, bad;
+    double minp;
+};
+
+// ---- Z_blk = G[r0 : r0 + RB, :] Q -------------------------------------------------------------------------------------
+// RT row tiles of 8 rows; the 8 warps are RT x KS with KS = 8 / RT splits of the contraction; partials meet in shared memory
+// and are summed in a fixed order.  shift != 0: Z_blk = G Q - shift Q_own is formed later by the caller (Chebyshev).
+template <int RT>
+__device__ __forceinline__ void product_phase(const PersistArgs& a, const double* __restrict__ Q, int r0, Smem& sm) {
+    constexpr int KS = 8 / RT;
+    constexpr int RB = 8 * RT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, kq = lane & 3;
+    const int rt = warp / KS, ks = warp % KS;
+    const int R = a.R;
+    const int row = r0 + rt * 8 + g;
+    const bool row_ok = row < R;
+    const int kchunk = ((R + KS - 1) / KS + 3) & ~3;
+    const int k0 = ks * kchunk, k1 = min(R, k0 + kchunk);
+    const double* grow = a.G + (int64_t)min(row, R - 1) * R;
+    double acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 5
+    for (int k = k0; k < k1; k += 4) {
+        const int kk = k + kq;
+        const bool ok = kk < k1;
+        const double av = (ok && row_ok) ? __ldg(grow + kk) : 0.0;
+        const double* qrow = Q + (int64_t)min(kk, R - 1) * PB + g;
+        double b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) b[t] = ok ? __ldcg(qrow + t * 8) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dmma884(acc[t][0], acc[t][1], av, b[t]);
+    }
+    constexpr int PPS = PB + 2;      // stride of the partial rows: the 8 row groups of a warp land in different banks
+    double* out = sm.part + ((ks * RB) + rt * 8 + g) * PPS + kq * 2;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        out[t * 8] = acc[t][0];
+        out[t * 8 + 1] = acc[t][1];
+    }
+    __syncthreads();
+    for (int e = tid; e < RB * PB; e += PT) {
+        const int r = e / PB, c = e - r * PB;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < KS; ++q) s += sm.part[(q * RB + r) * PPS + c];
+        sm.Z[r][c] = (r0 + r < R) ? s : 0.0;
+    }
+    __syncthreads();
+}
+
+// ---- partials of this CTA: S_c = Z_blk' Z_blk, optionally H_c = Q_blk' Z_blk ------------------------------------------
+__device__ __forceinline__ void partials_phase(const PersistArgs& a, const double (*Zs)[PS], bool with_h, Smem& sm) {
+    const int tid = threadIdx.x;
+    double* dst = a.Pp + (int64_t)blockIdx.x * 2048;
+    const int RB = a.RB;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = tid + u * PT, i = e / PB, j = e - i * PB;
+        double s = 0.0, h = 0.0;
+        for (int r = 0; r < RB; ++r) {
+            const double zj = Zs[r][j];
+            s = fma(Zs[r][i], zj, s);
+            if (with_h) h = fma(sm.Q[r][i], zj, h);
+        }
+        __stcg(dst + e, s);
+        if (with_h) __stcg(dst + 1024 + e, h);
+    }
+}
+
+// ---- every CTA reduces a contiguous slice of the `len` partial elements over the P CTAs, in a fixed order ------------
+__device__ __forceinline__ void reduce_phase(const PersistArgs& a, int len, Smem& sm) {
+    const int tid = threadIdx.x, P = a.P;
+    const int E = (len + P - 1) / P;                       // elements per CTA
+    int epad = 1;
+    while (epad < E && epad < PT) epad <<= 1;
+    const int ng = PT / epad;                              // groups of partials summed side by side
+    const int el = tid % epad, grp = tid / epad;
+    const int e_begin = blockIdx.x * E, e_end = min(len, e_begin + E);
+    for (int e0 = e_begin; e0 < e_end; e0 += epad) {
+        const int e = e0 + el;
+        double s = 0.0;
+        if (e < e_end) {
+#pragma unroll 4
+            for (int p = grp; p < P; p += ng) s += __ldcg(a.Pp + (int64_t)p * 2048 + e);
+        }
+        sm.part[grp * epad + el] = s;
+        __syncthreads();
+        if (grp == 0 && e < e_end) {
+            double t = 0.0;
+            for (int q = 0; q < ng; ++q) t += sm.part[q * epad + el];
+            __stcg(a.Pred + e, t);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- column-scaled Cholesky of sm.S (B x B): L with 1 / L[j][j] on the diagonal, sm.dscale, sm.minp, sm.bad ------------
+__device__ __forceinline__ void cholesky_phase(Smem& sm) {
+    const int tid = threadIdx.x;
+    if (tid < PB) sm.dscale[tid] = sm.S[tid][tid] > 0.0 ? rsqrt(sm.S[tid][tid]) : 1.0;
+    if (tid == 0) { sm.bad = 0; sm.minp = 1.0; }
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+        const int i = e / PB, j = e - i * PB;
+        sm.A[i][j] = 0.5 * (sm.S[i][j] + sm.S[j][i]) * sm.dscale[i] * sm.dscale[j];
+    }
+    __syncthreads();
+    // right-looking over the whole CTA, one barrier per column: step j reads column j, writes columns > j
+    const int c = tid % PB, rbase = tid / PB, rstep = PT / PB;
+    int bad = 0;
+    double minp = 1.0;
+    for (int j = 0; j < PB; ++j) {
+        const double pj = sm.A[j][j];
+        double rd = rsqrt(pj);
+        if (!(pj > 1e-30)) { bad = j + 1; rd = 1.0; }
+        minp = fmin(minp, pj);
+        const double rd2 = rd * rd;
+        if (c > j) {
+            const double acj = sm.A[c][j] * rd2;
+            for (int r = rbase; r < PB; r += rstep)
+                if (r >= c) sm.A[r][c] = fma(-sm.A[r][j], acj, sm.A[r][c]);
+        } else if (c == j) {
+            for (int r = rbase; r < PB; r += rstep) sm.L[r][j] = r > j ? sm.A[r][j] * rd : (r == j ? rd : 0.0);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { sm.bad = bad; sm.minp = minp; }
+    __syncthreads();
+}
+
+// ---- Q_blk = src D L^-T (forward substitution, one thread per row, the row in registers) ------------------------------
+__device__ __forceinline__ void apply_phase(const PersistArgs& a, const double (*src)[PS], Smem& sm) {
+    const int tid = threadIdx.x;
+    if (tid < a.RB) {
+        double z[PB];
+#pragma unroll
+        for (int c = 0; c < PB; ++c) z[c] = src[tid][c] * sm.dscale[c];
+#pragma unroll
+        for (int c = 0; c < PB; ++c) {
+            const double q = z[c] * sm.L[c][c];
+            z[c] = q;
+#pragma unroll
+            for (int b = c + 1; b < PB; ++b) z[b] = fma(-q, sm.L[b][c], z[b]);
+        }
+#pragma unroll
+        for (int c = 0; c < PB; ++c) sm.Q[tid][c] = z[c];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store_rows(const PersistArgs& a, double* __restrict__ Qdst, const double (*src)[PS], int r0) {
+    for (int e = threadIdx.x; e < a.RB * PB; e += PT) {
+        const int r = e / PB, c = e - r * PB;
+        if (r0 + r < a.R) __stcg(Qdst + (int64_t)(r0 + r) * PB + c, src[r][c]);
+    }
+}
+
+// ---- H (sm.A, symmetric B x B) = V diag(theta) V': parallel cyclic Jacobi, round-robin pairing -------------------------
+// Result: sm.L = V with its columns sorted by descending theta, sm.th = theta.  One CTA.
+__device__ __forceinline__ int jacobi_phase(Smem& sm) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += PT) sm.L[e / PB][e % PB] = (e / PB == e % PB) ? 1.0 : 0.0;
+    __syncthreads();
+    int sweeps_run = 0;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        ++sweeps_run;
+        if (tid == 0) { sm.flag = 0; sm.flag_big = 0; }
+        __syncthreads();
+        for (int round = 0; round < PB - 1; ++round) {
+            if (tid < PB / 2) {
+                int p, q;
+                if (tid == 0) { p = PB - 1; q = round; }
+                else { p = (round + tid) % (PB - 1); q = (round - tid + (PB - 1)) % (PB - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double app = sm.A[p][p], aqq = sm.A[q][q], apq = sm.A[p][q];
+                double c = 1.0, s = 0.0;
+                if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
+                    // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
+                    const double zeta = aqq - app, beta = 2.0 * apq;
+                    const double irr = rsqrt(fma(zeta, zeta, beta * beta));
+                    const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
+                    const double ic = rsqrt(c2);
+                    c = c2 * ic;
+                    s = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
+                    sm.flag = 1;
+                    if (apq * apq > 1e-20 * fabs(app * aqq)) sm.flag_big = 1;
+                }
+                sm.cs[tid][0] = c; sm.cs[tid][1] = s;
+                sm.pr[tid][0] = p; sm.pr[tid][1] = q;
+            }
+            __syncthreads();
+            {
+                // A <- J' A J in one phase: thread (a, b) owns the 2 x 2 block rows (p, q) of pair a x columns (p', q') of pair b
+                const int ia = tid / (PB / 2), ib = tid % (PB / 2);
+                const int p = sm.pr[ia][0], q = sm.pr[ia][1], pp = sm.pr[ib][0], qq = sm.pr[ib][1];
+                const double c = sm.cs[ia][0], s = sm.cs[ia][1], cc = sm.cs[ib][0], ss = sm.cs[ib][1];
+                const double x00 = sm.A[p][pp], x01 = sm.A[p][qq], x10 = sm.A[q][pp], x11 = sm.A[q][qq];
+                const double r00 = c * x00 - s * x10, r01 = c * x01 - s * x11;
+                const double r10 = s * x00 + c * x10, r11 = s * x01 + c * x11;
+                // V <- V J: (pair i, row j) tasks, two per thread
+                double v[2][2];
+                int vi[2], vj[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = tid + u * PT;
+                    vi[u] = e / PB; vj[u] = e % PB;
+                    v[u][0] = sm.L[vj[u]][sm.pr[vi[u]][0]];
+                    v[u][1] = sm.L[vj[u]][sm.pr[vi[u]][1]];
+                }
+                sm.A[p][pp] = cc * r00 - ss * r01;
+                sm.A[p][qq] = ss * r00 + cc * r01;
+                sm.A[q][pp] = cc * r10 - ss * r11;
+                sm.A[q][qq] = ss * r10 + cc * r11;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double c1 = sm.cs[vi[u]][0], s1 = sm.cs[vi[u]][1];
+                    sm.L[vj[u]][sm.pr[vi[u]][0]] = c1 * v[u][0] - s1 * v[u][1];
+                    sm.L[vj[u]][sm.pr[vi[u]][1]] = s1 * v[u][0] + c1 * v[u][1];
+                }
+            }
+            __syncthreads();
+        }
+        // quadratic convergence: a sweep whose largest relative off-diagonal entry was below 1e-10 leaves them below rounding
+        const bool stop = !sm.flag || !sm.flag_big;
+        __syncthreads();
+        if (stop) break;
+    }
+    // sort descending (rank sort): sm.th, sm.V = V with permuted columns
+    if (tid < PB) {
+        const double t = sm.A[tid][tid];
+        int rank = 0;
+        for (int i = 0; i < PB; ++i) {
+            const double u = sm.A[i][i];
+            rank += (u > t) || (u == t && i < tid);
+        }
+        sm.pr[tid % (PB / 2)][tid / (PB / 2)] = rank;
+        sm.th[rank] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+        const int i = e / PB, j = e % PB;
+        sm.V[i][sm.pr[j % (PB / 2)][j / (PB / 2)]] = sm.L[i][j];
+    }
+    __syncthreads();
+    return sweeps_run;
+}
+
+__device__ __forceinline__ void trace_mark(const PersistArgs& a, int& n, int phase) {
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && n < kMaxTrace) a.trace[n++] = ((long long)phase << 48) | (clock64() & 0xFFFFFFFFFFFFll);
+}
+
+// dst (B x B) = lhs' rhs or lhs rhs for B x B shared-memory operands (every thread 4 entries)
+__device__ __forceinline__ void small_mm(double (*dst)[PS], const double (*lhs)[PS], const double (*rhs)[PS], bool lhs_t) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + u * PT, i = e / PB, j = e - i * PB;
+        double s = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < PB; ++q) s = fma(lhs_t ? lhs[q][i] : lhs[i][q], rhs[q][j], s);
+        dst[i][j] = s;
+    }
+}
+
+enum Phase { PH_START = 1, PH_PRODUCT, PH_PARTIALS, PH_BAR, PH_REDUCE, PH_CHOL, PH_APPLY, PH_JACOBI, PH_ROTATE, PH_CHECK, PH_CHEB, PH_END };
+
+template <int RT>
+__global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, cta = blockIdx.x, R = a.R, RB = a.RB, P = a.P;
+    const int r0 = cta * RB;
+    unsigned target = 0;
+    int ntrace = 0;
+    int cur = 0;
+    double* Qbuf[2] = {a.Q0, a.Q1};
+    trace_mark(a, ntrace, PH_START);
+    if (cta == 0 && tid == 0) a.state[5] = 0;
+
+    // One round of column-scaled Cholesky QR of the rows in `src` (partials -> reduce -> Cholesky -> substitution);
+    // with `have_S` the reduced S is already in sm.S.  Leaves Q_blk in sm.Q; returns false on a Cholesky breakdown.
+    auto ortho = [&](const double (*src)[PS], bool have_S) -> bool {
+        for (int round = 0; round < 2; ++round) {
+            if (!(round == 0 && have_S)) {
+                partials_phase(a, round == 0 ? src : sm.Q, false, sm);
+                trace_mark(a, ntrace, PH_PARTIALS);
+                grid_barrier(a.bar, target, P);
+                reduce_phase(a, 1024, sm);
+                trace_mark(a, ntrace, PH_REDUCE);
+                grid_barrier(a.bar, target, P);
+                for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = __ldcg(a.Pred + e);
+                __syncthreads();
+            }
+            cholesky_phase(sm);
+            trace_mark(a, ntrace, PH_CHOL);
+            if (sm.bad) return false;
+            apply_phase(a, round == 0 ? src : sm.Q, sm);
+            trace_mark(a, ntrace, PH_APPLY);
+            // kappa^2 of the scaled block ~ 1 / min pivot: below 1e-4 the orthogonality error of one round exceeds ~1e-12,
+            // so the block is orthogonalised once more (Cholesky QR 2); every CTA sees the same pivots and takes the same branch
+            if (sm.minp >= 1e-4) break;
+            if (round == 0 && cta == 0 && tid == 0) a.state[5] += 1;
+        }
+        return true;
+    };
+
+    // ---- start block: fixed hash of (row, column), uniform in (-1, 1) ----
+    for (int e = tid; e < RB * PB; e += PT) {
+        const int r = e / PB, c = e - r * PB;
+        double v = 0.0;
+        if (r0 + r < R) {
+            uint64_t x = (uint64_t)((int64_t)(r0 + r) * PB + c) * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+            v = (double)(int64_t)(x >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+        }
+        sm.Z[r][c] = v;
+    }
+    __syncthreads();
+    bool ok = ortho(sm.Z, false);
+    int converged = 0, it = 0, n_rr = 0, n_cheb = 0;
+    if (ok) {
+        store_rows(a, Qbuf[cur], sm.Q, r0);
+        grid_barrier(a.bar, target, P);
+    }
+    int next_rr = a.first;
+    while (ok && it < a.max_iter) {
+        ++it;
+        product_phase<RT>(a, Qbuf[cur], r0, sm);
+        trace_mark(a, ntrace, PH_PRODUCT);
+        const bool rr = it >= next_rr;
+        if (!rr) {
+            ok = ortho(sm.Z, false);
+            if (!ok) break;
+            store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
+            grid_barrier(a.bar, target, P);
+            cur ^= 1;
+            continue;
+        }
+        // ---- Rayleigh-Ritz pass ----
+        ++n_rr;
+        partials_phase(a, sm.Z, true, sm);
+        grid_barrier(a.bar, target, P);
+        reduce_phase(a, 2048, sm);
+        grid_barrier(a.bar, target, P);
+        trace_mark(a, ntrace, PH_REDUCE);
+        if (cta == 0) {
+            for (int e = tid; e < PB * PB; e += PT) sm.L[e / PB][e % PB] = __ldcg(a.Pred + 1024 + e);
+            __syncthreads();
+            for (int e = tid; e < PB * PB; e += PT) {
+                const int i = e / PB, j = e % PB;
+                sm.A[i][j] = 0.5 * (sm.L[i][j] + sm.L[j][i]);
+            }
+            __syncthreads();
+            const int sweeps = jacobi_phase(sm);
+            for (int e = tid; e < PB * PB; e += PT) __stcg(a.Vm + e, sm.V[e / PB][e % PB]);
+            if (tid < PB) __stcg(a.theta + tid, sm.th[tid]);
+            if (tid == 0) a.state[3] = sweeps;
+            trace_mark(a, ntrace, PH_JACOBI);
+        }
+        grid_barrier(a.bar, target, P);
+        for (int e = tid; e < PB * PB; e += PT) {
+            sm.V[e / PB][e % PB] = __ldcg(a.Vm + e);
+            sm.S[e / PB][e % PB] = __ldcg(a.Pred + e);
+        }
+        if (tid < PB) sm.th[tid] = __ldcg(a.theta + tid);
+        __syncthreads();
+        // X_blk = Q_blk V, Z_blk <- Z_blk V (row-local), residual and sign partials
+        {
+            double xv[4], zv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = tid + u * PT, r = e / PB, c = e - r * PB;
+                double x = 0.0, z = 0.0;
+                if (r < RB) {
+#pragma unroll 8
+                    for (int q = 0; q < PB; ++q) {
+                        x = fma(sm.Q[r][q], sm.V[q][c], x);
+                        z = fma(sm.Z[r][q], sm.V[q][c], z);
+                    }
+                }
+                xv[u] = x; zv[u] = z;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = tid + u * PT, r = e / PB, c = e - r * PB;
+                if (r < RB) { sm.X[r][c] = xv[u]; sm.Z[r][c] = zv[u]; }
+            }
+            __syncthreads();
+            if (tid < PB) {
+                double s = 0.0, best = 0.0, best_abs = -1.0;
+                const double th = sm.th[tid];
+                for (int r = 0; r < RB; ++r) {
+                    if (r0 + r >= R) break;
+                    const double x = sm.X[r][tid], d = sm.Z[r][tid] - th * x;
+                    s = fma(d, d, s);
+                    if (fabs(x) > best_abs) { best_abs = fabs(x); best = x; }
+                }
+                __stcg(a.Pr + (int64_t)cta * 64 + tid, s);
+                __stcg(a.Pr + (int64_t)cta * 64 + 32 + tid, best);
+            }
+        }
+        trace_mark(a, ntrace, PH_ROTATE);
+        grid_barrier(a.bar, target, P);
+        // every CTA folds the P partials itself, in the same order: the same decision everywhere
+        {
+            const int j = tid % PB, grp = tid / PB;          // 8 groups of CTAs
+            double s = 0.0, best = 0.0;
+            for (int p = grp; p < P; p += PT / PB) {
+                s += __ldcg(a.Pr + (int64_t)p * 64 + j);
+                const double x = __ldcg(a.Pr + (int64_t)p * 64 + 32 + j);
+                if (fabs(x) > fabs(best)) best = x;
+            }
+            sm.part[grp * PB + j] = s;
+            sm.part[1024 + grp * PB + j] = best;
+            __syncthreads();
+            if (tid < PB) {
+                double t = 0.0, b = 0.0;
+                for (int q = 0; q < PT / PB; ++q) {
+                    t += sm.part[q * PB + tid];
+                    const double x = sm.part[1024 + q * PB + tid];
+                    if (fabs(x) > fabs(b)) b = x;
+                }
+                sm.red[tid] = sqrt(t);
+                sm.dscale[tid] = b < 0.0 ? -1.0 : 1.0;       // sign that makes the largest-|component| positive
+            }
+            __syncthreads();
+            if (tid == 0) {
+                bool conv = true;
+                const double lim = a.tol * fabs(sm.th[0]);
+                for (int q = 0; q < a.kk; ++q) conv = conv && (sm.red[q] <= lim);
+                sm.flag = conv;
+            }
+            __syncthreads();
+            converged = sm.flag;
+        }
+        trace_mark(a, ntrace, PH_CHECK);
+        if (converged) break;
+        // ---- not yet: filtered continuation ----
+        // Damp [0, b], b = smallest Ritz value of the block (<= lambda_32 by interlacing; whatever the block has not captured
+        // lies at or below it and is amplified less than every wanted pair).  With t(lambda) = 2 lambda / b - 1 a degree-d
+        // Chebyshev filter gains T_d(t(theta_k)) ~ cosh(d acosh t_k) on wanted pair k.  Rounds of degree <= dcap, each
+        // followed by Cholesky QR only (no Jacobi), until the predicted gain on the worst wanted pair reaches the tolerance
+        // (x 10 margin); then one product and the next Rayleigh-Ritz.  dcap bounds what one Cholesky QR (+ its second round)
+        // has to take: the contamination of an unconverged column by the leading direction grows like
+        // (b / theta_0) T_d(t(theta_0)).  Spectra with a huge spread (C3: theta_0 / b ~ 10^3) get dcap = 1, i.e. shifted
+        // power passes; slowly decaying ones get the high degrees they need.
+        const double bnd = fmax(sm.th[PB - 1], 1e-300), th0 = fabs(sm.th[0]);
+        const double tk = 2.0 * sm.th[a.kk - 1] / bnd - 1.0, t0 = 2.0 * th0 / bnd - 1.0;
+        double worst = 0.0;
+        for (int q = 0; q < a.kk; ++q) worst = fmax(worst, sm.red[q]);
+        if (!a.cheb || !(tk > 1.0 + 1e-6)) {
+            // plain pass: S of the rotated block follows from the reduced S: S <- V' S V (no second round of partials)
+            small_mm(sm.A, sm.S, sm.V, false);
+            __syncthreads();
+            small_mm(sm.L, sm.V, sm.A, true);
+            __syncthreads();
+            for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = sm.L[e / PB][e % PB];
+            __syncthreads();
+            ok = ortho(sm.Z, true);
+            next_rr = it + a.period;
+        } else {
+            const double need = log(fmax(10.0 * worst / (a.tol * th0), 2.0));
+            const double ak = acosh(tk), a0 = acosh(fmax(t0, 1.0 + 1e-6));
+            const int dcap = max(1, (int)floor((log(1e7 * (t0 + 1.0) * 0.5) + log(2.0)) / a0));
+            const double ce = 0.5 * bnd;                     // half-width and centre of [0, b]
+            const double sig1 = ce / (th0 - ce);             // scaled so that p(theta_0) stays O(1)
+            double gain = 0.0;
+            for (int e = tid; e < RB * PB; e += PT) { const int r = e / PB, c = e - r * PB; sm.Q[r][c] = sm.X[r][c]; }
+            __syncthreads();
+            while (gain < need && it < a.max_iter) {
+                const int d = (int)fmin(fmin((double)dcap, fmax(1.0, ceil((need - gain + log(2.0)) / ak))),
+                                        fmin(40.0, (double)(a.max_iter - it)));
+                store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);      // start block of this round: Ritz vectors / the last Q
+                grid_barrier(a.bar, target, P);
+                cur ^= 1;
+                // Y_1 = (sigma_1 / e) (G - c I) Y_0,  Y_{i+1} = (2 sigma_{i+1} / e) (G - c I) Y_i - sigma_i sigma_{i+1} Y_{i-1}:
+                // the rows of Y_i live in sm.Q, those of Y_{i-1} in sm.X; one barrier per product
+                double sig = sig1;
+                for (int i = 1; i <= d; ++i) {
+                    product_phase<RT>(a, Qbuf[cur], r0, sm);
+                    const double sig_next = 1.0 / (2.0 / sig1 - sig);
+                    for (int e = tid; e < RB * PB; e += PT) {
+                        const int r = e / PB, c = e - r * PB;
+                        const double y = sm.Q[r][c], gy = sm.Z[r][c] - ce * y;
+                        const double yn = i == 1 ? (sig1 / ce) * gy : (2.0 * sig_next / ce) * gy - sig * sig_next * sm.X[r][c];
+                        sm.X[r][c] = y;
+                        sm.Q[r][c] = yn;
+                    }
+                    if (i > 1) sig = sig_next;
+                    __syncthreads();
+                    ++it; ++n_cheb;
+                    if (i < d) {
+                        store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
+                        grid_barrier(a.bar, target, P);
+                        cur ^= 1;
+                    }
+                    trace_mark(a, ntrace, PH_CHEB);
+                }
+                gain += log(cosh((double)d * ak));
+                for (int e = tid; e < RB * PB; e += PT) { const int r = e / PB, c = e - r * PB; sm.Z[r][c] = sm.Q[r][c]; }
+                __syncthreads();
+                ok = ortho(sm.Z, false);
+                if (!ok) break;
+            }
+            next_rr = it + 1;                                // Rayleigh-Ritz right after the next product
+        }
+        if (!ok) break;
+        store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
+        grid_barrier(a.bar, target, P);
+        cur ^= 1;
+    }
+    // ---- results ----
+    if (converged) {
+        for (int e = tid; e < RB * a.kp; e += PT) {
+            const int r = e / a.kp, j = e - r * a.kp;
+            if (r0 + r < R) a.U[(int64_t)(r0 + r) * a.kp + j] = j < a.kk ? sm.dscale[j] * sm.X[r][j] : 0.0;
+        }
+        if (cta == 0 && tid < a.n_keep && tid < PB) a.evals[tid] = sm.th[tid];
+    }
+    if (cta == 0 && tid == 0) {
+        a.state[0] = converged;
+        a.state[1] = it;
+        a.state[2] = ok ? 0 : (sm.bad ? sm.bad : -1);
+        a.state[4] = n_rr;
+        a.state[6] = n_cheb;
+        if (a.flag_out) *a.flag_out = converged ? 0.0 : 1.0;
+    }
+    trace_mark(a, ntrace, PH_END);
+    if (a.trace && cta == 0 && tid == 0) a.trace[kMaxTrace] = ntrace;
+    // the last CTA out re-arms the counters for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(a.bar + 1, 1u);
+        if (old == (unsigned)P - 1) { a.bar[0] = 0; a.bar[1] = 0; __threadfence(); }
+    }
+}
+
+template <int RT>
+void launch_persist(const PersistArgs& a, cudaStream_t s) {
+    // per device (a process may drive several): cheap enough to repeat on every launch
+    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ek_persistent_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    static const bool coop = [] { const char* v = std::getenv("RUVIII_EIG_COOP"); return !(v && *v == '0'); }();
+    PersistArgs args = a;
+    if (coop) {
+        void* params[] = {&args};
+        RUVIII_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)ek_persistent_kernel<RT>, dim3(a.P), dim3(PT), params, sizeof(Smem), s));
+    } else {
+        ek_persistent_kernel<RT><<<a.P, PT, sizeof(Smem), s>>>(args);
+        RUVIII_LAUNCH_CHECK();
+    }
+}
+
+}  // namespace
+
+// Rows of G per CTA for the persistent solver, or 0 when the order does not fit one co-resident grid.
+int topk_persist_rows(int R, int n_sms) {
+    const char* pv = std::getenv("RUVIII_EIG_PERSIST");
+    const int off = pv && *pv == '0' ? 1 : 0;
+    if (off || R < 4 * PB) return 0;
+    for (int rb : {8, 16, 32})
+        if ((R + rb - 1) / rb <= n_sms) return rb;
+    return 0;
+}
+
+size_t topk_persist_doubles(int n_sms) { return (size_t)n_sms * (2048 + 64) + 2048 + PB * PB + PB + (kMaxTrace + 2); }
+
+// Enqueues the solve and returns at once.  h_state (pinned, >= 8 ints) receives the device state behind the kernel on the
+// same stream; the caller reads it after its own synchronisation (TopkResult::pending) or asks for `sync`.
+TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_keep, TopkWork& w, double* persist_ws, double* U,
+                                 double* evals, double* flag_out, double tol, int max_iter, int n_sms, int* h_state, bool sync,
+                                 cudaStream_t s) {
+    TopkResult res;
+    const int rb = topk_persist_rows(R, n_sms);
+    if (!rb || kk > kTopkMaxK || n_keep > PB) throw Error(6, "topk_eigen_persistent: outside the supported range");
+    PersistArgs a{};
+    a.G = G; a.R = R; a.RB = rb; a.P = (R + rb - 1) / rb;
+    a.Q0 = w.Q; a.Q1 = w.X;
+    double* p = persist_ws;
+    a.Pp = p; p += (size_t)n_sms * 2048;
+    a.Pr = p; p += (size_t)n_sms * 64;
+    a.Pred = p; p += 2048;
+    a.Vm = p; p += PB * PB;
+    a.theta = p; p += PB;
+    static const bool trace_on = [] { const char* v = std::getenv("RUVIII_EIG_TRACE"); return v && *v == '1'; }();
+    a.trace = trace_on ? reinterpret_cast<long long*>(p) : nullptr;
+    a.U = U; a.evals = evals; a.flag_out = flag_out;
+    a.kk = kk; a.kp = kp; a.n_keep = n_keep; a.tol = tol; a.max_iter = max_iter;
+    static const int first_env = [] { const char* v = std::getenv("RUVIII_EIG_FIRST"); return v && *v ? std::atoi(v) : 0; }();
+    static const int cheb_env = [] { const char* v = std::getenv("RUVIII_EIG_CHEB"); return v && *v ? std::atoi(v) : 1; }();
+    a.first = first_env > 0 ? first_env : 6;
+    a.period = 3;
+    a.cheb = cheb_env;
+    a.bar = reinterpret_cast<unsigned*>(w.state + 8);
+    a.state = w.state;
+    switch (rb) {
+        case 8: launch_persist<1>(a, s); break;
+        case 16: launch_persist<2>(a, s); break;
+        default: launch_persist<4>(a, s); break;
+    }
+    res.launches = 1;
+    RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!sync && !trace_on) {
+        res.pending = true;
+        res.converged = true;
+        return res;
+    }
+    for (int spin = 0; spin < (1 << 22) && cudaStreamQuery(s) == cudaErrorNotReady; ++spin) {}
+    RUVIII_CUDA_CHECK(cudaStreamSynchronize(s));
+    res.converged = h_state[0] != 0;
+    res.iterations = h_state[1];
+    if (trace_on) {
+        std::vector<long long> t(kMaxTrace + 2);
+        RUVIII_CUDA_CHECK(cudaMemcpy(t.data(), a.trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int n = (int)std::min<long long>(t[kMaxTrace], kMaxTrace);
+        static const char* names[] = {"?", "start", "product", "partials", "bar", "reduce", "chol", "apply", "jacobi", "rotate", "check",
+                                      "cheb", "end"};
+        fprintf(stderr, "[eig persist] R=%d RB=%d P=%d converged=%d products=%d rr=%d sweeps=%d chol2=%d cheb=%d; cycles:", R, rb, a.P,
+                h_state[0], h_state[1], h_state[4], h_state[3], h_state[5], h_state[6]);
+        for (int i = 1; i < n; ++i)
+            fprintf(stderr, " %s=%lld", names[std::min<long long>(t[i] >> 48, 12)], (t[i] & 0xFFFFFFFFFFFFll) - (t[i - 1] & 0xFFFFFFFFFFFFll));
+        fprintf(stderr, " total=%lld\n", n > 1 ? (t[n - 1] & 0xFFFFFFFFFFFFll) - (t[0] & 0xFFFFFFFFFFFFll) : 0);
+    }
+    return res;
+}
+
+}  // namespace ruviii

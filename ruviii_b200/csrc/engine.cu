@@ -23,6 +23,8 @@ ruviii_handle::~ruviii_handle() {
         if (s.ev_fork) cudaEventDestroy(s.ev_fork);
         if (s.ev_gather) cudaEventDestroy(s.ev_gather);
         if (s.ev_acgram) cudaEventDestroy(s.ev_acgram);
+        if (s.ev_g0) cudaEventDestroy(s.ev_g0);
+        if (s.ev_g1) cudaEventDestroy(s.ev_g1);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
                                   &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
@@ -58,6 +60,7 @@ ruviii_handle::~ruviii_handle() {
     if (solver) cusolverDnDestroy(solver);
     if (blas) cublasDestroy(blas);
     if (h_flags) cudaFreeHost(h_flags);
+    if (h_dflag) cudaFreeHost(h_dflag);
 }
 
 namespace ruviii {
@@ -90,6 +93,10 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_gather, cudaEventDisableTiming));
     RUVIII_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_acgram, cudaEventDisableTiming));
+    RUVIII_CUDA_CHECK(cudaEventCreate(&s.ev_g0));
+    RUVIII_CUDA_CHECK(cudaEventCreate(&s.ev_g1));
+    // RUVIII_L2_GRAN=32/64/128: cap on the DRAM -> L2 fetch size (the control-gene gather uses one 8-byte element per sector)
+    if (const int gran = env_int("RUVIII_L2_GRAN", 0)) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     h->n_sms = sms;
@@ -97,8 +104,10 @@ void init_shard(ruviii_handle* h, Shard& s, int device) {
 
 void finish_create(ruviii_handle* h) {
     RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
-    RUVIII_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flags, 64 * sizeof(int), cudaHostAllocDefault));
-    std::memset(h->h_flags, 0, 64 * sizeof(int));
+    RUVIII_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flags, kHostFlagInts * sizeof(int), cudaHostAllocDefault));
+    std::memset(h->h_flags, 0, kHostFlagInts * sizeof(int));
+    RUVIII_CUDA_CHECK(cudaHostAlloc((void**)&h->h_dflag, 64 * sizeof(double), cudaHostAllocDefault));
+    std::memset(h->h_dflag, 0, 64 * sizeof(double));
     h->gram_impl = env_int("RUVIII_GRAM_IMPL", 1);
     h->eig_impl = env_int("RUVIII_EIG_IMPL", 0);
     h->upd_impl = env_int("RUVIII_UPD_IMPL", 3);   // 1 a~ in registers, 2 TMA ring, 3 a~ in shared memory (default)
@@ -382,7 +391,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.alpha.alloc((size_t)kp * s.ld);
             s.at.alloc((size_t)kp * s.ld);
             s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
-            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp);
+            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp + 1);   // [A | ac ac' | eigensolver flag]
             s.Yc.alloc((size_t)h->rows_w * s.ldc, false);
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
@@ -395,12 +404,11 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
     }
-    // ---- solver (global rank 0 only) ----
+    // ---- eigensolver: subspace iteration on every shard that runs it, cuSOLVER on global rank 0 only ----
     h->use_topk = false;
-    if (!skip && h->rank0 == 0 && R > 0) {
+    h->persist_rb = 0;
+    if (!skip && R > 0) {
         const int GO = h->gorder;
-        Shard& s = h->shards[0];
-        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         // block subspace iteration when only the leading kk rows of fullalpha are wanted and the block (32) leaves
         // room for oversampling; cuSOLVER otherwise and as the fallback
         const bool topk_ok = h->n_alpha_rows == h->kk && h->kk <= kTopkMaxK && GO >= 4 * kTopkBlock &&
@@ -409,25 +417,39 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             throw Error(RUVIII_ERR_UNSUPPORTED, "RUVIII_EIG_IMPL=3 but the problem is outside the subspace-iteration range");
         h->use_topk = topk_ok && (h->eig_impl == 0 || h->eig_impl == 3);
         if (h->use_topk) {
-            s.topk_buf.alloc(topk_work_doubles(GO, kTopkBlock), false);
-            s.topk_state.alloc(4);
-            topk_bind(s.topk, s.topk_buf.p, s.topk_state.p, GO, kTopkBlock);
+            // The persistent single-kernel form runs redundantly on EVERY shard (the allreduced Gram is the same bits
+            // everywhere), which removes the broadcast of U; the multi-kernel form (large orders) runs on global rank 0.
+            h->persist_rb = topk_persist_rows(GO, h->n_sms);
+            for (int i = 0; i < nsh; ++i) {
+                if (!h->persist_rb && !(i == 0 && h->rank0 == 0)) continue;
+                Shard& s = h->shards[i];
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                const size_t base = topk_work_doubles(GO, kTopkBlock);
+                s.topk_buf.alloc(base + topk_persist_doubles(h->n_sms), false);
+                s.topk_state.alloc(16);
+                topk_bind(s.topk, s.topk_buf.p, s.topk_state.p, GO, kTopkBlock);
+                s.persist_ws = s.topk_buf.p + base;
+            }
         }
-        if (!h->solver) {
-            RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
-            RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
+        if (h->rank0 == 0) {
+            Shard& s = h->shards[0];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            if (!h->solver) {
+                RUVIII_SOLVER_CHECK(cusolverDnCreate(&h->solver));
+                RUVIII_SOLVER_CHECK(cusolverDnSetStream(h->solver, s.stream));
+            }
+            int lwork = 0, meig = 0;
+            if (h->eig_impl == 1 || h->n_keep >= GO) {
+                RUVIII_SOLVER_CHECK(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, GO,
+                                                                s.G.p, GO, s.evals_asc.p, &lwork));
+            } else {
+                RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                                                 CUBLAS_FILL_MODE_UPPER, GO, s.G.p, GO, 0.0, 0.0,
+                                                                 GO - h->n_keep + 1, GO, &meig, s.evals_asc.p, &lwork));
+            }
+            h->solver_work.alloc((size_t)lwork, false);
+            h->solver_info.alloc(4);
         }
-        int lwork = 0, meig = 0;
-        if (h->eig_impl == 1 || h->n_keep >= GO) {
-            RUVIII_SOLVER_CHECK(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, GO,
-                                                            s.G.p, GO, s.evals_asc.p, &lwork));
-        } else {
-            RUVIII_SOLVER_CHECK(cusolverDnDsyevdx_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
-                                                             CUBLAS_FILL_MODE_UPPER, GO, s.G.p, GO, 0.0, 0.0,
-                                                             GO - h->n_keep + 1, GO, &meig, s.evals_asc.p, &lwork));
-        }
-        h->solver_work.alloc((size_t)lwork, false);
-        h->solver_info.alloc(4);
     }
     h->planned = true;
 }
@@ -461,16 +483,30 @@ void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS,
     h->ran = false;
 }
 
-void eigensolve(ruviii_handle* h) {
+// Products with G the subspace iteration may spend before cuSOLVER takes over.  In the multi-kernel form a pass costs ~60 us
+// against ~15 ms of syevdx at R ~ 10^3; in the persistent form a filtered product costs a few microseconds.
+static int eig_max_products(const ruviii_handle* h) {
+    if (h->persist_rb) return env_int("RUVIII_EIG_MAXIT", 400);
+    return env_int("RUVIII_EIG_MAXIT", h->kk > kTopkBlock / 2 ? kTopkPatience : 150);
+}
+
+// Global rank 0 decomposes the Gram on shards[0]; the caller broadcasts.  This entry WAITS for the verdict of the subspace
+// iteration (the pipelined host path uses it, and do_run when its optimistic persistent solve did not converge:
+// allow_subspace = false goes straight to cuSOLVER).
+void eigensolve(ruviii_handle* h, bool allow_subspace) {
     Shard& s = h->shards[0];
     const int R = h->gorder;            // order of the Gram being decomposed
     RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
     h->h_flags[0] = 0;
     h->eig_iterations = 0;
-    if (h->use_topk) {
-        TopkResult tr = topk_eigen(s.G.p, R, h->kk, h->kp, h->n_keep, kTopkBlock, s.topk, s.U.p, s.evals.p, h->eig_tol,
-                                   env_int("RUVIII_EIG_MAXIT", h->kk > kTopkBlock / 2 ? kTopkPatience : 150), h->n_sms,
-                                   &h->h_flags[60], s.stream);
+    if (h->use_topk && allow_subspace) {
+        TopkResult tr;
+        if (h->persist_rb)
+            tr = topk_eigen_persistent(s.G.p, R, h->kk, h->kp, h->n_keep, s.topk, s.persist_ws, s.U.p, s.evals.p, nullptr, h->eig_tol,
+                                       eig_max_products(h), h->n_sms, &h->h_flags[64], true, s.stream);
+        else
+            tr = topk_eigen(s.G.p, R, h->kk, h->kp, h->n_keep, kTopkBlock, s.topk, s.U.p, s.evals.p, h->eig_tol, eig_max_products(h),
+                            h->n_sms, &h->h_flags[60], s.stream);
         h->launches += tr.launches;
         h->eig_iterations = tr.iterations;
         if (tr.converged) {
@@ -564,7 +600,9 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
                 RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
                 RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_g0, s.copy_stream));
                 launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, 0, 0.0, s.copy_stream);
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_g1, s.copy_stream));
                 RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
             });
             h->launches += 1;
@@ -636,22 +674,47 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 allreduce_sum(h, b, (size_t)GO * GO);
             }
             rec(E_AR1);
-            if (h->rank0 == 0) eigensolve(h);
-            rec(E_EIG);
-            {
-                std::vector<double*> b;
-                for (auto& s : h->shards) b.push_back(s.U.p);
-                broadcast0(h, b, (size_t)GO * kp);
-                b.clear();
-                for (auto& s : h->shards) b.push_back(s.evals.p);
-                broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
-                if (h->n_alpha_rows > kk) {
-                    b.clear();
-                    for (auto& s : h->shards) b.push_back(s.Vd.p);
-                    broadcast0(h, b, (size_t)GO * h->n_keep);
+        }
+        // Everything behind the Gram.  classic = false: the persistent eigensolver is enqueued on every shard WITHOUT waiting
+        // for its verdict and the rest of the pass is queued behind it; its "not converged" flag travels in the [A | ac ac']
+        // allreduce, so every rank learns after the final synchronisation whether ANY rank has to fall back, and then all of
+        // them run this tail once more with classic = true (cuSOLVER on global rank 0 + broadcast).
+        bool persist_used = false;
+        auto tail = [&](bool classic) {
+        const int GO = h->gorder;
+        const size_t flag_off = (size_t)h->rows_w * kp + (size_t)kp * kp;
+        persist_used = !classic && !h->have_user_alpha && h->use_topk && h->persist_rb > 0;
+        if (!h->have_user_alpha) {
+            if (persist_used) {
+                for (size_t i = 0; i < h->shards.size(); ++i) {
+                    Shard& s = h->shards[i];
+                    RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                    topk_eigen_persistent(s.G.p, GO, kk, kp, h->n_keep, s.topk, s.persist_ws, s.U.p, s.evals.p, s.AG.p + flag_off,
+                                          h->eig_tol, eig_max_products(h), h->n_sms, &h->h_flags[64 + 16 * i], false, s.stream);
                 }
+                h->launches += 1;
+                h->eig_solver_used = 3;
+                rec(E_EIG);
+                rec(E_BCAST);
+            } else {
+                for_shards([&](Shard& s) { RUVIII_CUDA_CHECK(cudaMemsetAsync(s.AG.p + flag_off, 0, sizeof(double), s.stream)); });
+                if (h->rank0 == 0) eigensolve(h, !classic);
+                rec(E_EIG);
+                {
+                    std::vector<double*> b;
+                    for (auto& s : h->shards) b.push_back(s.U.p);
+                    broadcast0(h, b, (size_t)GO * kp);
+                    b.clear();
+                    for (auto& s : h->shards) b.push_back(s.evals.p);
+                    broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
+                    if (h->n_alpha_rows > kk) {
+                        b.clear();
+                        for (auto& s : h->shards) b.push_back(s.Vd.p);
+                        broadcast0(h, b, (size_t)GO * h->n_keep);
+                    }
+                }
+                rec(E_BCAST);
             }
-            rec(E_BCAST);
             for_shards([&](Shard& s) {
                 if (h->gene_side) {
                     const int j = h->rank0 + (int)(&s - h->shards.data());      // this shard's rows of V
@@ -681,6 +744,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         } else {
             for (int e = E_RESIDOP; e <= E_BCAST; ++e) rec(e);
             for_shards([&](Shard& s) {
+                RUVIII_CUDA_CHECK(cudaMemsetAsync(s.AG.p + flag_off, 0, sizeof(double), s.stream));
                 launch_alpha_finalize(s.alpha.p, 1, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
             });
             h->launches += 2;
@@ -703,9 +767,14 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         {
             std::vector<double*> b;
             for (auto& s : h->shards) b.push_back(s.AG.p);
-            allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
+            allreduce_sum(h, b, flag_off + 1);
         }
         rec(E_AR2);
+        for (size_t i = 0; i < h->shards.size(); ++i) {
+            Shard& s = h->shards[i];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_dflag[i], s.AG.p + flag_off, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        }
         for_shards([&](Shard& s) {
             const double* A = s.AG.p;
             const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
@@ -749,6 +818,20 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             Shard& s = h->shards[i];
             RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
             RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[1 + i], s.status.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+        };   // tail
+        tail(false);
+        if (persist_used) {
+            sync_all(h);
+            bool redo = false;
+            for (size_t i = 0; i < h->shards.size(); ++i) redo = redo || h->h_dflag[i] != 0.0;
+            h->eig_iterations = h->h_flags[64 + 1];
+            if (redo) {
+                if (h->eig_impl == 3)
+                    throw Error(RUVIII_ERR_SOLVER, "subspace iteration did not converge in " + std::to_string(h->eig_iterations) +
+                                                       " products (RUVIII_EIG_IMPL=3 forbids the cuSOLVER fallback)");
+                tail(true);
+            }
         }
     }
     if (h->prm.average_rep) {                               // ruvIII.R:148-149, after either branch
@@ -800,6 +883,12 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         I.ms_solve = el(E_AR2, E_SOLVE);
         I.ms_update = el(E_SOLVE, E_UPDATE);
         I.ms_total = el(E_START, E_UPDATE);
+        if (!skip) { float ms = 0.f; if (cudaEventElapsedTime(&ms, s.ev_g0, s.ev_g1) == cudaSuccess) I.ms_gather = ms; else cudaGetLastError(); }
+        if (!skip && !h->have_user_alpha && h->eig_solver_used == 3 && h->persist_rb) {
+            I.eig_rr = h->h_flags[64 + 4];
+            I.eig_chol2 = h->h_flags[64 + 5];
+            I.eig_filter_products = h->h_flags[64 + 6];
+        }
         if (!skip && !h->have_user_alpha) {
             std::vector<double> ev(h->kk + 1, 0.0);
             const int have = std::min(h->kk + 1, h->n_keep);

@@ -139,6 +139,7 @@ struct Shard {
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
     cudaEvent_t ev_acgram = nullptr;                      // aux -> main join of ac %*% t(ac)
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;         // timing of the control-gene gather on the auxiliary stream
     int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
@@ -152,12 +153,14 @@ struct Shard {
     DevBuf<int2> tile_map;
     DevBuf<int> ctl_idx, grp_start, grp_rows, status, topk_state, all_start, all_rows, status1, set_start, set_rows;
     TopkWork topk{};
+    double* persist_ws = nullptr;          // workspace of the persistent eigensolver (inside topk_buf)
     alignas(64) unsigned char tmap[128];   // host copy of the CUtensorMap of Y0 (gram impl 2)
     alignas(64) unsigned char tmap_y[128]; // host copy of the CUtensorMap of Y (update impl 2)
     GramPlan gp;
     int rsplit = 1;
 };
 
+constexpr int kHostFlagInts = 64 + 16 * 16;
 enum Ev { E_START, E_LOG, E_RESIDOP, E_GRAM, E_AR1, E_EIG, E_BCAST, E_PROJECT, E_CTL, E_AR2, E_SOLVE, E_UPDATE, E_COUNT };
 
 }  // namespace ruviii
@@ -174,7 +177,9 @@ struct ruviii_handle {
     cublasHandle_t blas = nullptr;
     ruviii::DevBuf<double> solver_work;
     ruviii::DevBuf<int> solver_info;
-    int* h_flags = nullptr;             // pinned: [0] cusolver devInfo, [1..] cholesky status per shard
+    int* h_flags = nullptr;             // pinned: [0] cusolver devInfo, [1..] cholesky status per shard, [60..63] multi-kernel
+                                        // eigensolver state, [64 + 16 i ..] persistent eigensolver state of shard i
+    double* h_dflag = nullptr;          // pinned: [i] = allreduced "some rank's eigensolver did not converge" flag of shard i
 
     // plan
     bool planned = false, uploaded = false, ran = false, logged = false, have_user_alpha = false;
@@ -197,6 +202,7 @@ struct ruviii_handle {
     int gram_impl = 1, eig_impl = 0;   // eig_impl: 0 auto, 1 syevd, 2 syevdx, 3 subspace iteration only
     int rank_bound = 0, eig_solver_used = 0, eig_iterations = 0;
     bool use_topk = false;
+    int persist_rb = 0;                 // rows of G per CTA of the persistent eigensolver; 0 = multi-kernel form / cuSOLVER
     bool active_all_ps = false;         // every non-singleton row is a PRPS row (the PRPS regime)
     int pipelined_last = 0;             // 1 when the last ruviii_normalise took the pipelined host path
     bool gene_side = false;             // Gram = Z'Z (n x n) instead of Z Z' (R x R): taken when R > n
@@ -231,7 +237,7 @@ void sync_all(ruviii_handle* h);
 void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps, const int32_t* group_of_row,
              const uint8_t* ctl, const int32_t* ks, int nk);
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS);
-void eigensolve(ruviii_handle* h);
+void eigensolve(ruviii_handle* h, bool allow_subspace = true);
 void do_run(ruviii_handle* h, ruviii_info* info_out);
 void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W);
 // engine_pipeline.cu

@@ -75,6 +75,7 @@ struct TopkWork {
 };
 struct TopkResult {
     bool converged = false;
+    bool pending = false;        // persistent solver launched without waiting: the verdict is in h_state once the stream drained
     int iterations = 0, launches = 0;
 };
 constexpr int kTopkBlock = 32;   // block width B of the subspace iteration
@@ -88,6 +89,17 @@ void topk_bind(TopkWork& w, double* base, int* state, int R, int B);
 // U: row-major R x kp (first kk columns, sign fixed); evals: n_keep descending Ritz values (only the first kk converged)
 TopkResult topk_eigen(const double* G, int R, int kk, int kp, int n_keep, int B, TopkWork& w, double* U, double* evals,
                       double tol, int max_iter, int n_sms, int* h_state, cudaStream_t s);
+
+// K3, persistent form (eigen_persist.cu): the same iteration as ONE cooperative kernel for Gram orders that fit a
+// co-resident grid (R <= 32 x #SMs), convergence decided on the device, Chebyshev-filtered continuation for slowly decaying
+// spectra.  topk_persist_rows: rows of G per CTA (8/16/32) or 0 when the order is out of range (or RUVIII_EIG_PERSIST=0).
+// persist_ws: topk_persist_doubles(n_sms) doubles; w.state must hold 16 ints (zeroed once).  flag_out (optional): receives
+// 0.0 / 1.0 (converged / not) so that the next allreduce tells every rank whether any rank has to fall back.
+int topk_persist_rows(int R, int n_sms);
+size_t topk_persist_doubles(int n_sms);
+TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_keep, TopkWork& w, double* persist_ws, double* U,
+                                 double* evals, double* flag_out, double tol, int max_iter, int n_sms, int* h_state, bool sync,
+                                 cudaStream_t s);
 
 // K4  ruvIII.R:140  fullalpha = t(U) %*% Y  (rows 1..kk; = t(U) %*% Y0 because U is orthogonal to col(M)).
 // part: rsplit x kp x ld partial sums over row chunks of Y0 (summed by launch_alpha_finalize).
