@@ -212,6 +212,16 @@ int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1
 int ruviii_fast_residop(ruviii_handle* h, const double* A_rowmajor_rows_x_n, int32_t rows, int32_t n,
                         const int32_t* group_of_row, double* out);
 
+/* The other four primitives of RcppExports.R:12-26 -- matrixMult(A, B), matSubtraction(A, B), matTranspose(A), matInverse(A).
+ * The reference declares them (`.Call('_RUVIIIPRPS_matrixMult', ...)` etc.) but ships no implementation and never calls them;
+ * they are provided so that the declared boundary is complete.  Column-major (R) host matrices, first GPU of the handle;
+ * none is on the hot path: the product is a plain cuBLAS Dgemm, the inverse cuSOLVER getrf + getrs against the identity
+ * (LAPACK's dgesv route, what R's solve(A) runs; an exactly singular matrix is RUVIII_ERR_SINGULAR, R stops too). */
+int ruviii_mat_mult(ruviii_handle* h, const double* A, int32_t m, int32_t k, const double* B, int32_t n, double* out /* m x n */);
+int ruviii_mat_subtract(ruviii_handle* h, const double* A, const double* B, int64_t count, double* out);
+int ruviii_mat_transpose(ruviii_handle* h, const double* A, int32_t m, int32_t n, double* out /* n x m */);
+int ruviii_mat_inverse(ruviii_handle* h, const double* A, int32_t n, double* out /* n x n */);
+
 /* Page-locked host memory.  ruviii_normalise overlaps upload, compute and download only when Y and newY_out are
  * page-locked (these helpers, cudaHostAlloc or cudaHostRegister); with pageable buffers it copies, computes and
  * copies back in sequence.  Returns NULL when no CUDA device is present. */

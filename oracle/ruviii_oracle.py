@@ -95,19 +95,39 @@ def residop(A, B):
     return A - BtBB_inv_tBA             # :94
 
 
+def design_matrix_t(eta, n, include_intercept=True):
+    """``t(ruv::design.matrix(eta, include.intercept))`` as ``ruv::RUV1`` uses it: q x n, one column per gene.
+
+    Restated from memory of ruv 0.9.7.1 (the package source is not in the container): ``RUV1`` turns a single number
+    into ``matrix(1, n, 1)`` (intercept only); ``design.matrix`` prepends the column of ones when ``include.intercept``
+    and the constant vector is not already in the column span of the design
+    (``sum(residop(matrix(1, n, 1), A)^2) > 1e-8``).  A gene-wise matrix may be given n x q (R) or q x n.
+    """
+    e = np.asarray(eta, dtype=np.float64)
+    if e.ndim == 0 or e.size == 1:
+        return np.ones((1, n))
+    e = np.atleast_2d(e)
+    if e.shape[1] != n and e.shape[0] == n:
+        e = e.T
+    if e.shape[1] != n:
+        raise ValueError("eta must have one row per gene (n x q)")
+    if include_intercept:
+        A = e.T                                                   # n x q, the design as R holds it
+        ones = np.ones((n, 1))
+        if float(np.sum(residop(ones, A) ** 2)) > 1e-8:
+            e = np.vstack([np.ones((1, n)), e])
+    return e
+
+
 def RUV1(Y, eta, ctl, include_intercept=True):
     """``ruv::RUV1`` (ruvIII.R:116, fastruvIII.R:133-134).  Identity for ``eta = NULL`` (the default,
     normalise.R:81).  The ``eta`` branch restates ruv 0.9.7.1 from memory of its published source
-    (``Y - Y_c eta_c' (eta_c eta_c')^-1 eta``; a row of ones is prepended when ``include.intercept``);
+    (``Y - Y_c eta_c' (eta_c eta_c')^-1 eta`` with ``eta = t(design.matrix(eta))``, see :func:`design_matrix_t`);
     the package source is not in the container, so that branch is doubly unpinned.
     """
     if eta is None:
         return Y
-    eta = np.atleast_2d(np.asarray(eta, dtype=np.float64))
-    if eta.shape[1] != Y.shape[1]:
-        raise ValueError("eta must be q x n (one column per gene)")
-    if include_intercept:
-        eta = np.vstack([np.ones((1, Y.shape[1])), eta])
+    eta = design_matrix_t(eta, Y.shape[1], include_intercept)
     Yc = Y[:, ctl]
     etac = eta[:, ctl]
     return Y - Yc @ etac.T @ np.linalg.inv(etac @ etac.T) @ eta

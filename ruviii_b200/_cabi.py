@@ -21,7 +21,7 @@ SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
     "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats",
-    "ruviii_fast_residop", "ruviii_probe",
+    "ruviii_fast_residop", "ruviii_probe", "ruviii_mat_mult", "ruviii_mat_subtract", "ruviii_mat_transpose", "ruviii_mat_inverse",
 ]
 
 
@@ -102,6 +102,10 @@ def load_library():
                                C.c_int32, vp, vp, vp, vp]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
     lib.ruviii_probe.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    lib.ruviii_mat_mult.argtypes = [H, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp]
+    lib.ruviii_mat_subtract.argtypes = [H, vp, vp, C.c_int64, vp]
+    lib.ruviii_mat_transpose.argtypes = [H, vp, C.c_int32, C.c_int32, vp]
+    lib.ruviii_mat_inverse.argtypes = [H, vp, C.c_int32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("ruviii_destroy", "ruviii_last_error", "ruviii_host_alloc", "ruviii_host_free"):
@@ -409,6 +413,44 @@ class Engine:
         g = np.ascontiguousarray(group_of_row, dtype=np.int32)
         out = np.empty_like(A)
         self._check(self._lib.ruviii_fast_residop(self._h, _ptr(A), A.shape[0], A.shape[1], _ptr(g), _ptr(out)))
+        return out
+
+    # ---- the generic primitives of RcppExports.R:12-26 (R matrices are column-major: numpy arrays go in Fortran order) ----
+    @staticmethod
+    def _colmajor(a, name):
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim != 2:
+            raise TypeError("%s must be a matrix" % name)
+        return np.asfortranarray(a)
+
+    def matrixMult(self, A, B):
+        A, B = self._colmajor(A, "A"), self._colmajor(B, "B")
+        if A.shape[1] != B.shape[0]:
+            raise RuviiiError(ERR_INVALID, "non-conformable arguments")
+        out = np.empty((A.shape[0], B.shape[1]), dtype=np.float64, order="F")
+        self._check(self._lib.ruviii_mat_mult(self._h, _ptr(A), A.shape[0], A.shape[1], _ptr(B), B.shape[1], _ptr(out)))
+        return out
+
+    def matSubtraction(self, A, B):
+        A, B = self._colmajor(A, "A"), self._colmajor(B, "B")
+        if A.shape != B.shape:
+            raise RuviiiError(ERR_INVALID, "non-conformable arrays")
+        out = np.empty(A.shape, dtype=np.float64, order="F")
+        self._check(self._lib.ruviii_mat_subtract(self._h, _ptr(A), _ptr(B), A.size, _ptr(out)))
+        return out
+
+    def matTranspose(self, A):
+        A = self._colmajor(A, "A")
+        out = np.empty((A.shape[1], A.shape[0]), dtype=np.float64, order="F")
+        self._check(self._lib.ruviii_mat_transpose(self._h, _ptr(A), A.shape[0], A.shape[1], _ptr(out)))
+        return out
+
+    def matInverse(self, A):
+        A = self._colmajor(A, "A")
+        if A.shape[0] != A.shape[1]:
+            raise RuviiiError(ERR_INVALID, "'a' must be a square matrix")
+        out = np.empty(A.shape, dtype=np.float64, order="F")
+        self._check(self._lib.ruviii_mat_inverse(self._h, _ptr(A), A.shape[0], _ptr(out)))
         return out
 
     def probe(self, which, size=0):

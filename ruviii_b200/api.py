@@ -111,7 +111,8 @@ def _prepare(se_obj, assay_name, replicate_data, ctl, inputcheck, n_rows_for_che
 def _design_matrix_t(eta, n, include_intercept):
     """t(design.matrix(eta, include.intercept)) of ruv::RUV1: q x n with one column per gene.  A single number means
     "intercept only" (RUV1: ``if (length(eta) == 1) eta = matrix(1, n, 1)``); a gene-wise matrix may be given as n x q
-    (R's orientation) or q x n; the row of ones is prepended unless a constant row is already present."""
+    (R's orientation) or q x n; the row of ones is prepended unless the constant vector already lies in the span of the
+    design (design.matrix: ``sum(residop(matrix(1, n, 1), A)^2) > 1e-8``).  Host-side bookkeeping on a q x n matrix, q <= 32."""
     e = np.asarray(eta, dtype=np.float64)
     if e.ndim == 0 or e.size == 1:
         return np.ones((1, n))
@@ -120,8 +121,11 @@ def _design_matrix_t(eta, n, include_intercept):
         e = e.T
     if e.shape[1] != n:
         raise ValueError("eta must have one row per gene (n x q)")
-    if include_intercept and not any(np.ptp(row) == 0 and row[0] != 0 for row in e):
-        e = np.vstack([np.ones((1, n)), e])
+    if include_intercept:
+        ones = np.ones(n)
+        coef = np.linalg.lstsq(e.T, ones, rcond=None)[0]
+        if float(np.sum((ones - e.T @ coef) ** 2)) > 1e-8:
+            e = np.vstack([np.ones((1, n)), e])
     return np.ascontiguousarray(e)
 
 

@@ -49,6 +49,7 @@ struct PersistArgs {
     double* evals;                // out: n_keep leading Ritz values
     double* flag_out;             // optional: 0.0 when converged, 1.0 otherwise (summed by the next allreduce)
     int kk, kp, n_keep;
+    int ldg;                      // row pitch of the shared-memory copy of this CTA's rows of G (GS kernels)
     double tol;
     int max_iter, first, period, cheb;
     unsigned* bar;                // [0] barrier counter, [1] exit counter
@@ -63,18 +64,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "d"(a), "d"(b));
 }
 
-// Grid barrier: one monotone counter; release/acquire at GPU scope by thread 0, CTA barriers on both sides.
+// Grid barrier: one monotone counter.  Thread 0 arrives with a release (which orders every earlier write of the CTA, made
+// visible to it by the CTA barrier, before the increment), polls with relaxed loads and closes with one acquire fence.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target, unsigned P) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += P;
-        __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
-        __threadfence();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -93,6 +94,7 @@ struct Smem {
     double cs[PB / 2][2];
     int pr[PB / 2][2];
     double red[PB];
+    double sgn[PB];
     int flag, flag_big, bad;
     double minp;
 };
@@ -100,8 +102,9 @@ struct Smem {
 // ---- Z_blk = G[r0 : r0 + RB, :] Q -------------------------------------------------------------------------------------
 // RT row tiles of 8 rows; the 8 warps are RT x KS with KS = 8 / RT splits of the contraction; partials meet in shared memory
 // and are summed in a fixed order.  shift != 0: Z_blk = G Q - shift Q_own is formed later by the caller (Chebyshev).
-template <int RT>
-__device__ __forceinline__ void product_phase(const PersistArgs& a, const double* __restrict__ Q, int r0, Smem& sm) {
+template <int RT, bool GS>
+__device__ __forceinline__ void product_phase(const PersistArgs& a, const double* __restrict__ Q, int r0, Smem& sm,
+                                              const double* __restrict__ gs) {
     constexpr int KS = 8 / RT;
     constexpr int RB = 8 * RT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, kq = lane & 3;
@@ -111,15 +114,21 @@ __device__ __forceinline__ void product_phase(const PersistArgs& a, const double
     const bool row_ok = row < R;
     const int kchunk = ((R + KS - 1) / KS + 3) & ~3;
     const int k0 = ks * kchunk, k1 = min(R, k0 + kchunk);
-    const double* grow = a.G + (int64_t)min(row, R - 1) * R;
+    const double* grow = GS ? gs + (rt * 8 + g) * a.ldg : a.G + (int64_t)min(row, R - 1) * R;
     double acc[4][2];
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    // Every CTA multiplies by the same Q at the same time: walking the contraction from a CTA-dependent offset keeps the
+    // ~100 CTAs off the same L2 lines (the summation order is still fixed per CTA).
+    const int nsteps = k1 > k0 ? (k1 - k0 + 3) / 4 : 0;
+    int st = nsteps > 0 ? (int)((blockIdx.x * 7u) % (unsigned)nsteps) : 0;
 #pragma unroll 5
-    for (int k = k0; k < k1; k += 4) {
+    for (int i = 0; i < nsteps; ++i) {
+        const int k = k0 + 4 * st;
+        st = st + 1 == nsteps ? 0 : st + 1;
         const int kk = k + kq;
         const bool ok = kk < k1;
-        const double av = (ok && row_ok) ? __ldg(grow + kk) : 0.0;
+        const double av = (ok && row_ok) ? (GS ? grow[kk] : __ldg(grow + kk)) : 0.0;
         const double* qrow = Q + (int64_t)min(kk, R - 1) * PB + g;
         double b[4];
 #pragma unroll
@@ -192,36 +201,36 @@ __device__ __forceinline__ void reduce_phase(const PersistArgs& a, int len, Smem
 }
 
 // ---- column-scaled Cholesky of sm.S (B x B): L with 1 / L[j][j] on the diagonal, sm.dscale, sm.minp, sm.bad ------------
+// One warp, lane i holds row i of the scaled matrix in registers; right-looking, column j of L travels by shuffles, so the
+// 32 dependent steps cost one rsqrt + two shuffles + one FMA of latency each and no CTA barrier (a CTA-wide version with
+// one barrier per column measured 35 k cycles per factorisation, five times the product with G).
 __device__ __forceinline__ void cholesky_phase(Smem& sm) {
     const int tid = threadIdx.x;
-    if (tid < PB) sm.dscale[tid] = sm.S[tid][tid] > 0.0 ? rsqrt(sm.S[tid][tid]) : 1.0;
-    if (tid == 0) { sm.bad = 0; sm.minp = 1.0; }
-    __syncthreads();
-    for (int e = tid; e < PB * PB; e += PT) {
-        const int i = e / PB, j = e - i * PB;
-        sm.A[i][j] = 0.5 * (sm.S[i][j] + sm.S[j][i]) * sm.dscale[i] * sm.dscale[j];
-    }
-    __syncthreads();
-    // right-looking over the whole CTA, one barrier per column: step j reads column j, writes columns > j
-    const int c = tid % PB, rbase = tid / PB, rstep = PT / PB;
-    int bad = 0;
-    double minp = 1.0;
-    for (int j = 0; j < PB; ++j) {
-        const double pj = sm.A[j][j];
-        double rd = rsqrt(pj);
-        if (!(pj > 1e-30)) { bad = j + 1; rd = 1.0; }
-        minp = fmin(minp, pj);
-        const double rd2 = rd * rd;
-        if (c > j) {
-            const double acj = sm.A[c][j] * rd2;
-            for (int r = rbase; r < PB; r += rstep)
-                if (r >= c) sm.A[r][c] = fma(-sm.A[r][j], acj, sm.A[r][c]);
-        } else if (c == j) {
-            for (int r = rbase; r < PB; r += rstep) sm.L[r][j] = r > j ? sm.A[r][j] * rd : (r == j ? rd : 0.0);
+    if (tid < PB) {
+        const unsigned full = 0xffffffffu;
+        const int i = tid;
+        const double sii = sm.S[i][i];
+        const double di = sii > 0.0 ? rsqrt(sii) : 1.0;
+        sm.dscale[i] = di;
+        __syncwarp();
+        double a[PB];
+#pragma unroll
+        for (int c = 0; c < PB; ++c) a[c] = 0.5 * (sm.S[i][c] + sm.S[c][i]) * di * sm.dscale[c];
+        int bad = 0;
+        double minp = 1.0;
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const double pj = __shfl_sync(full, a[j], j);
+            double rd = rsqrt(pj);
+            if (!(pj > 1e-30)) { bad = j + 1; rd = 1.0; }
+            minp = fmin(minp, pj);
+            const double lij = a[j] * rd;                    // L[i][j] for i >= j
+            sm.L[i][j] = i > j ? lij : (i == j ? rd : 0.0);  // diagonal: 1 / L[j][j]
+#pragma unroll
+            for (int c = j + 1; c < PB; ++c) a[c] = fma(-lij, __shfl_sync(full, lij, c), a[c]);
         }
-        __syncthreads();
+        if (i == 0) { sm.bad = bad; sm.minp = minp; }
     }
-    if (tid == 0) { sm.bad = bad; sm.minp = minp; }
     __syncthreads();
 }
 
@@ -253,68 +262,66 @@ __device__ __forceinline__ void store_rows(const PersistArgs& a, double* __restr
 }
 
 // ---- H (sm.A, symmetric B x B) = V diag(theta) V': parallel cyclic Jacobi, round-robin pairing -------------------------
-// Result: sm.L = V with its columns sorted by descending theta, sm.th = theta.  One CTA.
+// Result: sm.V = V with its columns sorted by descending theta, sm.th = theta.  One CTA; uses sm.L and sm.S as scratch.
+// One CTA barrier per round: thread (ia, ib) owns the 2 x 2 block rows (pair ia) x columns (pair ib) of A and rows
+// 2 ia, 2 ia + 1 x columns (pair ib) of V; the rotation of pair ib is computed by the lane itself from the CURRENT copy
+// of A, that of pair ia comes by shuffle from lane ia of the same warp (lane l holds pair l % 16), and the rotated block
+// is written to the OTHER copy of A, so nothing read in a round is written in it.  (The version with a 16-thread
+// rotation phase and two barriers per round cost 1,200 cycles per round, 93 us for the 5 sweeps of C3.)
 __device__ __forceinline__ int jacobi_phase(Smem& sm) {
     const int tid = threadIdx.x;
-    for (int e = tid; e < PB * PB; e += PT) sm.L[e / PB][e % PB] = (e / PB == e % PB) ? 1.0 : 0.0;
+    const int ia = tid / (PB / 2), ib = tid % (PB / 2);
+    double (*Ab[2])[PS] = {sm.A, sm.L};
+    double (*Vacc)[PS] = sm.S;
+    for (int e = tid; e < PB * PB; e += PT) Vacc[e / PB][e % PB] = (e / PB == e % PB) ? 1.0 : 0.0;
     __syncthreads();
-    int sweeps_run = 0;
+    int cur = 0, sweeps_run = 0;
     for (int sweep = 0; sweep < 16; ++sweep) {
         ++sweeps_run;
         if (tid == 0) { sm.flag = 0; sm.flag_big = 0; }
         __syncthreads();
+        // round-robin tournament: pair 0 = (B - 1, round); pair i = ((round + i) mod (B - 1), (round - i) mod (B - 1))
+        int ua = ia % (PB - 1), va = (PB - 1 - ia) % (PB - 1), ub = ib % (PB - 1), vb = (PB - 1 - ib) % (PB - 1);
         for (int round = 0; round < PB - 1; ++round) {
-            if (tid < PB / 2) {
-                int p, q;
-                if (tid == 0) { p = PB - 1; q = round; }
-                else { p = (round + tid) % (PB - 1); q = (round - tid + (PB - 1)) % (PB - 1); }
-                if (p > q) { const int t = p; p = q; q = t; }
-                const double app = sm.A[p][p], aqq = sm.A[q][q], apq = sm.A[p][q];
-                double c = 1.0, s = 0.0;
-                if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
-                    // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
-                    const double zeta = aqq - app, beta = 2.0 * apq;
-                    const double irr = rsqrt(fma(zeta, zeta, beta * beta));
-                    const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
-                    const double ic = rsqrt(c2);
-                    c = c2 * ic;
-                    s = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
+            int pa = ia == 0 ? PB - 1 : ua, qa = ia == 0 ? round : va;
+            int pb = ib == 0 ? PB - 1 : ub, qb = ib == 0 ? round : vb;
+            if (pa > qa) { const int t = pa; pa = qa; qa = t; }
+            if (pb > qb) { const int t = pb; pb = qb; qb = t; }
+            const double (*A)[PS] = Ab[cur];
+            double (*An)[PS] = Ab[cur ^ 1];
+            const double app = A[pb][pb], aqq = A[qb][qb], apq = A[pb][qb];
+            const double x00 = A[pa][pb], x01 = A[pa][qb], x10 = A[qa][pb], x11 = A[qa][qb];
+            double cb = 1.0, sb = 0.0;
+            if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
+                // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
+                const double zeta = aqq - app, beta = 2.0 * apq;
+                const double irr = rsqrt(fma(zeta, zeta, beta * beta));
+                const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
+                const double ic = rsqrt(c2);
+                cb = c2 * ic;
+                sb = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
+                if (ia == 0) {
                     sm.flag = 1;
                     if (apq * apq > 1e-20 * fabs(app * aqq)) sm.flag_big = 1;
                 }
-                sm.cs[tid][0] = c; sm.cs[tid][1] = s;
-                sm.pr[tid][0] = p; sm.pr[tid][1] = q;
             }
-            __syncthreads();
-            {
-                // A <- J' A J in one phase: thread (a, b) owns the 2 x 2 block rows (p, q) of pair a x columns (p', q') of pair b
-                const int ia = tid / (PB / 2), ib = tid % (PB / 2);
-                const int p = sm.pr[ia][0], q = sm.pr[ia][1], pp = sm.pr[ib][0], qq = sm.pr[ib][1];
-                const double c = sm.cs[ia][0], s = sm.cs[ia][1], cc = sm.cs[ib][0], ss = sm.cs[ib][1];
-                const double x00 = sm.A[p][pp], x01 = sm.A[p][qq], x10 = sm.A[q][pp], x11 = sm.A[q][qq];
-                const double r00 = c * x00 - s * x10, r01 = c * x01 - s * x11;
-                const double r10 = s * x00 + c * x10, r11 = s * x01 + c * x11;
-                // V <- V J: (pair i, row j) tasks, two per thread
-                double v[2][2];
-                int vi[2], vj[2];
+            const double ca = __shfl_sync(0xffffffffu, cb, ia), sa = __shfl_sync(0xffffffffu, sb, ia);
+            const double r00 = ca * x00 - sa * x10, r01 = ca * x01 - sa * x11;      // rows:    J_a' X
+            const double r10 = sa * x00 + ca * x10, r11 = sa * x01 + ca * x11;
+            An[pa][pb] = cb * r00 - sb * r01;                                        // columns: (.) J_b
+            An[pa][qb] = sb * r00 + cb * r01;
+            An[qa][pb] = cb * r10 - sb * r11;
+            An[qa][qb] = sb * r10 + cb * r11;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int e = tid + u * PT;
-                    vi[u] = e / PB; vj[u] = e % PB;
-                    v[u][0] = sm.L[vj[u]][sm.pr[vi[u]][0]];
-                    v[u][1] = sm.L[vj[u]][sm.pr[vi[u]][1]];
-                }
-                sm.A[p][pp] = cc * r00 - ss * r01;
-                sm.A[p][qq] = ss * r00 + cc * r01;
-                sm.A[q][pp] = cc * r10 - ss * r11;
-                sm.A[q][qq] = ss * r10 + cc * r11;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const double c1 = sm.cs[vi[u]][0], s1 = sm.cs[vi[u]][1];
-                    sm.L[vj[u]][sm.pr[vi[u]][0]] = c1 * v[u][0] - s1 * v[u][1];
-                    sm.L[vj[u]][sm.pr[vi[u]][1]] = s1 * v[u][0] + c1 * v[u][1];
-                }
+            for (int u = 0; u < 2; ++u) {                                            // V <- V J_b on this thread's two rows
+                const int j = 2 * ia + u;
+                const double vx = Vacc[j][pb], vy = Vacc[j][qb];
+                Vacc[j][pb] = cb * vx - sb * vy;
+                Vacc[j][qb] = sb * vx + cb * vy;
             }
+            ua = ua + 1 == PB - 1 ? 0 : ua + 1;  va = va + 1 == PB - 1 ? 0 : va + 1;
+            ub = ub + 1 == PB - 1 ? 0 : ub + 1;  vb = vb + 1 == PB - 1 ? 0 : vb + 1;
+            cur ^= 1;
             __syncthreads();
         }
         // quadratic convergence: a sweep whose largest relative off-diagonal entry was below 1e-10 leaves them below rounding
@@ -322,12 +329,13 @@ __device__ __forceinline__ int jacobi_phase(Smem& sm) {
         __syncthreads();
         if (stop) break;
     }
+    const double (*A)[PS] = Ab[cur];
     // sort descending (rank sort): sm.th, sm.V = V with permuted columns
     if (tid < PB) {
-        const double t = sm.A[tid][tid];
+        const double t = A[tid][tid];
         int rank = 0;
         for (int i = 0; i < PB; ++i) {
-            const double u = sm.A[i][i];
+            const double u = A[i][i];
             rank += (u > t) || (u == t && i < tid);
         }
         sm.pr[tid % (PB / 2)][tid / (PB / 2)] = rank;
@@ -336,7 +344,7 @@ __device__ __forceinline__ int jacobi_phase(Smem& sm) {
     __syncthreads();
     for (int e = tid; e < PB * PB; e += PT) {
         const int i = e / PB, j = e % PB;
-        sm.V[i][sm.pr[j % (PB / 2)][j / (PB / 2)]] = sm.L[i][j];
+        sm.V[i][sm.pr[j % (PB / 2)][j / (PB / 2)]] = Vacc[i][j];
     }
     __syncthreads();
     return sweeps_run;
@@ -360,10 +368,11 @@ __device__ __forceinline__ void small_mm(double (*dst)[PS], const double (*lhs)[
 
 enum Phase { PH_START = 1, PH_PRODUCT, PH_PARTIALS, PH_BAR, PH_REDUCE, PH_CHOL, PH_APPLY, PH_JACOBI, PH_ROTATE, PH_CHECK, PH_CHEB, PH_END };
 
-template <int RT>
+template <int RT, bool GS>
 __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    double* gs = reinterpret_cast<double*>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));   // GS: RB x ldg doubles behind Smem
     const int tid = threadIdx.x, cta = blockIdx.x, R = a.R, RB = a.RB, P = a.P;
     const int r0 = cta * RB;
     unsigned target = 0;
@@ -372,6 +381,10 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
     double* Qbuf[2] = {a.Q0, a.Q1};
     trace_mark(a, ntrace, PH_START);
     if (cta == 0 && tid == 0) a.state[5] = 0;
+    auto gbar = [&]() {
+        grid_barrier(a.bar, target, P);
+        trace_mark(a, ntrace, PH_BAR);
+    };
 
     // One round of column-scaled Cholesky QR of the rows in `src` (partials -> reduce -> Cholesky -> substitution);
     // with `have_S` the reduced S is already in sm.S.  Leaves Q_blk in sm.Q; returns false on a Cholesky breakdown.
@@ -380,10 +393,10 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             if (!(round == 0 && have_S)) {
                 partials_phase(a, round == 0 ? src : sm.Q, false, sm);
                 trace_mark(a, ntrace, PH_PARTIALS);
-                grid_barrier(a.bar, target, P);
+                gbar();
                 reduce_phase(a, 1024, sm);
                 trace_mark(a, ntrace, PH_REDUCE);
-                grid_barrier(a.bar, target, P);
+                gbar();
                 for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = __ldcg(a.Pred + e);
                 __syncthreads();
             }
@@ -400,7 +413,8 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
         return true;
     };
 
-    // ---- start block: fixed hash of (row, column), uniform in (-1, 1) ----
+    // ---- start block: fixed hash of (row, column), uniform in (-1, 1).  It is not orthogonalised: the first product
+    //      G Q_0 does not care, and its Cholesky QR (two rounds: the columns of G Q_0 are nearly parallel) does the job ----
     for (int e = tid; e < RB * PB; e += PT) {
         const int r = e / PB, c = e - r * PB;
         double v = 0.0;
@@ -409,35 +423,41 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
             v = (double)(int64_t)(x >> 11) * (1.0 / 4503599627370496.0) - 1.0;
         }
-        sm.Z[r][c] = v;
+        sm.Q[r][c] = v;
+    }
+    if (GS) {
+        // this CTA's rows of G stay in shared memory for the whole solve (RB = 8: 8 R doubles)
+        const int ldg = a.ldg;
+        for (int e = tid; e < RB * R; e += PT) {
+            const int r = e / R, c = e - r * R;
+            gs[r * ldg + c] = (r0 + r < R) ? __ldg(a.G + (int64_t)(r0 + r) * R + c) : 0.0;
+        }
     }
     __syncthreads();
-    bool ok = ortho(sm.Z, false);
+    bool ok = true;
     int converged = 0, it = 0, n_rr = 0, n_cheb = 0;
-    if (ok) {
-        store_rows(a, Qbuf[cur], sm.Q, r0);
-        grid_barrier(a.bar, target, P);
-    }
+    store_rows(a, Qbuf[cur], sm.Q, r0);
+    gbar();
     int next_rr = a.first;
     while (ok && it < a.max_iter) {
         ++it;
-        product_phase<RT>(a, Qbuf[cur], r0, sm);
+        product_phase<RT, GS>(a, Qbuf[cur], r0, sm, gs);
         trace_mark(a, ntrace, PH_PRODUCT);
         const bool rr = it >= next_rr;
         if (!rr) {
             ok = ortho(sm.Z, false);
             if (!ok) break;
             store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
-            grid_barrier(a.bar, target, P);
+            gbar();
             cur ^= 1;
             continue;
         }
         // ---- Rayleigh-Ritz pass ----
         ++n_rr;
         partials_phase(a, sm.Z, true, sm);
-        grid_barrier(a.bar, target, P);
+        gbar();
         reduce_phase(a, 2048, sm);
-        grid_barrier(a.bar, target, P);
+        gbar();
         trace_mark(a, ntrace, PH_REDUCE);
         if (cta == 0) {
             for (int e = tid; e < PB * PB; e += PT) sm.L[e / PB][e % PB] = __ldcg(a.Pred + 1024 + e);
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             if (tid == 0) a.state[3] = sweeps;
             trace_mark(a, ntrace, PH_JACOBI);
         }
-        grid_barrier(a.bar, target, P);
+        gbar();
         for (int e = tid; e < PB * PB; e += PT) {
             sm.V[e / PB][e % PB] = __ldcg(a.Vm + e);
             sm.S[e / PB][e % PB] = __ldcg(a.Pred + e);
@@ -497,28 +517,29 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             }
         }
         trace_mark(a, ntrace, PH_ROTATE);
-        grid_barrier(a.bar, target, P);
+        gbar();
         // every CTA folds the P partials itself, in the same order: the same decision everywhere
         {
             const int j = tid % PB, grp = tid / PB;          // 8 groups of CTAs
-            double s = 0.0, best = 0.0;
+            double s = 0.0, best = 0.0, best_abs = -1.0;
             for (int p = grp; p < P; p += PT / PB) {
                 s += __ldcg(a.Pr + (int64_t)p * 64 + j);
                 const double x = __ldcg(a.Pr + (int64_t)p * 64 + 32 + j);
-                if (fabs(x) > fabs(best)) best = x;
+                const double ax = fabs(x);
+                if (ax > best_abs) { best_abs = ax; best = x; }
             }
             sm.part[grp * PB + j] = s;
             sm.part[1024 + grp * PB + j] = best;
             __syncthreads();
             if (tid < PB) {
-                double t = 0.0, b = 0.0;
+                double t = 0.0, b = 0.0, b_abs = -1.0;
                 for (int q = 0; q < PT / PB; ++q) {
                     t += sm.part[q * PB + tid];
-                    const double x = sm.part[1024 + q * PB + tid];
-                    if (fabs(x) > fabs(b)) b = x;
+                    const double x = sm.part[1024 + q * PB + tid], ax = fabs(x);
+                    if (ax > b_abs) { b_abs = ax; b = x; }
                 }
                 sm.red[tid] = sqrt(t);
-                sm.dscale[tid] = b < 0.0 ? -1.0 : 1.0;       // sign that makes the largest-|component| positive
+                sm.sgn[tid] = b < 0.0 ? -1.0 : 1.0;          // sign that makes the largest-|component| positive
             }
             __syncthreads();
             if (tid == 0) {
@@ -568,13 +589,13 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 const int d = (int)fmin(fmin((double)dcap, fmax(1.0, ceil((need - gain + log(2.0)) / ak))),
                                         fmin(40.0, (double)(a.max_iter - it)));
                 store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);      // start block of this round: Ritz vectors / the last Q
-                grid_barrier(a.bar, target, P);
+                gbar();
                 cur ^= 1;
                 // Y_1 = (sigma_1 / e) (G - c I) Y_0,  Y_{i+1} = (2 sigma_{i+1} / e) (G - c I) Y_i - sigma_i sigma_{i+1} Y_{i-1}:
                 // the rows of Y_i live in sm.Q, those of Y_{i-1} in sm.X; one barrier per product
                 double sig = sig1;
                 for (int i = 1; i <= d; ++i) {
-                    product_phase<RT>(a, Qbuf[cur], r0, sm);
+                    product_phase<RT, GS>(a, Qbuf[cur], r0, sm, gs);
                     const double sig_next = 1.0 / (2.0 / sig1 - sig);
                     for (int e = tid; e < RB * PB; e += PT) {
                         const int r = e / PB, c = e - r * PB;
@@ -588,7 +609,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                     ++it; ++n_cheb;
                     if (i < d) {
                         store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
-                        grid_barrier(a.bar, target, P);
+                        gbar();
                         cur ^= 1;
                     }
                     trace_mark(a, ntrace, PH_CHEB);
@@ -603,14 +624,14 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
         }
         if (!ok) break;
         store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
-        grid_barrier(a.bar, target, P);
+        gbar();
         cur ^= 1;
     }
     // ---- results ----
     if (converged) {
         for (int e = tid; e < RB * a.kp; e += PT) {
             const int r = e / a.kp, j = e - r * a.kp;
-            if (r0 + r < R) a.U[(int64_t)(r0 + r) * a.kp + j] = j < a.kk ? sm.dscale[j] * sm.X[r][j] : 0.0;
+            if (r0 + r < R) a.U[(int64_t)(r0 + r) * a.kp + j] = j < a.kk ? sm.sgn[j] * sm.X[r][j] : 0.0;
         }
         if (cta == 0 && tid < a.n_keep && tid < PB) a.evals[tid] = sm.th[tid];
     }
@@ -633,17 +654,17 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
     }
 }
 
-template <int RT>
-void launch_persist(const PersistArgs& a, cudaStream_t s) {
+template <int RT, bool GS>
+void launch_persist(const PersistArgs& a, size_t smem, cudaStream_t s) {
     // per device (a process may drive several): cheap enough to repeat on every launch
-    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ek_persistent_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ek_persistent_kernel<RT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const bool coop = [] { const char* v = std::getenv("RUVIII_EIG_COOP"); return !(v && *v == '0'); }();
     PersistArgs args = a;
     if (coop) {
         void* params[] = {&args};
-        RUVIII_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)ek_persistent_kernel<RT>, dim3(a.P), dim3(PT), params, sizeof(Smem), s));
+        RUVIII_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)ek_persistent_kernel<RT, GS>, dim3(a.P), dim3(PT), params, smem, s));
     } else {
-        ek_persistent_kernel<RT><<<a.P, PT, sizeof(Smem), s>>>(args);
+        ek_persistent_kernel<RT, GS><<<a.P, PT, smem, s>>>(args);
         RUVIII_LAUNCH_CHECK();
     }
 }
@@ -655,8 +676,10 @@ int topk_persist_rows(int R, int n_sms) {
     const char* pv = std::getenv("RUVIII_EIG_PERSIST");
     const int off = pv && *pv == '0' ? 1 : 0;
     if (off || R < 4 * PB) return 0;
+    const char* fv = std::getenv("RUVIII_EIG_RB");          // experiments: force 8 / 16 / 32 rows per CTA
+    const int forced = fv && *fv ? std::atoi(fv) : 0;
     for (int rb : {8, 16, 32})
-        if ((R + rb - 1) / rb <= n_sms) return rb;
+        if ((R + rb - 1) / rb <= n_sms && (!forced || rb >= forced)) return rb;
     return 0;
 }
 
@@ -685,15 +708,24 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
     a.kk = kk; a.kp = kp; a.n_keep = n_keep; a.tol = tol; a.max_iter = max_iter;
     static const int first_env = [] { const char* v = std::getenv("RUVIII_EIG_FIRST"); return v && *v ? std::atoi(v) : 0; }();
     static const int cheb_env = [] { const char* v = std::getenv("RUVIII_EIG_CHEB"); return v && *v ? std::atoi(v) : 1; }();
-    a.first = first_env > 0 ? first_env : 6;
+    a.first = std::max(2, first_env > 0 ? first_env : 6);   // the start block is not orthonormal: no Rayleigh-Ritz on pass 1
     a.period = 3;
     a.cheb = cheb_env;
     a.bar = reinterpret_cast<unsigned*>(w.state + 8);
     a.state = w.state;
+    // RB = 8: the CTA's 8 rows of G (8 R doubles, pitch = 4 mod 16 doubles so that the 8 x 4 fragment loads of a warp spread
+    // over the banks) live in shared memory behind the Smem block
+    const size_t base_smem = (sizeof(Smem) + 15) & ~size_t(15);
+    a.ldg = (int)round_up(R, 16) + 4;
+    const size_t gs_smem = base_smem + (size_t)8 * a.ldg * sizeof(double);
+    static const bool gs_off = [] { const char* v = std::getenv("RUVIII_EIG_GSMEM"); return v && *v == '0'; }();
     switch (rb) {
-        case 8: launch_persist<1>(a, s); break;
-        case 16: launch_persist<2>(a, s); break;
-        default: launch_persist<4>(a, s); break;
+        case 8:
+            if (!gs_off && gs_smem <= 200 * 1024) launch_persist<1, true>(a, gs_smem, s);
+            else launch_persist<1, false>(a, base_smem, s);
+            break;
+        case 16: launch_persist<2, false>(a, base_smem, s); break;
+        default: launch_persist<4, false>(a, base_smem, s); break;
     }
     res.launches = 1;
     RUVIII_CUDA_CHECK(cudaMemcpyAsync(h_state, w.state, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));

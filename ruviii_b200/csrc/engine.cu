@@ -595,10 +595,11 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         // Control-gene gather on the auxiliary stream.  It depends on Y only; it is forked AFTER the (bandwidth- and
         // tensor-bound) residop and Gram so that it fills the otherwise idle GPU during the eigensolve, whose kernels
         // are latency-bound and occupy a handful of SMs (forked at the start it only stole HBM bandwidth from K1).
-        auto fork_gather = [&]() {
+        bool defer_gather = false;
+        auto fork_gather = [&](bool record = true) {
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
-                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
+                if (record) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
                 RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
                 RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_g0, s.copy_stream));
                 launch_ctl_gather(src, h->rows_w, s.ctl_idx.p, s.n_ctl, s.Yc.p, s.ldc, 0, 0.0, s.copy_stream);
@@ -667,7 +668,15 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 h->launches += 2;
             }
             rec(E_GRAM);
-            if (gather_at == 0) fork_gather();
+            // Persistent eigensolver: its ~100 CTAs must all become resident, and a gather that is already running (6,000 short
+            // CTAs on a low-priority stream) keeps back-filling every slot that frees up (measured: the solve then starts
+            // ~0.17 ms late, when the gather is done).  So the fork is only RECORDED here; the gather itself is launched
+            // right after the solver, and fills what the solver leaves free.
+            defer_gather = gather_at == 0 && !h->have_user_alpha && h->use_topk && h->persist_rb > 0;
+            if (gather_at == 0) {
+                if (defer_gather) for_shards([&](Shard& s) { RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream)); });
+                else fork_gather();
+            }
             {
                 std::vector<double*> b;
                 for (auto& s : h->shards) b.push_back(s.G.p);
@@ -694,6 +703,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 }
                 h->launches += 1;
                 h->eig_solver_used = 3;
+                if (defer_gather) { fork_gather(false); defer_gather = false; }
                 rec(E_EIG);
                 rec(E_BCAST);
             } else {

@@ -4,10 +4,12 @@
 
 PARITY UNPINNED: the reference ships no golden vectors and R is not installed in the build container, so
 these files pin the *restatement*, not an R session.  Every matrix is stored exactly as R would hold it --
-raw little-endian float64, column-major -- next to a JSON sidecar with dim/dimnames, so a real R session can
-replay the same bytes later:
+raw little-endian float64, column-major -- next to a JSON sidecar with dim/dimnames (for the Python tests) and a
+base-R-readable sidecar (<case>.manifest.tsv, <case>.sample_names.txt, <case>.replicate_names.txt,
+<case>.ctl_index_1based.txt), so that ONE command in an R session that has the reference installed settles the pin:
 
-    con <- file("mid.assay.bin", "rb"); x <- matrix(readBin(con, "double", n = prod(dim), endian = "little"), dim[1], dim[2])
+    Rscript tests/golden/replay.R            # replays every fixture through the reference's own ruvIII / fastruvIII /
+                                             # ruvIIIMultipleK and exits non-zero above 1e-9 (rel. Frobenius)
 """
 import json
 import os
@@ -79,8 +81,28 @@ def main():
             Lc = O.ruvIII_literal(counts, c["sample_names"], c["replicate_data"], c["replicate_names"], c["ctl"],
                                   c["k"], apply_log=True, pseudo_count=1.0)
             meta["dims"]["ruvIII.log.newY"] = put(case, "ruvIII.log.newY", Lc["newY"])
+        # eta != NULL (ruv::RUV1 pre-step, ruvIII.R:116): a gene-wise covariate, intercept added by design.matrix
+        if case == "mid":
+            n = c["assay"].shape[0]
+            eta = np.cos(np.arange(n) * 0.37)[None, :] + 0.1 * np.arange(n)[None, :] / n
+            meta["dims"]["eta"] = put(case, "eta", eta.T)              # n x 1, the orientation R users pass
+            Le = O.ruvIII_literal(c["assay"], c["sample_names"], c["replicate_data"], c["replicate_names"], c["ctl"],
+                                  c["k"], apply_log=False, eta=eta, include_intercept=True)
+            meta["dims"]["ruvIII.eta.newY"] = put(case, "ruvIII.eta.newY", Le["newY"])
         with open(os.path.join(HERE, "%s.json" % case), "w") as f:
             json.dump(meta, f, indent=1)
+        # base-R-readable sidecars for replay.R
+        with open(os.path.join(HERE, "%s.manifest.tsv" % case), "w") as f:
+            f.write("name\tnrow\tncol\n")
+            for name, dim in meta["dims"].items():
+                f.write("%s\t%d\t%d\n" % (name, dim[0], dim[1]))
+            f.write("k\t%d\t0\n" % meta["k"])
+            for kv in meta["ks_multi"]:
+                f.write("k_multi\t%d\t0\n" % kv)
+        for key, vals in (("sample_names", meta["sample_names"]), ("replicate_names", meta["replicate_names"]),
+                          ("ctl_index_1based", [i + 1 for i in meta["ctl_index_0based"]])):
+            with open(os.path.join(HERE, "%s.%s.txt" % (case, key)), "w") as f:
+                f.write("\n".join(str(v) for v in vals) + "\n")
         print(case, {k: v for k, v in meta["dims"].items()})
 
 

@@ -131,4 +131,12 @@ def test_persistent_matches_multikernel_solver():
             os.environ.pop("RUVIII_EIG_PERSIST", None)
     assert np.allclose(outs[0][1], outs[1][1], rtol=1e-12)
     assert O.rel_frob(outs[0][0], outs[1][0]) < 1e-11
-    assert O.rel_frob(outs[0][2], outs[1][2]) < 1e-8          # same deterministic sign convention
+    # deterministic sign convention of both forms: the largest-magnitude component of every eigenvector is positive
+    bad = {}
+    for which, (_, ev, fa) in zip(("persistent", "multi-kernel"), outs):
+        Uh = (Z @ fa.T) / ev[None, :]
+        top = Uh[np.abs(Uh).argmax(axis=0), np.arange(K)]
+        if not np.all(top > 0):
+            bad[which] = np.nonzero(top <= 0)[0].tolist()
+    assert not bad, "sign convention violated for columns %s" % bad
+    assert O.rel_frob(outs[0][2], outs[1][2]) < 1e-8

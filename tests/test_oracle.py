@@ -147,3 +147,87 @@ def test_apply_log_and_average_rep(prob):
     avg = O.ruvIII_literal(prob.assay, prob.sample_names, prob.replicate_data, prob.replicate_names, prob.ctl, 2,
                            apply_log=False, apply_average_rep=True)
     assert avg["newY"].shape[0] == 150 + 11                              # one row per column of M (ruvIII.R:149)
+
+
+# ---- the second, independent oracle (oracle/ruviii_oracle2.py): different numerical routes, no shared arithmetic ----------
+
+def _o2():
+    from oracle import ruviii_oracle2 as O2
+    return O2
+
+
+@pytest.mark.parametrize("shape", [dict(m1=60, n=300, groups=7, rep=3, n_ctl=40, k=4, seed=3),
+                                   dict(m1=150, n=700, groups=11, rep=3, n_ctl=80, k=5, seed=7),
+                                   dict(m1=90, n=400, groups=20, rep=2, n_ctl=60, k=9, seed=11)])
+def test_independent_oracle_agrees_with_the_restatement(shape):
+    """QR-projection residop, gesvd of Y0 itself, least-squares W and RUV1 (oracle2) against the R-statement transcription
+    with dgesdd / explicit inverses (oracle): newY, W alpha (sign-free), fullalpha rows after sign alignment."""
+    O2 = _o2()
+    p = make_problem(**shape)
+    k = shape["k"]
+    a = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, k, apply_log=False)
+    b = O2.ruvIII(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, k, apply_log=False)
+    assert O.rel_frob(b["newY"], a["newY"]) < 1e-10
+    assert b["fullalpha"].shape == a["fullalpha"].shape
+    assert O.rel_frob(O.align_rows_sign(b["fullalpha"][:k], a["fullalpha"][:k]), a["fullalpha"][:k]) < 1e-8
+    assert O.rel_frob(b["W"] @ b["fullalpha"][:k], a["W"] @ a["fullalpha"][:k]) < 1e-10
+    fa = O.fastruvIII_literal(p.assay, p.replicate_data, p.replicate_names, p.ctl, k, apply_log=False)
+    fb = O2.fastruvIII(p.assay, p.replicate_data, p.replicate_names, p.ctl, k, apply_log=False)
+    assert O.rel_frob(fb["newY"], fa["newY"]) < 1e-10
+    assert O.rel_frob(O.align_rows_sign(fb["fullalpha"], fa["fullalpha"]), fa["fullalpha"]) < 1e-8
+
+
+def test_independent_oracle_options(golden_mid):
+    """apply.log, apply.average.rep, eta (RUV1 with the intercept rule of design.matrix), index-vector ctl."""
+    O2 = _o2()
+    g = golden_mid
+    m = g["meta"]
+    k = m["k"]
+    args = (m["sample_names"], g["replicate_data"], m["replicate_names"])
+    b = O2.ruvIII(g["counts"], *args, g["ctl"], k, apply_log=True, pseudo_count=1.0)
+    assert O.rel_frob(b["newY"], g["ruvIII.log.newY"]) < 1e-10
+    b = O2.ruvIII(g["assay"], *args, np.asarray(m["ctl_index_0based"]), k, apply_log=False)          # tological()
+    assert O.rel_frob(b["newY"], g["ruvIII.newY"]) < 1e-10
+    eta = g["eta"]                                                                                   # n x 1, as R passes it
+    b = O2.ruvIII(g["assay"], *args, g["ctl"], k, apply_log=False, eta=eta, include_intercept=True)
+    assert O.rel_frob(b["newY"], g["ruvIII.eta.newY"]) < 1e-10
+    a = O.ruvIII_literal(g["assay"], *args, g["ctl"], k, apply_log=False, apply_average_rep=True)
+    b = O2.ruvIII(g["assay"], *args, g["ctl"], k, apply_log=False, apply_average_rep=True)
+    assert O.rel_frob(b["newY"], a["newY"]) < 1e-10
+    # an eta that already spans the constant vector gets no second intercept (design.matrix), a scalar means intercept only
+    n = g["assay"].shape[0]
+    eta2 = np.vstack([np.full(n, 3.0), np.sin(np.arange(n))])
+    a = O.ruvIII_literal(g["assay"], *args, g["ctl"], k, apply_log=False, eta=eta2)
+    b = O2.ruvIII(g["assay"], *args, g["ctl"], k, apply_log=False, eta=eta2)
+    assert O.rel_frob(b["newY"], a["newY"]) < 1e-10
+    assert O.design_matrix_t(eta2, n).shape[0] == 2 and O.design_matrix_t(1.0, n).shape == (1, n)
+    assert O.design_matrix_t(np.sin(np.arange(n)), n).shape[0] == 2
+
+
+def test_every_golden_fixture_reproduces_under_both_oracles(golden_tiny, golden_mid):
+    O2 = _o2()
+    for g in (golden_tiny, golden_mid):
+        m = g["meta"]
+        args = (g["assay"], m["sample_names"], g["replicate_data"], m["replicate_names"], g["ctl"])
+        for fn in (lambda k: O.ruvIII_literal(*args, k, apply_log=False), lambda k: O2.ruvIII(*args, k, apply_log=False)):
+            assert O.rel_frob(fn(m["k"])["newY"], g["ruvIII.newY"]) < 1e-10
+            for k in m["ks_multi"]:
+                assert O.rel_frob(fn(k)["newY"], g["ruvIIIMultipleK.k%d.newY" % k]) < 1e-10
+        f2 = O2.fastruvIII(g["assay"], g["replicate_data"], m["replicate_names"], g["ctl"], m["k"], apply_log=False)
+        assert O.rel_frob(f2["newY"], g["fastruvIII.newY"]) < 1e-10
+
+
+def test_replay_script_covers_every_fixture():
+    """tests/golden/replay.R is the one-command R pin: it must read every stored output named in the manifests."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    script = open(os.path.join(here, "replay.R")).read()
+    for case in ("tiny", "mid"):
+        names = [ln.split("\t")[0] for ln in open(os.path.join(here, case + ".manifest.tsv")).read().splitlines()[1:]]
+        for name in names:
+            if name in ("k", "k_multi"):
+                continue
+            key = "ruvIIIMultipleK.k" if name.startswith("ruvIIIMultipleK.k") else name
+            assert ('"%s' % key) in script, "replay.R never reads %s.%s.bin" % (case, name)
+        for side in ("sample_names", "replicate_names", "ctl_index_1based"):
+            assert os.path.exists(os.path.join(here, "%s.%s.txt" % (case, side)))
