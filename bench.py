@@ -40,7 +40,11 @@ def parse():
                          "2,000 PRPS sets (the PRPS-shaped large-sample case of SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--probes", action="store_true", help="also measure copy / cuBLAS Dgemm / DMMA ceilings")
+    ap.add_argument("--probes", action="store_true", help="also measure copy variants / PCIe / allreduce ceilings (the cuBLAS Dgemm "
+                                                          "and DMMA-issue FP64 ceilings are always measured: they cost < 1 s)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 (k = 1..20) and C5 (60,000 x 20,000) legs appended to a C3 run")
+    ap.add_argument("--ref-full", action="store_true", help="--impl reference: the literal algorithm at the FULL size of the workload "
+                                                            "(C3: one 12,200 x 12,200 dgesdd, minutes) instead of the bounded sample")
     return ap.parse_args()
 
 
@@ -138,14 +142,14 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def reference_sample(workload):
-    """Bounded sample of the workload for the CPU arm: same generator, same gene count, about a tenth of the
+def reference_sample(workload, full=False):
+    """Bounded sample of the workload for the CPU arm: same generator, same gene count, about a quarter of the
     samples and PRPS sets.  The literal algorithm costs O(m^3), so cells/s at this size OVERSTATES what the
-    reference would reach at the full size (it flatters the CPU, not us)."""
+    reference would reach at the full size (it flatters the CPU, not us).  full = True: the whole workload."""
     from ruviii_b200.synth import make_config, make_problem
     if workload == "tiny":
         return make_problem(m1=300, n=2000, groups=20, rep=3, n_ctl=150, k=5, seed=98), "tiny/2"
-    scale = 3000.0 / 11000.0 if workload in ("C3", "C4") else 1.0     # ~10-20 s of literal CPU work per k
+    scale = 3000.0 / 11000.0 if workload in ("C3", "C4") and not full else 1.0     # ~10-20 s of literal CPU work per k
     p = make_config("C3" if workload == "C4" else workload, scale_rows=scale)
     return p, "%s generator at %d samples x %d genes, %d PRPS rows (rows scaled x%.3f), literal per-k loop" % (
         workload, p.meta["m1"], p.meta["n"], p.meta["n_ps"], scale)
@@ -166,23 +170,26 @@ def main():
         if rank != 0:
             return 0
         use_all_host_threads()
-        sample, desc = reference_sample(args.workload)
+        sample, desc = reference_sample(args.workload, full=args.ref_full)
         ks = list(range(1, 21)) if args.workload == "C4" else [sample.k]
         if args.workload == "C4":
             ks = ks[:2]
             desc += "; 2 of the 20 k values timed (each k is an independent full ruvIII in the reference)"
-        for _ in range(max(0, min(args.warmup, 1))):
+        n_warm = 0 if args.ref_full else max(0, min(args.warmup, 1))      # a literal pass takes 10-20 s: at most one untimed pass
+        for _ in range(n_warm):
             cpu_reference_run(sample, ks)
-        vals, times = [], []
+        times = []
         for _ in range(args.steps):
             v, dt = cpu_reference_run(sample, ks)
-            vals.append(v)
             times.append(dt)
         v = sample.meta["m1"] * sample.meta["n"] * len(ks) * len(times) / sum(times)
+        same = bool(args.ref_full or sample.meta["m1"] == 11000 or args.workload not in ("C3", "C4"))
         line = {"impl": "reference", "metric": "RUVIII cells/s", "value": v, "unit": "cells/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                "steps": args.steps, "warmup": n_warm, "warmup_requested": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "sample": desc},
+                "config": {"workload": args.workload, "sample": desc, "same_config_as_gpu_arm": same,
+                           "note": None if same else "bounded sample (rows scaled): the literal algorithm is O(m^3), so the CPU figure at "
+                                                     "this size is an UPPER bound on what it reaches at the full size"},
                 "cpu_baseline": {"value": v, "unit": "cells/s", "cores": blas_threads(), "kind": "port", "sample": desc,
                                  "note": "numpy/OpenBLAS literal restatement of ruvIII.R:93-146 (R is not installed); "
                                          "stock R often links a single-threaded BLAS and would be slower"},
@@ -246,88 +253,170 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def resident_leg(ks_, warmup, steps, sample_clocks):
+        """plan + upload once, then `warmup` + `steps` full passes over the resident assay (device time, max over ranks)."""
+        eng.plan(prm, m1, n_loc, n_ps, groups, ctl_loc, ks_)
+        eng.upload(Y_h, PS_h)
+        for _ in range(warmup):
+            eng.run()
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        barrier()
+        torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
+        eng.barrier()      # device-side: the host barrier releases ranks milliseconds apart, which is several passes
+        if world > 1:
+            # Alignment pass (one more untimed warm-up): ranks still leave the barrier up to ~9 ms apart on the host side
+            # (measured, r01m6), and the early rank would book that wait as "allreduce time" of its first timed pass.  Every
+            # pass ends right after a collective, so after this one all ranks enter the timed loop within microseconds.
+            eng.run()
+        stage, dev, marks, per_step = {}, 0.0, [], []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            info = eng.run()
+            marks.append((info.host_t_enter, info.host_t_done, time.monotonic()))
+            dev += info.ms_total
+            per_step.append(info.ms_total)
+            for name, _ in info._fields_:
+                if name.startswith("ms_"):
+                    stage[name] = stage.get(name, 0.0) + getattr(info, name)
+        torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
+        barrier()
+        t1 = time.perf_counter()
+        clocks = sampler.stop(t0, t1) if sampler else None
+        return dict(info=info, clocks=clocks, wall_ms=max_over_ranks((t1 - t0) * 1e3 / steps), dev_ms=max_over_ranks(dev / steps),
+                    stage_ms={k: v / steps for k, v in stage.items()}, marks=marks, per_step=per_step)
+
+    def e2e_leg(ks_, Yb, PSb, outb, n_warm, n_timed):
+        for _ in range(n_warm):
+            eng.normalise_oneshot(prm, Yb, PSb, groups, ctl_loc, ks_, outb)
+        barrier()
+        eng.barrier()
+        te0 = time.perf_counter()
+        for _ in range(n_timed):
+            eng.normalise_oneshot(prm, Yb, PSb, groups, ctl_loc, ks_, outb)
+        barrier()
+        return max_over_ranks((time.perf_counter() - te0) / n_timed), int(eng._info.pipelined)
+
+    def parity_vs_oracle(ks_, out_blocks, n_rows=192):
+        """Relative Frobenius error of `n_rows` random sample rows of every requested k against the structural restatement of
+        ruvIII.R:116-146 (oracle/, the checker), over this rank's genes; combined over the ranks.  Outside any timed region."""
+        from oracle import ruviii_oracle as O
+        rows = np.sort(np.random.default_rng(12345).choice(m1, size=min(n_rows, m1), replace=False))
+        ref, lam, _ = O.ruvIII_structural_rows(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, ks_, rows,
+                                               apply_log=False)
+        num = den = 0.0
+        worst = 0.0
+        for i, k in enumerate(ks_):
+            d = out_blocks[i][rows] - ref[k][:, g0:g1]
+            nu, de = float(np.sum(d * d)), float(np.sum(ref[k][:, g0:g1] ** 2))
+            num += nu
+            den += de
+            worst = max(worst, nu / max(de, 1e-300))
+        tot = sum_over_ranks([num, den])
+        return {"rel_frob": float(np.sqrt(tot[0] / max(tot[1], 1e-300))), "worst_k_rel_frob_this_rank": float(np.sqrt(worst)),
+                "rows": int(rows.size), "ks": len(ks_), "against": "oracle.ruvIII_structural_rows (numpy restatement of "
+                "ruvIII.R:116-146; parity unpinned against R, see DESIGN.md)", "tolerance": 1e-9}
+
     # ---- device-resident leg: plan + upload once, then W + K full passes -------------------------------------
-    eng.plan(prm, m1, n_loc, n_ps, groups, ctl_loc, ks)
-    eng.upload(Y_h, PS_h)
-    for _ in range(args.warmup):
-        eng.run()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
-    eng.barrier()      # device-side: the host barrier releases ranks milliseconds apart, which is several passes
-    stage_ms = {}
-    dev_ms = 0.0
-    host_marks = []
-    step_ms = []
-    if world > 1:
-        # Alignment pass (one more untimed warm-up): ranks still leave the barrier up to ~9 ms apart on the host side
-        # (measured, r01m6), and the early rank would book that wait as "allreduce time" of its first timed pass.  Every
-        # pass ends right after a collective, so after this one all ranks enter the timed loop within microseconds.
-        eng.run()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        info = eng.run()
-        host_marks.append((info.host_t_enter, info.host_t_done, time.monotonic()))
-        dev_ms += info.ms_total
-        step_ms.append(info.ms_total)
-        for name, _ in info._fields_:
-            if name.startswith("ms_"):
-                stage_ms[name] = stage_ms.get(name, 0.0) + getattr(info, name)
-    torch.cuda.synchronize(local_rank) if torch.cuda.is_available() else None
-    barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler else None
-    wall_ms = max_over_ranks((t1 - t0) * 1e3 / args.steps)
-    dev_ms = max_over_ranks(dev_ms / args.steps)
-    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    leg = resident_leg(ks, args.warmup, args.steps, True)
+    info, clocks, wall_ms, dev_ms, stage_ms, step_ms = leg["info"], leg["clocks"], leg["wall_ms"], leg["dev_ms"], leg["stage_ms"], leg["per_step"]
     stage_ms_per_rank = None
     if world > 1:                                   # every rank's view of the stages (skew shows up as allreduce time)
         gathered = [None] * world
         mine = {k: round(v, 4) for k, v in stage_ms.items() if v > 0.002}
-        base = host_marks[0][0]
-        mine["host_marks_ms"] = [[round((a - base) * 1e3, 3), round((b - base) * 1e3, 3), round((c - base) * 1e3, 3)] for a, b, c in host_marks[:6]]
+        base = leg["marks"][0][0]
+        mine["host_marks_ms"] = [[round((a - base) * 1e3, 3), round((b - base) * 1e3, 3), round((c - base) * 1e3, 3)] for a, b, c in leg["marks"][:6]]
         mine["host_base"] = base
         dist.all_gather_object(gathered, mine)
         stage_ms_per_rank = gathered
     launches = info.kernel_launches * args.steps
     cells = float(m1) * n * len(ks)
     value = cells / (dev_ms * 1e-3)
+    # parity of the resident result (every N: each rank checks its own gene slab)
+    parity = None
+    if not sliced:
+        eng.download(out=out_h)
+        parity = parity_vs_oracle(ks, out_h)
 
     allreduce_us = None
     if args.probes and world > 1:            # every rank takes part
         allreduce_us = {"%d KiB" % kb: round(eng.probe(5, kb), 1) for kb in (8, 128, 1500, 5000, 20000)}
 
-    # ---- end-to-end leg: ruviii_normalise, pinned host in / pinned host out -----------------------------------
-    e2e = None
+    # ---- end-to-end legs: ruviii_normalise, host in / host out, copies inside the timed region -----------------
+    e2e = e2e_pageable = None
     if not args.no_e2e:
-        for _ in range(min(args.warmup, 2)):
-            eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
-        barrier()
-        eng.barrier()
-        te0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
-        for _ in range(n_e2e):
-            eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, out_h)
-        barrier()
-        te = max_over_ranks((time.perf_counter() - te0) / n_e2e)
+        te, pipelined = e2e_leg(ks, Y_h, PS_h, out_h, min(args.warmup, 2), n_e2e)
         # the overlapped one-shot path must return exactly what upload -> run -> download returns (same kernels, same order):
         # recompute this rank's shard through the sequential path and compare bit for bit
-        pipelined = int(eng._info.pipelined)
         check = None
+        ref_h = None
         if pipelined:
-            ref_h = pinned((len(ks), m1, n_loc))
+            ref_h = np.empty((len(ks), m1, n_loc))
             os.environ["RUVIII_PIPELINE"] = "2"
             try:
                 eng.normalise_oneshot(prm, Y_h, PS_h, groups, ctl_loc, ks, ref_h)
             finally:
                 os.environ.pop("RUVIII_PIPELINE", None)
             check = bool(np.array_equal(ref_h, out_h))
-            del ref_h
         e2e = {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3, "bit_identical_to_sequential_path": check,
                "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world,
                "d2h_bytes_per_step": int(out_h.nbytes) * world, "steps": n_e2e,
                "api": "ruviii_normalise (C ABI) with pinned host buffers, copies inside the timed region",
                "pipelined": pipelined}
+        # the same call on PAGEABLE buffers (what an R session owns: REALSXPs cannot be page-locked): through the engine's
+        # pinned bounce buffers, filled and drained by its pool of host threads
+        Y_pg, PS_pg, out_pg = np.array(Y_h), np.array(PS_h), np.empty((len(ks), m1, n_loc))
+        out_pg[...] = 0.0                     # touch the pages once: R's allocator hands over touched memory after the first call
+        tp, pipelined_pg = e2e_leg(ks, Y_pg, PS_pg, out_pg, min(args.warmup, 2), n_e2e)
+        e2e_pageable = {"value": cells / tp, "unit": "cells/s", "ms_per_step": tp * 1e3, "vs_pinned": tp / te,
+                        "bit_identical_to_sequential_path": bool(np.array_equal(out_pg, ref_h)) if ref_h is not None else None,
+                        "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world, "d2h_bytes_per_step": int(out_h.nbytes) * world,
+                        "steps": n_e2e, "pipelined": pipelined_pg, "host_threads": os.environ.get("RUVIII_HOST_THREADS", "auto (<= 16)"),
+                        "api": "ruviii_normalise (C ABI) with PAGEABLE host buffers (numpy heap), copies inside the timed region"}
+        del Y_pg, PS_pg, out_pg, ref_h
+
+    # ---- extra legs (C3 runs only): BASELINE configs 4 and 5 in the same JSON line ------------------------------
+    extras = {}
+    if args.workload == "C3" and not args.no_extra:
+        peaks_x, _ = measured_peaks()
+        hbm_x = float(peaks_x.get("hbm_gbs", 6650.0))
+        # C4: ruvIIIMultipleK, k = 1..20 on the same data (ruvIIIMultipleK.R:75-94): one Gram / eigensolve, 20 streamed outputs
+        try:
+            ks4 = list(range(1, 21))
+            leg4 = resident_leg(ks4, 2, 3, False)
+            out4 = np.empty((len(ks4), m1, n_loc))
+            out4[...] = 0.0
+            t4, pl4 = e2e_leg(ks4, np.array(Y_h), np.array(PS_h), out4, 1, 2)
+            par4 = parity_vs_oracle(ks4, out4, n_rows=64)
+            b4 = 8.0 * m1 * n_loc * (1 + len(ks4))
+            cells4 = float(m1) * n * len(ks4)
+            extras["C4"] = {
+                "workload": "C4: C3 data, k = 1..20 in one call (ruvIIIMultipleK semantics)", "ms_per_step": leg4["dev_ms"],
+                "value": cells4 / (leg4["dev_ms"] * 1e-3), "unit": "cells/s", "steps": 3, "warmup": 2,
+                "stage_ms": {k: round(v, 4) for k, v in leg4["stage_ms"].items() if v > 0.002},
+                "roofline": {"kernel": "update_smem_kernel (K6, 21 streams)", "bound": "hbm", "algorithmic_bytes_per_launch": b4,
+                             "achieved": b4 / (leg4["stage_ms"]["ms_update"] * 1e-3) / 1e9, "peak": hbm_x, "unit": "GB/s",
+                             "frac": b4 / (leg4["stage_ms"]["ms_update"] * 1e-3) / 1e9 / hbm_x, "traffic": None},
+                "e2e": {"value": cells4 / t4, "unit": "cells/s", "ms_per_step": t4 * 1e3, "pipelined": pl4, "steps": 2,
+                        "h2d_bytes_per_step": int(Y_h.nbytes + PS_h.nbytes) * world, "d2h_bytes_per_step": int(out4.nbytes) * world,
+                        "api": "ruviii_normalise with PAGEABLE buffers (35 GB of outputs at N = 1)"},
+                "parity": par4, "eig_iterations": leg4["info"].eig_iterations,
+                "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration"}.get(leg4["info"].eig_solver)}
+            del out4
+        except Exception as e:       # the headline must survive a failing extra leg
+            extras["C4"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        # C5: 60,000 x 20,000 dense replicate design (20,000 groups of 3): gene-side Gram, 20,000^2 eigensolve
+        try:
+            extras["C5"] = extra_c5(eng, rank, world, local_rank, pinned, barrier, max_over_ranks, sum_over_ranks, hbm_x)
+        except Exception as e:
+            extras["C5"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
         eng.close()
@@ -347,38 +436,46 @@ def main():
         gram_flops = float(R) * (R + 1) * helm / world
     else:                                                            # Z t(Z): order = Helmert rows, contraction = this rank's genes
         gram_flops = float(R) * (R + 1) * n_loc                      # symmetric half, FMA = 2 flop
+    # FP64 ceilings measured on this very GPU in this very run (MEASURED_PEAKS.json holds no FP64 figure): cuBLAS Dgemm
+    # 8192^3 and a pure DMMA issue loop; the Gram is quoted against the measured Dgemm, the nominal 40 TFLOP/s beside it
+    dgemm_tf = eng.probe(1, 8192)
+    dmma_tf = eng.probe(2, 0)
     kernels = {
         "update": {"bound": "hbm", "ms": stage_ms["ms_update"], "achieved": upd_bytes / (stage_ms["ms_update"] * 1e-3) / 1e9,
                    "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": upd_bytes},
         "residop": {"bound": "hbm", "ms": stage_ms["ms_residop"], "achieved": res_bytes / max(stage_ms["ms_residop"], 1e-6) / 1e6,
                     "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes": res_bytes},
         "gram": {"bound": "fp64-tensor", "ms": stage_ms["ms_gram"], "achieved": gram_flops / max(stage_ms["ms_gram"], 1e-6) / 1e9,
-                 "peak": 40.0, "unit": "TFLOP/s", "algorithmic_flops": gram_flops,
-                 "peak_note": "nominal B200 FP64 (DMMA) 40 TFLOP/s; MEASURED_PEAKS.json holds no FP64 figure"},
+                 "peak": dgemm_tf, "unit": "TFLOP/s", "algorithmic_flops": gram_flops,
+                 "peak_note": "measured in this run: cuBLAS Dgemm 8192^3 (%.1f TFLOP/s); pure DMMA issue loop %.1f; nominal B200 FP64 "
+                              "40" % (dgemm_tf, dmma_tf)},
     }
     for kinfo in kernels.values():
         kinfo["frac"] = kinfo["achieved"] / kinfo["peak"]
-    traffic = None
+    kernels["gram"]["frac_of_nominal_40"] = kernels["gram"]["achieved"] / 40.0
+    kernels["gram"]["frac_of_dmma_issue"] = kernels["gram"]["achieved"] / dmma_tf
+    for kinfo in (kernels["update"], kernels["residop"]):
+        kinfo["frac_of_nominal_8000"] = kinfo["achieved"] / 8000.0
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("update_kernel_dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic, traffic_src = tj.get("update_kernel_dram_bytes_per_launch"), tj.get("source")
     except Exception:
         pass
     up = kernels["update"]
     roofline = {"kernel": "update_smem_kernel (K6, ruvIII.R:145)", "bound": "hbm", "achieved": up["achieved"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": up["frac"], "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": up["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": upd_bytes,
                 "share_of_step": stage_ms["ms_update"] / max(stage_ms["ms_total"], 1e-9)}
 
-    probes = None
+    probes = {"cublas_dgemm_tflops_8192": dgemm_tf, "dmma_issue_tflops": dmma_tf}
     if args.probes and world == 1:
-        probes = {"copy_gbs": eng.probe(0, 2048), "cublas_dgemm_tflops_8192": eng.probe(1, 8192),
-                  "dmma_issue_tflops": eng.probe(2, 0), "host_gather_11000x1000_ms": eng.probe(3, 1000),
-                  "pcie_duplex_gbs_1GiB_each_way": eng.probe(6, 1024),
-                  "copy_variants_gbs": dict(zip(["linear", "tiled_r4_plain", "tiled_r4_hint", "tiled_r8_hint", "tiled_r4_hint_16rows",
-                                                 "tiled_r4_hint_1600rows", "tiled_r16_hint", "tiled_r2_plain"],
-                                                [round(eng.probe(4, i), 1) for i in range(8)]))}
-        kernels["gram"]["frac_of_cublas_dgemm"] = kernels["gram"]["achieved"] / probes["cublas_dgemm_tflops_8192"]
+        probes.update({"copy_gbs": eng.probe(0, 2048), "host_gather_11000x1000_ms": eng.probe(3, 1000),
+                       "pcie_duplex_gbs_1GiB_each_way": eng.probe(6, 1024),
+                       "copy_variants_gbs": dict(zip(["linear", "tiled_r4_plain", "tiled_r4_hint", "tiled_r8_hint", "tiled_r4_hint_16rows",
+                                                      "tiled_r4_hint_1600rows", "tiled_r16_hint", "tiled_r2_plain"],
+                                                     [round(eng.probe(4, i), 1) for i in range(8)]))})
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -406,15 +503,112 @@ def main():
                    "eig_second_cholqr_rounds": info.eig_chol2,
                    "gram_impl": int(os.environ.get("RUVIII_GRAM_IMPL", "1")), "gram_order": info.gram_order,
                    "update_impl": int(os.environ.get("RUVIII_UPD_IMPL", "3"))},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "clocks": clocks, "parity": parity, "parity_rel_frob": None if parity is None else parity["rel_frob"],
+        "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "probes": probes, "nccl_allreduce_us": allreduce_us,
-        "stage_ms_per_rank": stage_ms_per_rank,
+        "stage_ms_per_rank": stage_ms_per_rank, "configs": extras or None,
     }
     print(json.dumps(line))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def extra_c5(eng, rank, world, local_rank, pinned, barrier, max_over_ranks, sum_over_ranks, hbm_peak):
+    """BASELINE config 5: 60,000 samples x 20,000 genes in 20,000 replicate groups of 3 (dense design, no PRPS rows), k = 10:
+    the residual has rank 40,000 > n, so the Gram is taken on the gene side (20,000^2), over several ranks by the row re-split.
+    Parity here is property-based (the full oracle would need a 40,000-row SVD): (i) the rows of alpha the engine returns are
+    eigen-directions of t(Y0) Y0 -- residual || t(Y0) Y0 a_j - lambda_j a_j || / lambda_1 with Y0 the group-mean residual
+    recomputed in numpy on this rank's gene slab and summed over the ranks; (ii) given that alpha, sample rows of newY equal
+    Y - W alpha with W = Ystand_c ac' (ac ac')^-1 recomputed in numpy (ruvIII.R:144-145)."""
+    import torch
+    from ruviii_b200 import _cabi
+    from ruviii_b200.synth import make_dense_design
+    m, n, k = 60000, 20000, 10
+    g0, g1 = n * rank // world, n * (rank + 1) // world
+    n_loc = g1 - g0
+    Y, gid, ctl = make_dense_design(m=m, n=n, group_size=3, n_ctl=1000, k=k, cols=(g0, g1))
+    Y_h = pinned((m, n_loc))
+    Y_h[...] = Y
+    del Y
+    out_h = pinned((1, m, n_loc))
+    PS_h = np.zeros((0, n_loc))
+    prm = _cabi.make_params(mode=_cabi.MODE_STACKED, apply_log=False)
+    eng.plan(prm, m, n_loc, 0, gid, ctl, [k])
+    eng.upload(Y_h, PS_h)
+    eng.run()
+    barrier()
+    eng.barrier()
+    if world > 1:
+        eng.run()
+    steps, dev, stage = 2, 0.0, {}
+    for _ in range(steps):
+        info = eng.run()
+        dev += info.ms_total
+        for name, _ in info._fields_:
+            if name.startswith("ms_"):
+                stage[name] = stage.get(name, 0.0) + getattr(info, name) / steps
+    dev_ms = max_over_ranks(dev / steps)
+    res = eng.download(want_fullalpha=True, out=out_h)
+    alpha = res["fullalpha"][:k]                                   # k x n_loc
+    # ---- (i) eigen-residual of alpha' against t(Y0) Y0 (all ranks together) ----
+    Yv = Y_h.reshape(m // 3, 3, n_loc)
+    Y0 = (Yv - Yv.mean(axis=1, keepdims=True)).reshape(m, n_loc)   # residop with a one-hot M (fastruvIII.R:88-95)
+    t = Y0 @ alpha.T                                               # m x k, partial over the genes of this rank
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.from_numpy(np.ascontiguousarray(t))
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        t = tt.numpy()
+    lam = np.array(sum_over_ranks(np.sum(alpha * alpha, axis=1)))  # ||sigma v'||^2 = sigma^2 = lambda
+    r = Y0.T @ t - alpha.T * lam[None, :]                          # n_loc x k
+    del Y0
+    rn = np.sqrt(np.array(sum_over_ranks(np.sum(r * r, axis=0))))
+    eig_resid = float(np.max(rn / (lam[0] * np.sqrt(lam))))        # ||G a - lambda a|| / (lambda_1 ||a||)
+    # ---- (ii) newY rows from alpha by the R formula ----
+    rows = np.sort(np.random.default_rng(777).choice(m, size=128, replace=False))
+    ac = alpha[:, ctl]
+    A = Y_h[:, ctl] @ ac.T
+    parts = sum_over_ranks(list(A.ravel()) + list((ac @ ac.T).ravel())) if world > 1 else None
+    if parts is not None:
+        A = np.array(parts[:m * k]).reshape(m, k)
+        Gm = np.array(parts[m * k:]).reshape(k, k)
+    else:
+        Gm = ac @ ac.T
+    A = A - A.mean(axis=0, keepdims=True)
+    W = np.linalg.solve(Gm, A.T).T
+    ref_rows = Y_h[rows] - W[rows] @ alpha
+    d = out_h[0][rows] - ref_rows
+    tot = sum_over_ranks([float(np.sum(d * d)), float(np.sum(ref_rows ** 2))])
+    rows_rel = float(np.sqrt(tot[0] / tot[1]))
+    # ---- end to end (sequential path: the gene-side regime needs the whole matrix before anything can be written) ----
+    eng.normalise_oneshot(prm, Y_h, PS_h, gid, ctl, [k], out_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        eng.normalise_oneshot(prm, Y_h, PS_h, gid, ctl, [k], out_h)
+    barrier()
+    te = max_over_ranks((time.perf_counter() - t0) / 2)
+    cells = float(m) * n
+    gram_flops = float(n) * (n + 1) * (m - m // 3) / world
+    upd_bytes = 16.0 * m * n_loc
+    return {"workload": "C5: 60,000 samples x 20,000 genes, 20,000 replicate groups of 3, 1,000 control genes, k=10, gene-side Gram, "
+                        "genes sharded over %d GPU(s)" % world,
+            "ms_per_step": dev_ms, "value": cells / (dev_ms * 1e-3), "unit": "cells/s", "steps": steps, "warmup": 1,
+            "stage_ms": {kk: round(v, 3) for kk, v in stage.items() if v > 0.002},
+            "eigensolver": {1: "cuSOLVER syevd", 2: "cuSOLVER syevdx", 3: "block subspace iteration"}.get(info.eig_solver),
+            "eig_iterations": info.eig_iterations, "gram_order": info.gram_order, "gram_side": info.gram_side,
+            "roofline": {"kernel": "gram_dmma_kernel (K2, gene side: all-to-all + transpose + Gram in ms_gram)", "bound": "fp64-tensor",
+                         "algorithmic_flops_per_gpu": gram_flops, "achieved": gram_flops / (stage["ms_gram"] * 1e-3) / 1e12,
+                         "peak": 40.0, "unit": "TFLOP/s", "frac": gram_flops / (stage["ms_gram"] * 1e-3) / 1e12 / 40.0,
+                         "peak_note": "nominal B200 FP64; the measured Dgemm ceiling is in probes"},
+            "update": {"achieved": upd_bytes / (stage["ms_update"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": upd_bytes / (stage["ms_update"] * 1e-3) / 1e9 / hbm_peak},
+            "e2e": {"value": cells / te, "unit": "cells/s", "ms_per_step": te * 1e3, "steps": 2, "h2d_bytes_per_step": int(Y_h.nbytes) * world,
+                    "d2h_bytes_per_step": int(out_h.nbytes) * world, "api": "ruviii_normalise, pinned buffers, sequential path"},
+            "parity": {"eigenpair_residual_rel": eig_resid, "newY_rows_rel_frob_given_alpha": rows_rel, "rows": 128,
+                       "kind": "property-based (see extra_c5 docstring): no 40,000-row oracle SVD at this size", "tolerance": 1e-9}}
 
 
 if __name__ == "__main__":

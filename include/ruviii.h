@@ -83,7 +83,8 @@ typedef struct ruviii_info {
     int32_t eig_solver;                /* 0 none, 1 cuSOLVER syevd, 2 cuSOLVER syevdx, 3 block subspace iteration   */
     int32_t eig_iterations;            /* subspace-iteration passes (solver 3); 0 otherwise                        */
     int32_t gram_order;                /* order of the Gram actually formed: active_rows - #non-singleton groups    */
-    int32_t pipelined;                 /* 1 when ruviii_normalise overlapped upload, compute and download (pinned buffers) */
+    int32_t pipelined;                 /* ruviii_normalise overlapped upload, compute and download: 0 no, 1 zero-copy pipeline (pinned),
+                                        * 2 staged path on pinned buffers, 3 staged path through pinned bounce buffers (pageable) */
     double host_t_enter, host_t_done;  /* CLOCK_MONOTONIC seconds at ruviii_run entry and when its last stream drained */
     float ms_gather;                   /* control-gene gather on its own stream (overlaps the eigensolve; not part of the sum) */
     int32_t eig_rr;                    /* solver 3, persistent form: Rayleigh-Ritz steps                                      */
@@ -136,6 +137,16 @@ int ruviii_normalise(ruviii_handle* h, const ruviii_params* params,
                      const int32_t* ks, int32_t nk,
                      double* newY_out, double* newY_ps_out,
                      double* fullalpha_out, double* W_out, ruviii_info* info);
+
+/* Same call with one output pointer PER k (block i = newY for ks[i], m1 x n, row stride n): what the R shim uses, so that
+ * every RUV_K<k> assay is written straight into its own R-allocated matrix (no intermediate nk x m1 x n buffer). */
+int ruviii_normalise_blocks(ruviii_handle* h, const ruviii_params* params,
+                            const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                            const double* PS, int64_t ldPS, int32_t n_ps,
+                            const int32_t* group_of_row, const uint8_t* ctl,
+                            const int32_t* ks, int32_t nk,
+                            double* const* newY_blocks, double* newY_ps_out,
+                            double* fullalpha_out, double* W_out, ruviii_info* info);
 
 /* ---- resident API: plan once, keep Y on the device, run many times ------------------------------------- */
 
@@ -222,9 +233,10 @@ int ruviii_mat_subtract(ruviii_handle* h, const double* A, const double* B, int6
 int ruviii_mat_transpose(ruviii_handle* h, const double* A, int32_t m, int32_t n, double* out /* n x m */);
 int ruviii_mat_inverse(ruviii_handle* h, const double* A, int32_t n, double* out /* n x n */);
 
-/* Page-locked host memory.  ruviii_normalise overlaps upload, compute and download only when Y and newY_out are
- * page-locked (these helpers, cudaHostAlloc or cudaHostRegister); with pageable buffers it copies, computes and
- * copies back in sequence.  Returns NULL when no CUDA device is present. */
+/* Page-locked host memory.  ruviii_normalise overlaps upload, compute and download for pageable and page-locked buffers
+ * alike (pageable ones go through pinned bounce buffers filled by a pool of host threads, RUVIII_HOST_THREADS); with
+ * page-locked Y / newY_out (these helpers, cudaHostAlloc or cudaHostRegister) the DMA engines use the caller's memory
+ * directly.  Returns NULL when no CUDA device is present. */
 void* ruviii_host_alloc(size_t bytes);
 void  ruviii_host_free(void* p);
 

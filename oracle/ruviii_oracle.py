@@ -368,3 +368,46 @@ def ruvIIIMultipleK_structural(assay, sample_names, replicate_data, replicate_na
         W, newY = _w_newy(Y, Y.shape[0], alpha, ctlb)
         out[k] = dict(newY=newY, fullalpha=base["fullalpha"], W=W, m1=base["m1"])
     return out
+
+
+def ruvIII_structural_rows(assay, sample_names, replicate_data, replicate_names, ctl, ks, rows,
+                           apply_log=True, pseudo_count=1.0):
+    """``newY[rows, ]`` (sample rows only) for every k in ``ks`` -- the arithmetic of :func:`ruvIIIMultipleK_structural`
+    without materialising any m x n result, so that a full-size run (11,000 x 20,000, k = 1..20) can be spot-checked in
+    seconds: one decomposition of the residual of the replicated rows, then per k
+    ``W = Ystand_c ac' (ac ac')^-1`` (ruvIII.R:144) over ALL m rows and ``newY[rows] = Y[rows] - W[rows] alpha`` (:145).
+    Returns ``(dict k -> len(rows) x n, eigenvalues, fullalpha[:max(ks)])``."""
+    expr = _log_assay(assay, apply_log, pseudo_count)
+    Ys = expr.T
+    PS = np.asarray(replicate_data, dtype=np.float64)
+    m1, n = Ys.shape
+    m = m1 + PS.shape[0]
+    gid = group_ids_from_names(list(sample_names) + list(replicate_names))
+    ctl = tological(ctl, n)
+    p = int(gid.max()) + 1
+    cnt = np.bincount(gid, minlength=p)
+    act = np.nonzero(cnt[gid] > 1)[0]
+    rows = np.asarray(rows)
+    ks = [int(k) for k in ks]
+    kmax = max(ks)
+    out = {}
+    if p >= m or kmax == 0 or act.size == 0:
+        return {k: np.array(Ys[rows]) for k in ks}, None, None
+    Ya = np.vstack([Ys[act[act < m1]], PS[act[act >= m1] - m1]])
+    ga = np.unique(gid[act], return_inverse=True)[1]
+    order, Y0a, _ = _group_mean_residual(Ya, ga)
+    r = min(m - p, int(ctl.sum()))
+    Ua, lam = _top_left_vectors(Y0a, min(r, kmax))
+    fullalpha = Ua.T @ Ya[order]
+    Yc = np.vstack([Ys[:, ctl], PS[:, ctl]])
+    for k in ks:
+        if k == 0:
+            out[k] = np.array(Ys[rows])
+            continue
+        alpha = fullalpha[:min(k, fullalpha.shape[0])]
+        ac = alpha[:, ctl]
+        A = Yc @ ac.T
+        A = A - A.mean(axis=0, keepdims=True)
+        W = np.linalg.solve(ac @ ac.T, A.T).T
+        out[k] = Ys[rows] - W[rows] @ alpha
+    return out, lam, fullalpha

@@ -1,8 +1,11 @@
 /*
  * .Call shim between the RUVIIIPRPS R package and libruviii_b200.so (include/ruviii.h).
  *
- * COMPILE-UNTESTED: the build container has no R (no Rinternals.h, no libR.so), so this file has never been
- * compiled.  It is deliberately free of logic: argument unpacking, one C-ABI call, result packing.
+ * NOT COMPILED AGAINST R IN THE BUILD CONTAINER (no R there: no Rinternals.h, no libR.so).  It IS compiled and run against
+ * a small mock of the R C API (tests/mock_r/: SEXPs on malloc) by tests/test_shim.py -- on the CPU to catch syntax / ABI
+ * drift, on the GPU box end to end against the Python binding -- so the argument unpacking, the layouts and the result
+ * packing below are exercised; what remains unverified is the real R runtime (PROTECT discipline, R_alloc lifetimes).
+ * The file is deliberately free of logic: argument unpacking, one C-ABI call, result packing.
  *
  * Naming follows the package's own (dangling) Rcpp boundary, R/RcppExports.R:4-26:
  *     .Call('_RUVIIIPRPS_<fn>', PACKAGE = 'RUVIIIPRPS', ...)
@@ -12,6 +15,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <stdlib.h>
 #include <string.h>
 #include "ruviii.h"
 
@@ -35,7 +39,9 @@ static ruviii_handle* engine(void) {
  *   ctl         logical n (after tological())                                         -- ruvIII.R:102
  *   k           integer vector (ruvIIIMultipleK's k)
  * returns list(newY = list of n x m1 matrices (one per k; exactly the new assay t(newY[1:m1, ])),
- *              fullalpha = n x r (R side applies t()), W = list of k x m_w (R side applies t()), info) */
+ *              fullalpha = n x r (R side applies t()), W = numeric, blocks of k x m_w (R side applies t()), r)
+ * ONE engine call (ruviii_normalise_blocks): every newY block is written by the engine straight into its own R matrix --
+ * from R's pageable heap through the engine's pinned bounce buffers, upload / update / download overlapped. */
 SEXP _RUVIIIPRPS_ruvIIICore(SEXP assay, SEXP tRep, SEXP groupId, SEXP ctl, SEXP k, SEXP mode, SEXP applyLog,
                             SEXP pseudoCount, SEXP returnInfo) {
     const int n = Rf_nrows(assay), m1 = Rf_ncols(assay), n_ps = Rf_ncols(tRep), nk = LENGTH(k);
@@ -48,43 +54,54 @@ SEXP _RUVIIIPRPS_ruvIIICore(SEXP assay, SEXP tRep, SEXP groupId, SEXP ctl, SEXP 
     prm.pseudo_count = Rf_asReal(pseudoCount);
     prm.n_alpha_rows = (info_wanted && prm.mode == RUVIII_MODE_STACKED) ? -1 : 0;
     unsigned char* ctl8 = (unsigned char*)R_alloc(n, 1);
-    for (int i = 0; i < n; ++i) ctl8[i] = LOGICAL(ctl)[i] == TRUE;
-    int* gid = (int*)R_alloc(LENGTH(groupId), sizeof(int));
-    for (int i = 0; i < LENGTH(groupId); ++i) gid[i] = INTEGER(groupId)[i] - 1;
-
-    ruviii_handle* h = engine();
-    if (ruviii_plan(h, &prm, m1, n, n_ps, gid, ctl8, INTEGER(k), nk) != RUVIII_OK ||
-        ruviii_upload(h, REAL(assay), n, REAL(tRep), n) != RUVIII_OK)
-        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
-    ruviii_info info;
-    if (ruviii_run(h, &info) != RUVIII_OK) Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
-
-    /* outputs are allocated by R and filled in place; the engine writes nk blocks back to back, so the
-       download goes through one contiguous REALSXP that is then split without copying the first block */
-    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
-    SEXP big = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nk * n * m1));
+    int n_ctl = 0;
+    for (int i = 0; i < n; ++i) { ctl8[i] = LOGICAL(ctl)[i] == TRUE; n_ctl += ctl8[i]; }
+    const int n_gid = LENGTH(groupId);
+    int* gid = (int*)R_alloc(n_gid > 0 ? n_gid : 1, sizeof(int));
+    int p = 0;                                    /* ncol(M): factor codes are dense 1..p */
+    for (int i = 0; i < n_gid; ++i) { gid[i] = INTEGER(groupId)[i] - 1; if (INTEGER(groupId)[i] > p) p = INTEGER(groupId)[i]; }
+    /* output sizes follow from the plan's own formulas (ruvIII.R:128-129,140,142): r = min(m - ncol(M), sum(ctl)) */
+    const int m_for_M = prm.mode == RUVIII_MODE_FAST ? n_ps : m1 + n_ps;
     const int m_w = prm.mode == RUVIII_MODE_FAST ? m1 : m1 + n_ps;
+    const int no_rep = p >= m_for_M;
+    int r = m_for_M - p;
+    if (prm.mode == RUVIII_MODE_STACKED && n_ctl < r) r = n_ctl;
+    if (r < 0) r = 0;
+    int kmax = 0;
+    for (int i = 0; i < nk; ++i) if (INTEGER(k)[i] > kmax) kmax = INTEGER(k)[i];
+    const int kmax_eff = kmax < r ? kmax : r;
+    const int have_info = info_wanted && !no_rep && kmax_eff > 0;
     R_xlen_t w_len = 0;
-    for (int i = 0; i < nk; ++i) w_len += (R_xlen_t)m_w * (INTEGER(k)[i] < info.r ? INTEGER(k)[i] : info.r);
-    const int fa_rows = prm.n_alpha_rows < 0 ? info.r : info.kmax_eff;
-    SEXP fa = PROTECT(Rf_allocMatrix(REALSXP, n, (info_wanted && !info.no_replicates) ? fa_rows : 0));
-    SEXP W = PROTECT(Rf_allocVector(REALSXP, (info_wanted && !info.no_replicates) ? w_len : 0));
-    if (ruviii_download(h, REAL(big), NULL, LENGTH(fa) ? REAL(fa) : NULL, LENGTH(W) ? REAL(W) : NULL) != RUVIII_OK) {
+    for (int i = 0; i < nk; ++i) w_len += (R_xlen_t)m_w * (INTEGER(k)[i] < r ? INTEGER(k)[i] : r);
+    const int fa_rows = prm.n_alpha_rows < 0 ? r : kmax_eff;
+
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SEXP newY = PROTECT(Rf_allocVector(VECSXP, nk));
+    double** blocks = (double**)R_alloc(nk > 0 ? nk : 1, sizeof(double*));
+    for (int i = 0; i < nk; ++i) {
+        SEXP mat = PROTECT(Rf_allocMatrix(REALSXP, n, m1));
+        SET_VECTOR_ELT(newY, i, mat);
+        UNPROTECT(1);                              /* held by newY from here on */
+        blocks[i] = REAL(mat);
+    }
+    SEXP fa = PROTECT(Rf_allocMatrix(REALSXP, n, have_info ? fa_rows : 0));
+    SEXP W = PROTECT(Rf_allocVector(REALSXP, have_info ? w_len : 0));
+    ruviii_handle* h = engine();
+    ruviii_info info;
+    if (ruviii_normalise_blocks(h, &prm, REAL(assay), n, m1, n, REAL(tRep), n, n_ps, gid, ctl8, INTEGER(k), nk, blocks, NULL,
+                                have_info ? REAL(fa) : NULL, have_info ? REAL(W) : NULL, &info) != RUVIII_OK) {
         UNPROTECT(4);
         Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
     }
-    SEXP newY = PROTECT(Rf_allocVector(VECSXP, nk));
-    for (int i = 0; i < nk; ++i) {
-        SEXP mat = PROTECT(Rf_allocMatrix(REALSXP, n, m1));
-        memcpy(REAL(mat), REAL(big) + (R_xlen_t)i * n * m1, sizeof(double) * (size_t)n * m1);
-        SET_VECTOR_ELT(newY, i, mat);
-        UNPROTECT(1);
+    if (info.r != r || info.no_replicates != no_rep) {
+        UNPROTECT(4);
+        Rf_error("RUVIIIPRPS: internal error, the engine planned r = %d where the shim expected %d", info.r, r);
     }
     SET_VECTOR_ELT(out, 0, newY);
     SET_VECTOR_ELT(out, 1, fa);
     SET_VECTOR_ELT(out, 2, W);
     SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(info.r));
-    UNPROTECT(5);
+    UNPROTECT(4);
     return out;
 }
 
@@ -110,6 +127,51 @@ SEXP _RUVIIIPRPS_fastResidop(SEXP A, SEXP B) {
     return out;
 }
 SEXP _RUVIIIPRPS_fastResidop2(SEXP A, SEXP B) { return _RUVIIIPRPS_fastResidop(A, B); }
+
+/* RcppExports.R:12-26  the four generic primitives (never called by the package; provided for completeness) */
+SEXP _RUVIIIPRPS_matrixMult(SEXP A, SEXP B) {
+    const int m = Rf_nrows(A), kk = Rf_ncols(A), n = Rf_ncols(B);
+    if (Rf_nrows(B) != kk) Rf_error("non-conformable arguments");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, n));
+    if (ruviii_mat_mult(engine(), REAL(A), m, kk, REAL(B), n, REAL(out)) != RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(g_handle));
+    }
+    UNPROTECT(1);
+    return out;
+}
+SEXP _RUVIIIPRPS_matSubtraction(SEXP A, SEXP B) {
+    const int m = Rf_nrows(A), n = Rf_ncols(A);
+    if (Rf_nrows(B) != m || Rf_ncols(B) != n) Rf_error("non-conformable arrays");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, n));
+    if (ruviii_mat_subtract(engine(), REAL(A), REAL(B), (int64_t)m * n, REAL(out)) != RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(g_handle));
+    }
+    UNPROTECT(1);
+    return out;
+}
+SEXP _RUVIIIPRPS_matTranspose(SEXP A) {
+    const int m = Rf_nrows(A), n = Rf_ncols(A);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, m));
+    if (ruviii_mat_transpose(engine(), REAL(A), m, n, REAL(out)) != RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(g_handle));
+    }
+    UNPROTECT(1);
+    return out;
+}
+SEXP _RUVIIIPRPS_matInverse(SEXP A) {
+    const int n = Rf_nrows(A);
+    if (Rf_ncols(A) != n) Rf_error("'a' must be a square matrix");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    if (ruviii_mat_inverse(engine(), REAL(A), n, REAL(out)) != RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(g_handle));
+    }
+    UNPROTECT(1);
+    return out;
+}
 
 /* ruvIII.R:116 / fastruvIII.R:133-134  RUV1(Y, eta, ctl): tEta = t(design.matrix(eta, include.intercept)) is q x n in R, whose
  * column-major bytes are n x q row-major -- the engine wants q x n row-major, i.e. the bytes of the n x q design matrix
@@ -159,13 +221,41 @@ SEXP _RUVIIIPRPS_fastPCA(SEXP assay, SEXP k, SEXP applyLog, SEXP pseudoCount, SE
     return out;
 }
 
+/* supervisedFindNCG.R:179-191,214-229: per-gene one-way ANOVA F (matrixTests::row_oneway_equalvar(...)$statistic) and / or
+ * Pearson correlation (Rfast::correls(..., type = "pearson")) of every gene with one variable.
+ *   groups     integer m1 (0-based level per sample, < 0 = sample left out) or NULL
+ *   covariate  numeric m1 or NULL
+ * returns list(F = numeric n or NULL, r = numeric n or NULL) */
+SEXP _RUVIIIPRPS_geneStats(SEXP assay, SEXP groups, SEXP covariate, SEXP applyLog, SEXP pseudoCount) {
+    const int n = Rf_nrows(assay), m1 = Rf_ncols(assay);
+    const int has_g = !Rf_isNull(groups), has_c = !Rf_isNull(covariate);
+    if ((has_g && LENGTH(groups) != m1) || (has_c && LENGTH(covariate) != m1)) Rf_error("one entry per sample is needed");
+    ruviii_handle* h = engine();
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP F = PROTECT(has_g ? Rf_allocVector(REALSXP, n) : R_NilValue), r = PROTECT(has_c ? Rf_allocVector(REALSXP, n) : R_NilValue);
+    if (ruviii_gene_stats(h, REAL(assay), n, m1, n, -1, Rf_asLogical(applyLog), Rf_asReal(pseudoCount), has_g ? INTEGER(groups) : NULL,
+                          has_c ? REAL(covariate) : NULL, has_g ? REAL(F) : NULL, has_c ? REAL(r) : NULL, NULL) != RUVIII_OK) {
+        UNPROTECT(3);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    }
+    SET_VECTOR_ELT(out, 0, F);
+    SET_VECTOR_ELT(out, 1, r);
+    UNPROTECT(3);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"_RUVIIIPRPS_ruvIIICore", (DL_FUNC)&_RUVIIIPRPS_ruvIIICore, 9},
     {"_RUVIIIPRPS_fastResidop", (DL_FUNC)&_RUVIIIPRPS_fastResidop, 2},
     {"_RUVIIIPRPS_fastResidop2", (DL_FUNC)&_RUVIIIPRPS_fastResidop2, 2},
+    {"_RUVIIIPRPS_matrixMult", (DL_FUNC)&_RUVIIIPRPS_matrixMult, 2},
+    {"_RUVIIIPRPS_matSubtraction", (DL_FUNC)&_RUVIIIPRPS_matSubtraction, 2},
+    {"_RUVIIIPRPS_matTranspose", (DL_FUNC)&_RUVIIIPRPS_matTranspose, 1},
+    {"_RUVIIIPRPS_matInverse", (DL_FUNC)&_RUVIIIPRPS_matInverse, 1},
     {"_RUVIIIPRPS_setEta", (DL_FUNC)&_RUVIIIPRPS_setEta, 1},
     {"_RUVIIIPRPS_prpsMeans", (DL_FUNC)&_RUVIIIPRPS_prpsMeans, 5},
     {"_RUVIIIPRPS_fastPCA", (DL_FUNC)&_RUVIIIPRPS_fastPCA, 6},
+    {"_RUVIIIPRPS_geneStats", (DL_FUNC)&_RUVIIIPRPS_geneStats, 5},
     {NULL, NULL, 0}};
 
 void R_init_RUVIIIPRPS(DllInfo* dll) {

@@ -19,7 +19,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 # every symbol include/ruviii.h declares (tests/test_cabi.py checks the header against this list and the .so)
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
-    "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_plan", "ruviii_upload", "ruviii_run",
+    "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_normalise_blocks", "ruviii_plan", "ruviii_upload", "ruviii_run",
     "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats",
     "ruviii_fast_residop", "ruviii_probe", "ruviii_mat_mult", "ruviii_mat_subtract", "ruviii_mat_transpose", "ruviii_mat_inverse",
 ]
@@ -82,6 +82,8 @@ def load_library():
     lib.ruviii_last_error.restype = C.c_char_p
     lib.ruviii_normalise.argtypes = [H, C.POINTER(Params), vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int64,
                                      C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.POINTER(Info)]
+    lib.ruviii_normalise_blocks.argtypes = [H, C.POINTER(Params), vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int64,
+                                            C.c_int32, vp, vp, vp, C.c_int32, C.POINTER(C.c_void_p), vp, vp, vp, C.POINTER(Info)]
     lib.ruviii_plan.argtypes = [H, C.POINTER(Params), C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32]
     lib.ruviii_upload.argtypes = [H, vp, C.c_int64, vp, C.c_int64]
     lib.ruviii_run.argtypes = [H, C.POINTER(Info)]
@@ -405,6 +407,22 @@ class Engine:
             self._h, C.byref(params), _ptr(Y), Y.strides[0] // 8, Y.shape[0], Y.shape[1], _ptr(PS),
             PS.strides[0] // 8, PS.shape[0], _ptr(group_of_row), _ptr(ctl_u8), _ptr(ks_arr), ks_arr.shape[0],
             _ptr(out), None, None, None, C.byref(info)))
+        self._info = info
+        return info
+
+    def normalise_blocks(self, params, Y, PS, group_of_row, ctl, ks, outs):
+        """ruviii_normalise_blocks: one separately allocated m1 x n output per k (what the R shim hands over)."""
+        Y = _rowmajor(Y, "Y")
+        PS = _rowmajor(PS, "PS")
+        group_of_row = np.ascontiguousarray(group_of_row, dtype=np.int32)
+        ctl_u8 = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
+        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        info = Info()
+        self._check(self._lib.ruviii_normalise_blocks(
+            self._h, C.byref(params), _ptr(Y), Y.strides[0] // 8, Y.shape[0], Y.shape[1], _ptr(PS),
+            PS.strides[0] // 8, PS.shape[0], _ptr(group_of_row), _ptr(ctl_u8), _ptr(ks_arr), ks_arr.shape[0],
+            ptrs, None, None, None, C.byref(info)))
         self._info = info
         return info
 

@@ -53,6 +53,7 @@ ruviii_handle::~ruviii_handle() {
         if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
         for (auto e : s.ev_chunk) cudaEventDestroy(e);
         for (auto e : s.ev_upd) cudaEventDestroy(e);
+        for (auto e : s.ev_d2h) cudaEventDestroy(e);
     }
     if (!shards.empty()) cudaSetDevice(shards[0].device);
     solver_work.release();
@@ -61,6 +62,7 @@ ruviii_handle::~ruviii_handle() {
     if (blas) cublasDestroy(blas);
     if (h_flags) cudaFreeHost(h_flags);
     if (h_dflag) cudaFreeHost(h_dflag);
+    if (stage) ruviii::stage_state_destroy(stage);
 }
 
 namespace ruviii {
@@ -312,6 +314,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         for (int g = 0; g < s.n; ++g)
             if (ctl[s.g0 + g]) cidx.push_back(g);
         s.n_ctl = (int)cidx.size();
+        s.ctl_idx_host = cidx;
         s.Y.alloc((size_t)std::max(m1, 1) * s.ld);
         s.PS.alloc((size_t)std::max(n_ps, 1) * s.ld);
         s.out.alloc((size_t)nk * std::max(m1, 1) * s.ld, false);
@@ -912,7 +915,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     if (info_out) *info_out = I;
 }
 
-void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W) {
+void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W, double* const* newY_blocks) {
     if (!h->ran) throw Error(RUVIII_ERR_STATE, "ruviii_download before ruviii_run");
     const bool fast = h->prm.mode == RUVIII_MODE_FAST;
     const bool skip = h->no_replicates || h->kk == 0;
@@ -921,9 +924,9 @@ void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullal
     for (auto& s : h->shards) {
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
-        if (newY && h->m1 > 0)
+        if ((newY || newY_blocks) && h->m1 > 0)
             for (int i = 0; i < nk; ++i)
-                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(newY + (size_t)i * h->m1 * n + s.g0, n * 8,
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync((newY_blocks ? newY_blocks[i] : newY + (size_t)i * h->m1 * n) + s.g0, n * 8,
                                                     s.out.p + (size_t)i * h->m1 * s.ld, s.ld * 8, (size_t)s.n * 8, h->m1,
                                                     cudaMemcpyDeviceToHost, s.stream));
         if (newY_ps) {
@@ -1129,29 +1132,56 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
     });
 }
 
-int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
-                     const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
-                     const int32_t* ks, int32_t nk, double* newY_out, double* newY_ps_out, double* fullalpha_out,
-                     double* W_out, ruviii_info* info) {
+// RUVIII_PIPELINE: 0 / 1 = auto (staged path when eligible), 2 = never overlap (upload -> run -> download in sequence),
+// 3 = the round-1 pipeline with the zero-copy control-gene gather (needs pinned buffers)
+static int normalise_any(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                         const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
+                         const int32_t* ks, int32_t nk, double* newY_out, double* const* newY_blocks, double* newY_ps_out,
+                         double* fullalpha_out, double* W_out, ruviii_info* info) {
     if (!h) return RUVIII_ERR_INVALID;
     return guarded(h, [&] {
-        if (!newY_out) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
+        if (!newY_out && !newY_blocks) throw Error(RUVIII_ERR_INVALID, "newY_out is NULL");
         const auto tp0 = std::chrono::steady_clock::now();
         do_plan(h, params, m1, n, n_ps, group_of_row, ctl, ks, nk);
         if (env_int("RUVIII_PIPE_TRACE", 0))
             fprintf(stderr, "[pipe trace] plan=%.2f ms\n",
                     1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
         h->pipelined_last = 0;
-        if (can_pipeline(h, Y, PS, newY_out, newY_ps_out)) {
-            if ((m1 > 0 && ldY < n) || (n_ps > 0 && (!PS || ldPS < n))) throw Error(RUVIII_ERR_INVALID, "row stride < n");
+        const int mode = env_int("RUVIII_PIPELINE", env_int("RUVIII_NO_PIPELINE", 0) ? 2 : 0);
+        std::vector<double*> blocks(nk);
+        for (int i = 0; i < nk; ++i) {
+            blocks[i] = newY_blocks ? newY_blocks[i] : newY_out + (size_t)i * m1 * n;
+            if (!blocks[i]) throw Error(RUVIII_ERR_INVALID, "a newY block is NULL");
+        }
+        if ((m1 > 0 && ldY < n) || (n_ps > 0 && PS && ldPS < n)) throw Error(RUVIII_ERR_INVALID, "row stride < n");
+        if (mode != 2 && mode != 3 && can_stage(h, PS, newY_ps_out)) {
+            do_normalise_staged(h, Y, ldY, PS, ldPS, blocks.data(), fullalpha_out, W_out);
+        } else if (mode == 3 && !newY_blocks && can_pipeline(h, Y, PS, newY_out, newY_ps_out)) {
             do_normalise_pipelined(h, Y, ldY, PS, ldPS, newY_out, fullalpha_out, W_out);
         } else {
             do_upload(h, Y, ldY, PS, ldPS);
             do_run(h, nullptr);
-            do_download(h, newY_out, newY_ps_out, fullalpha_out, W_out);
+            do_download(h, nullptr, newY_ps_out, fullalpha_out, W_out, blocks.data());
         }
         if (info) *info = h->info;
     });
+}
+
+int ruviii_normalise(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                     const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
+                     const int32_t* ks, int32_t nk, double* newY_out, double* newY_ps_out, double* fullalpha_out,
+                     double* W_out, ruviii_info* info) {
+    return normalise_any(h, params, Y, ldY, m1, n, PS, ldPS, n_ps, group_of_row, ctl, ks, nk, newY_out, nullptr, newY_ps_out,
+                         fullalpha_out, W_out, info);
+}
+
+int ruviii_normalise_blocks(ruviii_handle* h, const ruviii_params* params, const double* Y, int64_t ldY, int32_t m1, int32_t n,
+                            const double* PS, int64_t ldPS, int32_t n_ps, const int32_t* group_of_row, const uint8_t* ctl,
+                            const int32_t* ks, int32_t nk, double* const* newY_blocks, double* newY_ps_out, double* fullalpha_out,
+                            double* W_out, ruviii_info* info) {
+    if (!newY_blocks) return RUVIII_ERR_INVALID;
+    return normalise_any(h, params, Y, ldY, m1, n, PS, ldPS, n_ps, group_of_row, ctl, ks, nk, nullptr, newY_blocks, newY_ps_out,
+                         fullalpha_out, W_out, info);
 }
 
 void* ruviii_host_alloc(size_t bytes) {

@@ -128,13 +128,17 @@ struct DevBuf {
     }
 };
 
+struct StageState;
+void stage_state_destroy(StageState* st);
+
 struct Shard {
     int device = 0;
     int g0 = 0, n = 0;            // first gene (in the caller's matrix) and gene count of this shard
     int64_t ld = 0;               // device row pitch (doubles) of every genes-contiguous matrix
     int n_ctl = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
-    std::vector<cudaEvent_t> ev_chunk, ev_upd;   // pipelined host path: chunk uploaded / chunk updated
+    std::vector<cudaEvent_t> ev_chunk, ev_upd, ev_d2h;   // host-to-host paths: chunk uploaded / updated / downloaded
+    std::vector<int> ctl_idx_host;               // this shard's control-gene columns (local indices), host copy
     ncclComm_t comm = nullptr;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_fork = nullptr, ev_gather = nullptr;   // main -> aux stream fork, aux -> main join (control-gene gather)
@@ -221,6 +225,7 @@ struct ruviii_handle {
     int prps_n = 0;
     bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
     double eig_tol = 1e-13;
+    ruviii::StageState* stage = nullptr;   // pool of host threads + pinned bounce buffers of the staged host path
 
     ~ruviii_handle();
 };
@@ -239,11 +244,15 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS);
 void eigensolve(ruviii_handle* h, bool allow_subspace = true);
 void do_run(ruviii_handle* h, ruviii_info* info_out);
-void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W);
+void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W, double* const* newY_blocks = nullptr);
 // engine_pipeline.cu
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out);
 void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* newY_out,
                             double* fullalpha_out, double* W_out);
+// engine_stage.cu
+bool can_stage(ruviii_handle* h, const double* PS, const double* newY_ps_out);
+void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* const* out_blocks,
+                         double* fullalpha_out, double* W_out);
 // engine_aux.cu
 void apply_ruv1(ruviii_handle* h);
 void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,

@@ -23,9 +23,8 @@ const void* host_pinned(const void* p) {
 
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out) {
     if (h->n_ps > 0 && !PS) return false;      // replicate.data is built on the device from the whole assay
-    // RUVIII_PIPELINE: 0 / 1 = pipeline whenever eligible, 2 = never (upload -> run -> download in sequence)
-    const int mode = env_int("RUVIII_PIPELINE", env_int("RUVIII_NO_PIPELINE", 0) ? 2 : 0);
-    const bool off = mode == 2;
+    // selected by RUVIII_PIPELINE=3 (engine.cu normalise_any); eligibility only here
+    const bool off = false;
     const bool skip = h->no_replicates || h->kk == 0;
     return !off && !skip && h->eta_q == 0 && !h->gene_side && h->active_all_ps && !h->prm.average_rep && h->n_alpha_rows == h->kk &&
            h->m1 >= 256 && newY_ps_out == nullptr && host_pinned(Y) != nullptr && host_pinned(newY_out) != nullptr;

@@ -372,9 +372,9 @@ def test_tma_kernel_variants_match(env):
 @pytest.mark.parametrize("apply_log", [False, True], ids=["log2_input", "counts_apply_log"])
 @pytest.mark.parametrize("zc_pct", ["", "0", "40", "100"])
 def test_pipelined_host_path_matches_sequential(engine, apply_log, zc_pct, monkeypatch):
-    """ruviii_normalise with page-locked buffers overlaps upload / compute / download (control columns gathered on the
-    device for the leading row chunks and by zero-copy for the trailing ones, chunked update); whatever the split, it
-    must return exactly what the sequential upload -> run -> download path returns."""
+    """RUVIII_PIPELINE=3: the round-1 pipeline on page-locked buffers (control columns gathered on the device for the
+    leading row chunks and by zero-copy for the trailing ones, chunked update); whatever the split, it must return exactly
+    what the sequential upload -> run -> download path returns."""
     if zc_pct:
         monkeypatch.setenv("RUVIII_ZC_PCT", zc_pct)
     p = make_problem(m1=700, n=3001, groups=60, rep=3, n_ctl=200, k=7, seed=20, counts=apply_log)
@@ -386,6 +386,7 @@ def test_pipelined_host_path_matches_sequential(engine, apply_log, zc_pct, monke
     Yp, outp = _cabi.PinnedArray((700, 3001)), _cabi.PinnedArray((3, 700, 3001))
     Yp.array[...] = p.Y
     outp.array[...] = -1.0
+    monkeypatch.setenv("RUVIII_PIPELINE", "3")
     info = engine.normalise_oneshot(prm, Yp.array, p.replicate_data, groups, p.ctl, ks, outp.array)
     assert info.pipelined == 1
     for i in range(3):
@@ -393,6 +394,49 @@ def test_pipelined_host_path_matches_sequential(engine, apply_log, zc_pct, monke
     ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 7, apply_log=apply_log,
                            pseudo_count=1.0)
     assert O.rel_frob(outp.array[2], ref["newY"][:700]) < TOL_NEWY
+
+
+@pytest.mark.parametrize("apply_log", [False, True], ids=["log2_input", "counts_apply_log"])
+@pytest.mark.parametrize("threads", ["1", "5"])
+@pytest.mark.parametrize("m1", [700, 2500])
+def test_staged_host_path_matches_sequential(engine, apply_log, threads, m1, monkeypatch):
+    """The default one-shot path (ruviii_normalise / ruviii_normalise_blocks): control columns copied out by host threads,
+    assay streamed through in row chunks -- from PAGEABLE memory through the pinned bounce buffers (what R hands over),
+    from pinned memory directly, and with one separately allocated output per k.  Bit-identical to the sequential path."""
+    monkeypatch.setenv("RUVIII_HOST_THREADS", threads)
+    n = 3001 if m1 == 700 else 20000                          # 2,500 x 20,000: several row chunks per slot
+    p = make_problem(m1=m1, n=n, groups=60, rep=3, n_ctl=200, k=7, seed=20, counts=apply_log)
+    ks = [0, 3, 7]
+    groups = api.group_codes(p.sample_names + p.replicate_names)
+    prm = _cabi.make_params(apply_log=apply_log, pseudo_count=1.0)
+    monkeypatch.setenv("RUVIII_PIPELINE", "2")
+    seq = engine.normalise(prm, p.Y, p.replicate_data, groups, p.ctl, ks)
+    seq_one = np.full((3, m1, n), -1.0)
+    info = engine.normalise_oneshot(prm, np.ascontiguousarray(p.Y), p.replicate_data, groups, p.ctl, ks, seq_one)
+    assert info.pipelined == 0 and np.array_equal(seq_one, seq["newY"])
+    monkeypatch.delenv("RUVIII_PIPELINE")
+    # pageable in, pageable out (numpy heap)
+    out = np.full((3, m1, n), -1.0)
+    info = engine.normalise_oneshot(prm, np.ascontiguousarray(p.Y), p.replicate_data, groups, p.ctl, ks, out)
+    assert info.pipelined == 3
+    assert np.array_equal(out, seq["newY"])
+    # one separately allocated matrix per k (the R shim's REALSXPs)
+    outs = [np.full((m1, n), -2.0) for _ in ks]
+    info = engine.normalise_blocks(prm, np.ascontiguousarray(p.Y), p.replicate_data, groups, p.ctl, ks, outs)
+    assert info.pipelined == 3
+    for i in range(3):
+        assert np.array_equal(outs[i], seq["newY"][i])
+    # pinned in, pinned out: no bounce buffers
+    Yp, outp = _cabi.PinnedArray((m1, n)), _cabi.PinnedArray((3, m1, n))
+    Yp.array[...] = p.Y
+    outp.array[...] = -1.0
+    info = engine.normalise_oneshot(prm, Yp.array, p.replicate_data, groups, p.ctl, ks, outp.array)
+    assert info.pipelined == 2
+    assert np.array_equal(outp.array, seq["newY"])
+    ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 7, apply_log=apply_log,
+                           pseudo_count=1.0) if m1 == 700 else O.ruvIII_structural(
+        p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 7, apply_log=apply_log, pseudo_count=1.0)
+    assert O.rel_frob(out[2], ref["newY"][:m1]) < TOL_NEWY
 
 
 def test_eigensolvers_agree():

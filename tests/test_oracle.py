@@ -231,3 +231,15 @@ def test_replay_script_covers_every_fixture():
             assert ('"%s' % key) in script, "replay.R never reads %s.%s.bin" % (case, name)
         for side in ("sample_names", "replicate_names", "ctl_index_1based"):
             assert os.path.exists(os.path.join(here, "%s.%s.txt" % (case, side)))
+
+
+def test_structural_rows_matches_full_structural(prob):
+    """The row-subset form bench.py uses for its parity figure equals the full structural restatement."""
+    p = prob
+    rows = np.array([0, 3, 17, 88, 149])
+    sub, lam, fa = O.ruvIII_structural_rows(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, [0, 1, 3, 5], rows,
+                                            apply_log=False)
+    full = O.ruvIIIMultipleK_structural(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, [0, 1, 3, 5],
+                                        apply_log=False)
+    for k in (0, 1, 3, 5):
+        assert O.rel_frob(sub[k], full[k]["newY"][rows]) < 1e-12

@@ -1,0 +1,111 @@
+"""The R .Call shim (r-shim/src/shim.c) compiled and run against a mock of R's C API (tests/mock_r/).
+
+R is not installed in the build container, so the shim cannot be built with `R CMD SHLIB` here.  The mock supplies SEXPs on
+malloc and the handful of Rf_* entry points the shim uses, which is enough to (CPU) catch syntax / ABI drift between
+shim.c and include/ruviii.h and check the routine registration against R/RcppExports.R:4-26, and (GPU) run
+_RUVIIIPRPS_ruvIIICore and the matrix primitives end to end, looked up by name through the registered table as `.Call` does,
+against the Python binding and numpy.  What stays unverified is the real R runtime itself."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "shim_driver")
+    lib = os.path.join(ROOT, "ruviii_b200", "lib")
+    cmd = ["gcc", "-std=gnu11", "-Wall", "-Werror", "-Wno-cast-function-type", "-O1", "-I", os.path.join(ROOT, "tests", "mock_r"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r-shim", "src", "shim.c"),
+           os.path.join(ROOT, "tests", "mock_r", "mock_r.c"), os.path.join(ROOT, "tests", "mock_r", "shim_driver.c"),
+           "-L", lib, "-lruviii_b200", "-Wl,-rpath," + lib, "-o", out]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out
+
+
+def test_shim_compiles_and_registers_the_declared_boundary(driver):
+    """Every `.Call('_RUVIIIPRPS_<fn>')` of R/RcppExports.R:4-26 is registered with the argument count declared there, plus
+    the coarse entry points of the drop-in; R_useDynamicSymbols(dll, FALSE)."""
+    out = subprocess.run([driver, "list"], check=True, capture_output=True, text=True).stdout.split("\n")
+    reg = dict((ln.split()[0], int(ln.split()[1])) for ln in out if ln.strip())
+    legacy = {"fastResidop": 2, "fastResidop2": 2, "matrixMult": 2, "matSubtraction": 2, "matTranspose": 1, "matInverse": 1}
+    for name, nargs in legacy.items():
+        assert reg.get("_RUVIIIPRPS_" + name) == nargs
+    for name, nargs in {"ruvIIICore": 9, "setEta": 1, "prpsMeans": 5, "fastPCA": 6, "geneStats": 5}.items():
+        assert reg.get("_RUVIIIPRPS_" + name) == nargs
+    assert reg["dynamic_symbols"] == 0
+
+
+def _read_reals(f):
+    (n,) = struct.unpack("<q", f.read(8))
+    return np.frombuffer(f.read(8 * n), dtype="<f8").copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,return_info", [(0, True), (0, False), (1, True)])
+def test_shim_core_matches_python_binding(driver, tmp_path, mode, return_info):
+    import ruviii_b200 as rv
+    from oracle import ruviii_oracle as O
+    from ruviii_b200 import _cabi, api
+    from ruviii_b200.synth import make_problem
+    p = make_problem(m1=400, n=1500, groups=30, rep=3, n_ctl=120, k=6, seed=31)
+    ks = [0, 2, 6]
+    n, m1, n_ps = 1500, 400, p.replicate_data.shape[0]
+    names = list(p.replicate_names) if mode == 1 else list(p.sample_names) + list(p.replicate_names)
+    gid = api.group_codes(names).astype(np.int32) + 1                       # as.integer(factor(names)) is 1-based
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<8i", n, m1, n_ps, len(ks), mode, 0, int(return_info), gid.shape[0]))
+        f.write(struct.pack("<d", 1.0))
+        np.asfortranarray(p.assay).T.astype("<f8").tofile(f)                # n x m1 column-major = m1 x n row-major
+        np.ascontiguousarray(p.replicate_data).astype("<f8").tofile(f)      # t(replicate.data) column-major = PS row-major
+        gid.astype("<i4").tofile(f)
+        p.ctl.astype("<i4").tofile(f)
+        np.asarray(ks, dtype="<i4").tofile(f)
+    subprocess.run([driver, "core", inp, outp], check=True, capture_output=True, text=True, timeout=300)
+    with open(outp, "rb") as f:
+        newY = [_read_reals(f).reshape(m1, n) for _ in ks]                  # n x m1 column-major read back as m1 x n
+        fa = _read_reals(f)
+        W = _read_reals(f)
+        (r,) = struct.unpack("<i", f.read(4))
+    with rv.Engine(devices=[0]) as eng:
+        prm = _cabi.make_params(mode=mode, n_alpha_rows=-1 if (return_info and mode == 0) else 0)
+        ref = eng.normalise(prm, p.Y, p.replicate_data, gid - 1, p.ctl, ks, want_fullalpha=True, want_W=True)
+    assert r == ref["info"].r
+    for i in range(len(ks)):
+        assert O.rel_frob(newY[i], ref["newY"][i]) < 1e-12
+    assert np.array_equal(newY[0], p.Y)                                     # k = 0: newY = Y (ruvIII.R:134-136)
+    if return_info:
+        assert O.rel_frob(fa.reshape(-1, n), ref["fullalpha"]) < 1e-9
+        assert O.rel_frob(W, np.concatenate([w.ravel() for w in ref["W"]])) < 1e-9
+    else:
+        assert fa.size == 0 and W.size == 0
+    lit = (O.fastruvIII_literal(p.assay, p.replicate_data, p.replicate_names, p.ctl, 6, apply_log=False) if mode == 1 else
+           O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, 6, apply_log=False))
+    assert O.rel_frob(newY[2], lit["newY"][:m1]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_shim_matrix_primitives(driver, tmp_path):
+    """fastResidop / matrixMult / matSubtraction / matTranspose / matInverse (RcppExports.R:4-26) against numpy."""
+    outp = str(tmp_path / "prims.bin")
+    subprocess.run([driver, "prims", outp], check=True, capture_output=True, text=True, timeout=300)
+    with open(outp, "rb") as f:
+        A = _read_reals(f).reshape(4, 3).T          # column-major 3 x 4
+        B = _read_reals(f).reshape(2, 4).T
+        S = _read_reals(f).reshape(3, 3).T
+        mult = _read_reals(f).reshape(2, 3).T
+        sub = _read_reals(f).reshape(4, 3).T
+        tr = _read_reals(f).reshape(3, 4).T
+        inv = _read_reals(f).reshape(3, 3).T
+        res = _read_reals(f).reshape(4, 3).T
+    assert np.allclose(mult, A @ B, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(sub, np.zeros_like(A))
+    assert np.array_equal(tr, A.T)
+    assert np.allclose(inv @ S, np.eye(3), atol=1e-13)
+    M = np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    assert np.allclose(res, A - M @ np.linalg.solve(M.T @ M, M.T @ A), atol=1e-13)      # fastruvIII.R:88-95
