@@ -217,6 +217,10 @@ def main():
         numa = "cpus of GPU %d: %d" % (local_rank, len(os.sched_getaffinity(0)))
     except Exception as e:            # not fatal: the numbers are then simply those of an unbound process
         numa = "unbound (%s)" % type(e).__name__
+    # the staged host path of every rank runs its own pool of copy threads: share the cores this rank may use between the ranks
+    # of the host (one R session would have them all)
+    if world > 1:
+        os.environ.setdefault("RUVIII_HOST_THREADS", str(max(1, len(os.sched_getaffinity(0)) // world)))
     p, ks, sliced = workload_problem(args.workload, rank, world)
     m1, n, n_ps = p.meta["m1"], p.meta["n"], p.meta["n_ps"]
     g0, g1 = n * rank // world, n * (rank + 1) // world

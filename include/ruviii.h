@@ -217,6 +217,13 @@ int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1
                       double pseudo_count, const int32_t* group_of_sample, const double* covariate, double* F_out, double* r_out,
                       float* ms_out);
 
+/* Spearman's rho of every gene with a continuous variable: supervisedFindNCG.R:214-229,270-285 with corr.method = "spearman"
+ * (Rfast::correls(type = "spearman"): Pearson's r of the ranks, ties averaged).  X / slot as in ruviii_pca; a monotone transform
+ * such as log2(x + pseudo.count) does not change ranks, so there is no apply_log.  m1 <= 16384 (one gene's samples are sorted in
+ * shared memory); more is RUVIII_ERR_UNSUPPORTED. */
+int ruviii_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, const double* covariate,
+                         double* rho_out, float* ms_out);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

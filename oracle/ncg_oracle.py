@@ -33,6 +33,14 @@ def correls_pearson(y, x):
     return (xc * yc[:, None]).sum(axis=0) / np.sqrt((xc ** 2).sum(axis=0) * (yc ** 2).sum())
 
 
+def correls_spearman(y, x):
+    """Rfast::correls(y, x, type = "spearman")[, "correlation"]: Pearson's r of the average ranks (scipy.stats.rankdata, an
+    implementation independent of rank_average below)."""
+    from scipy.stats import rankdata
+    x = np.asarray(x, dtype=np.float64)
+    return correls_pearson(rankdata(np.asarray(y, dtype=np.float64)), rankdata(x, axis=0))
+
+
 def rank_average(x):
     """base::rank, ties.method = "average" (via a double argsort with tie groups averaged)."""
     x = np.asarray(x, dtype=np.float64)
@@ -42,8 +50,9 @@ def rank_average(x):
     return (0.5 * (starts + ends - 1) + 1.0)[inv]
 
 
-def supervised_find_ncg(assay, col_data, bio_variables, uv_variables, no_ncg, apply_log=True, pseudo_count=1.0):
+def supervised_find_ncg(assay, col_data, bio_variables, uv_variables, no_ncg, apply_log=True, pseudo_count=1.0, corr_method="pearson"):
     """The default-configuration flow of supervisedFindNCG.R:148-357 (see ruviii_b200/ncg.py for the two quirks)."""
+    correls_pearson = globals()["correls_spearman" if corr_method == "spearman" else "correls_pearson"]
     expr = np.log2(np.asarray(assay, dtype=np.float64) + pseudo_count) if apply_log else np.asarray(assay, dtype=np.float64)
     is_cat = lambda v: all(isinstance(t, str) for t in col_data[v])
     ranks = []

@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_normalise_blocks", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats", "ruviii_gene_spearman",
     "ruviii_fast_residop", "ruviii_probe", "ruviii_mat_mult", "ruviii_mat_subtract", "ruviii_mat_transpose", "ruviii_mat_inverse",
 ]
 
@@ -100,6 +100,7 @@ def load_library():
     lib.ruviii_prps.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, C.c_int32, vp, C.c_int64]
     lib.ruviii_set_prps_sets.argtypes = [H, vp, vp, C.c_int32]
     lib.ruviii_gene_stats.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
+    lib.ruviii_gene_spearman.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
     lib.ruviii_pca.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                C.c_int32, vp, vp, vp, vp]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
@@ -316,6 +317,21 @@ class Engine:
                                                 C.cast(C.byref(ms), C.c_void_p)))
         return dict(F=F, r=r, ms=float(ms.value))
 
+    def gene_spearman(self, X=None, covariate=None, slot=-1):
+        """K11b: Spearman's rho of every gene with ``covariate`` (supervisedFindNCG.R:214-229, corr.method = "spearman")."""
+        if X is not None:
+            X = _rowmajor(X, "X")
+            m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        else:
+            m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
+        c = np.ascontiguousarray(covariate, dtype=np.float64)
+        if c.shape[0] != m1:
+            raise RuviiiError(ERR_INVALID, "covariate needs one entry per sample")
+        rho = np.empty(n, dtype=np.float64)
+        ms = C.c_float(0.0)
+        self._check(self._lib.ruviii_gene_spearman(self._h, ptr, ldx, m1, n, int(slot), _ptr(c), _ptr(rho), C.cast(C.byref(ms), C.c_void_p)))
+        return dict(rho=rho, ms=float(ms.value))
+
     def set_prps_sets(self, sets):
         """Fused K0: the next plans with n_ps = len(sets) build replicate.data on the device when PS is None."""
         if not sets:
@@ -345,7 +361,7 @@ class Engine:
         if want_fullalpha and not skip:
             rows = info.r if pl["params"].n_alpha_rows < 0 else max(info.kmax_eff, min(info.r, pl["params"].n_alpha_rows))
             fa = np.empty((rows, pl["n"]), dtype=np.float64)
-        k_eff = [0 if skip else min(k, info.r) for k in pl["ks"]]
+        k_eff = [0 if skip else min(k, info.kmax_eff) for k in pl["ks"]]     # kmax_eff = min(max(k), r), or min(max(k), nrow(fullalpha))
         rows_w = pl["m1"] if pl["params"].mode == MODE_FAST else pl["m1"] + pl["n_ps"]
         if want_W and not skip:
             W = np.empty(sum(rows_w * k for k in k_eff), dtype=np.float64)

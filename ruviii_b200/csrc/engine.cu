@@ -27,8 +27,8 @@ ruviii_handle::~ruviii_handle() {
         if (s.ev_g1) cudaEventDestroy(s.ev_g1);
         DevBuf<double>* bufs[] = {&s.Y, &s.PS, &s.Y0, &s.G, &s.gram_ws, &s.Vd, &s.U, &s.evals, &s.part, &s.alpha, &s.acT,
                                   &s.AG, &s.Linv, &s.colmean, &s.At, &s.at, &s.out, &s.out_ps, &s.W, &s.evals_asc,
-                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage,
-                                  &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1,
+                                  &s.falpha, &s.topk_buf, &s.Zt, &s.avg, &s.Yc, &s.Zstage, &s.solve_ws,
+                                  &s.eta, &s.eta_t, &s.etacT, &s.AG1, &s.At1, &s.Linv1, &s.cm1, &s.Yc1, &s.PS1,
                                   &s.pX, &s.pG, &s.pWs, &s.pU, &s.pEv, &s.pPart, &s.pAlpha, &s.pStat, &s.pMean, &s.pSd, &s.pTopk,
                                   &s.pEvAsc, &s.gX, &s.gPart, &s.gCov, &s.gF, &s.gR};
         for (auto b : bufs) b->release();
@@ -172,7 +172,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
                                         "non-conformable arguments (fastruvIII.R:179-180)");
     if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
     h->prm = *prm;
-    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = h->ps_pending = false;
+    h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = h->ps_pending = h->yc_valid = false;
     if (h->eta_q > 0 && h->eta_n != n)
         throw Error(RUVIII_ERR_INVALID, "eta has " + std::to_string(h->eta_n) + " columns, the assay has " + std::to_string(n) +
                                             " genes (ruviii_set_eta)");
@@ -263,7 +263,9 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
     h->r = (int)std::max<int64_t>(0, std::min<int64_t>(rank_bound, fast ? (int64_t)rank_bound : h->n_ctl_global));
     h->kk = std::min(h->kmax, h->r);
     if (h->kk > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "k > 32 is not supported by the fused update");
-    h->kp = pad_k(std::max(h->kk, 1));
+    // register / buffer extent: by max(k), not by min(max(k), r), so that a user-supplied fullalpha with more rows than r
+    // (ruvIII.R:142 takes fullalpha[1:min(k, nrow(fullalpha)), ]) still fits
+    h->kp = pad_k(std::max(std::min(h->kmax, kMaxK), 1));
     const bool skip = h->no_replicates || h->kk == 0;
     h->n_alpha_rows = skip ? 0 : (prm->n_alpha_rows < 0 ? h->r : std::min(h->r, std::max(h->kk, prm->n_alpha_rows)));
     h->n_keep = skip ? 0 : std::min(h->R, std::max(h->n_alpha_rows, h->kk + 1));   // one extra: the gap lambda_kk+1
@@ -355,6 +357,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.Linv1.alloc((size_t)qp * qp);
             s.cm1.alloc(qp);
             s.Yc1.alloc((size_t)h->m * s.ldc, false);
+            if (n_ps > 0) s.PS1.alloc((size_t)n_ps * s.ld, false);
             s.status1.alloc(4);
         }
         if (!skip) {
@@ -399,6 +402,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
             s.colmean.alloc(kp);
+            s.solve_ws.alloc(solve_fused_ws_doubles(h->n_sms));
             if (h->n_alpha_rows > h->kk) s.falpha.alloc((size_t)h->n_alpha_rows * s.ld);
             s.W.alloc(std::max<size_t>(w_total, 1));
             if (s.gp.impl == 2) {
@@ -483,6 +487,7 @@ void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS,
     h->uploaded = true;
     h->logged = false;
     h->eta_applied = false;
+    h->yc_valid = false;
     h->ran = false;
 }
 
@@ -598,8 +603,22 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         // Control-gene gather on the auxiliary stream.  It depends on Y only; it is forked AFTER the (bandwidth- and
         // tensor-bound) residop and Gram so that it fills the otherwise idle GPU during the eigensolve, whose kernels
         // are latency-bound and occupy a handful of SMs (forked at the start it only stole HBM bandwidth from K1).
+        // The control-gene block Yc = Y[, ctl] depends on the uploaded matrices only (after their log transform, PRPS
+        // construction and RUV1 pre-step, all of which run once per upload), so it is gathered once per upload and every later
+        // pass on the resident assay reuses it: 5 % extra storage instead of 1.1 GB of sector traffic per pass.
         bool defer_gather = false;
         auto fork_gather = [&](bool record = true) {
+            if (h->yc_valid) {
+                for_shards([&](Shard& s) {
+                    if (record) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
+                    RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev_fork, 0));
+                    RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_g0, s.copy_stream));
+                    RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_g1, s.copy_stream));
+                    RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_gather, s.copy_stream));
+                });
+                return;
+            }
+            h->yc_valid = env_int("RUVIII_YC_CACHE", 1) != 0;
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
                 if (record) RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_fork, s.stream));
@@ -691,7 +710,21 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         // for its verdict and the rest of the pass is queued behind it; its "not converged" flag travels in the [A | ac ac']
         // allreduce, so every rank learns after the final synchronisation whether ANY rank has to fall back, and then all of
         // them run this tail once more with classic = true (cuSOLVER on global rank 0 + broadcast).
-        bool persist_used = false;
+        bool persist_used = false, eig_status_pending = false;
+        std::string eig_fail_local;
+        int eig_fail_code = RUVIII_ERR_SOLVER;
+        auto check_eig_status = [&]() {          // after a synchronisation: did global rank 0's decomposition fail?
+            if (!eig_status_pending) return;
+            eig_status_pending = false;
+            if (!eig_fail_local.empty()) throw Error(eig_fail_code, eig_fail_local);
+            for (size_t i = 0; i < h->shards.size(); ++i) {
+                if (h->h_dflag[16 + 2 * i] != 0.0)
+                    throw Error(RUVIII_ERR_SOLVER, "the eigensolve failed on global rank 0 (its own error message has the details)");
+                int devinfo = 0;
+                std::memcpy(&devinfo, &h->h_dflag[16 + 2 * i + 1], sizeof(int));
+                if (devinfo != 0) throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(devinfo) + " on global rank 0");
+            }
+        };
         auto tail = [&](bool classic) {
         const int GO = h->gorder;
         const size_t flag_off = (size_t)h->rows_w * kp + (size_t)kp * kp;
@@ -711,7 +744,29 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                 rec(E_BCAST);
             } else {
                 for_shards([&](Shard& s) { RUVIII_CUDA_CHECK(cudaMemsetAsync(s.AG.p + flag_off, 0, sizeof(double), s.stream)); });
-                if (h->rank0 == 0) eigensolve(h, !classic);
+                // Global rank 0 decomposes; everybody else waits in the broadcast.  A failure on rank 0 (cuSOLVER status, syevdx
+                // eigenpair count, no convergence under RUVIII_EIG_IMPL=3, devInfo != 0) must not leave the peers blocked or
+                // let them return garbage: the two spare doubles behind the eigenvalues carry [host-side failure, devInfo bits]
+                // through the broadcast, and every rank raises after the pass has drained.
+                const size_t ev_tail = (size_t)std::max(h->n_keep, kp);
+                eig_fail_local.clear();
+                if (h->rank0 == 0) {
+                    Shard& s0 = h->shards[0];
+                    RUVIII_CUDA_CHECK(cudaSetDevice(s0.device));
+                    RUVIII_CUDA_CHECK(cudaMemsetAsync(s0.evals.p + ev_tail, 0, 2 * sizeof(double), s0.stream));
+                    try {
+                        eigensolve(h, !classic);
+                    } catch (const Error& e) {
+                        eig_fail_local = e.what();
+                        eig_fail_code = e.code;
+                        cudaGetLastError();
+                    }
+                    h->h_dflag[48] = eig_fail_local.empty() ? 0.0 : 1.0;
+                    RUVIII_CUDA_CHECK(cudaMemcpyAsync(s0.evals.p + ev_tail, &h->h_dflag[48], sizeof(double), cudaMemcpyHostToDevice, s0.stream));
+                    if (h->eig_solver_used != 3 && h->solver_info.p)
+                        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s0.evals.p + ev_tail + 1, h->solver_info.p, sizeof(int), cudaMemcpyDeviceToDevice,
+                                                          s0.stream));
+                }
                 rec(E_EIG);
                 {
                     std::vector<double*> b;
@@ -719,7 +774,14 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                     broadcast0(h, b, (size_t)GO * kp);
                     b.clear();
                     for (auto& s : h->shards) b.push_back(s.evals.p);
-                    broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
+                    broadcast0(h, b, ev_tail + 2);
+                    for (size_t i = 0; i < h->shards.size(); ++i) {
+                        Shard& s = h->shards[i];
+                        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                        RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_dflag[16 + 2 * i], s.evals.p + ev_tail, 2 * sizeof(double),
+                                                          cudaMemcpyDeviceToHost, s.stream));
+                    }
+                    eig_status_pending = true;
                     if (h->n_alpha_rows > kk) {
                         b.clear();
                         for (auto& s : h->shards) b.push_back(s.Vd.p);
@@ -788,14 +850,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
             RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_dflag[i], s.AG.p + flag_off, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         }
-        for_shards([&](Shard& s) {
-            const double* A = s.AG.p;
-            const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
-            launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
-            launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
-            launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
-        });
-        h->launches += 3;
+        for_shards([&](Shard& s) { launch_solve(h, s); });
         rec(E_SOLVE);
         for_shards([&](Shard& s) {
             const int64_t stride = (int64_t)h->m1 * s.ld;
@@ -819,13 +874,8 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                                                       s.out_ps.p + (size_t)d.second * h->n_ps * s.ld,
                                                       (size_t)h->n_ps * s.ld * 8, cudaMemcpyDeviceToDevice, s.stream));
             }
-            size_t off = 0;
-            for (int i = 0; i < nk; ++i) {
-                launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
-                off += (size_t)h->rows_w * h->k_eff[i];
-            }
         });
-        h->launches += 1 + (want_ps ? 1 : 0) + nk;
+        h->launches += 1 + (want_ps ? 1 : 0);
         rec(E_UPDATE);
         for (size_t i = 0; i < h->shards.size(); ++i) {
             Shard& s = h->shards[i];
@@ -834,6 +884,10 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         }
         };   // tail
         tail(false);
+        if (eig_status_pending) {
+            sync_all(h);
+            check_eig_status();
+        }
         if (persist_used) {
             sync_all(h);
             bool redo = false;
@@ -844,6 +898,8 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                     throw Error(RUVIII_ERR_SOLVER, "subspace iteration did not converge in " + std::to_string(h->eig_iterations) +
                                                        " products (RUVIII_EIG_IMPL=3 forbids the cuSOLVER fallback)");
                 tail(true);
+                sync_all(h);
+                check_eig_status();
             }
         }
     }
@@ -915,6 +971,33 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     if (info_out) *info_out = I;
 }
 
+// K5c ruvIII.R:144 solve(ac %*% t(ac)) + centring (ruvIII.R:118-120) + A~ = A_c L^-T + a~ = L^-1 alpha.  One cooperative kernel
+// (solve.cu); RUVIII_SOLVE_FUSED=0 selects the three-kernel form.
+void launch_solve(ruviii_handle* h, Shard& s) {
+    const int kp = h->kp, kk = h->kk;
+    const double* A = s.AG.p;
+    const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
+    static const bool fused = env_int("RUVIII_SOLVE_FUSED", 1) != 0;
+    if (fused) {
+        launch_solve_fused(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.alpha.p, s.n, s.ld, s.solve_ws.p, s.Linv.p, s.colmean.p, s.status.p,
+                           s.At.p, s.at.p, h->n_sms, s.stream);
+        h->launches += 1;
+    } else {
+        launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
+        launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
+        launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
+        h->launches += 3;
+    }
+}
+
+void launch_w_blocks(ruviii_handle* h, Shard& s) {
+    size_t off = 0;
+    for (size_t i = 0; i < h->ks.size(); ++i) {
+        launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], h->kp, s.W.p + off, s.stream);
+        off += (size_t)h->rows_w * h->k_eff[i];
+    }
+}
+
 void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W, double* const* newY_blocks) {
     if (!h->ran) throw Error(RUVIII_ERR_STATE, "ruviii_download before ruviii_run");
     const bool fast = h->prm.mode == RUVIII_MODE_FAST;
@@ -947,6 +1030,7 @@ void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullal
     if (W && !skip) {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        launch_w_blocks(h, s);           // W_k = A~[:, :k] L^-1[:k, :k]: formed only when somebody asks for it (return.info)
         size_t w_total = 0;
         for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
         RUVIII_CUDA_CHECK(cudaMemcpyAsync(W, s.W.p, w_total * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -1105,8 +1189,9 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
         // alpha <- fullalpha[1:min(k, nrow(fullalpha)), ]  (ruvIII.R:142)
         const int kk = std::min(h->kmax, (int)rows);
         if (kk > kMaxK) throw Error(RUVIII_ERR_UNSUPPORTED, "k > 32");
-        if (kk > h->kk)
-            throw Error(RUVIII_ERR_INVALID, "fullalpha has more usable rows than the plan allows (min(k, r))");
+        if (h->kk == 0)
+            throw Error(RUVIII_ERR_UNSUPPORTED, "the plan found no usable factor (r = 0: no control genes?), so nothing was set up for "
+                                                "a supplied fullalpha");
         h->kk = kk;
         const int64_t n = h->n_local_total;
         for (auto& s : h->shards) {
@@ -1128,6 +1213,12 @@ int ruviii_set_fullalpha(ruviii_handle* h, const double* fullalpha, int32_t rows
             else h->dup_slots.emplace_back(i, h->slot_of_k[ke]);
         }
         for (int i = 0; i <= kMaxK; ++i) if (h->slot_of_k[i] < 0) h->slot_of_k[i] = 0;
+        size_t w_total = 0;
+        for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            s.W.alloc(std::max<size_t>(w_total, 1));
+        }
         h->have_user_alpha = true;
     });
 }

@@ -30,11 +30,18 @@ void apply_ruv1(ruviii_handle* h) {
         launch_chol_solve(A, m, 0, s.AG1.p + (size_t)m * qp, q, qp, s.Linv1.p, s.cm1.p, s.status1.p, s.stream);   // mu_rows = 0: no centring
         launch_atilde(A, m, s.cm1.p, s.Linv1.p, q, qp, s.At1.p, s.stream);
         launch_alpha_tilde(s.eta.p, s.Linv1.p, q, qp, s.n, s.ld, s.eta_t.p, s.stream);
-        if (m1 > 0)
-            launch_update_smem(s.Y.p, s.ld, m1, s.n, s.At1.p, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.Y.p, s.ld, 0, s.stream);
-        if (h->n_ps > 0)
-            launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At1.p + (size_t)m1 * qp, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.PS.p,
+        // The update kernels read their input through the non-coherent path (ld.global.nc) and declare input and output
+        // __restrict__, so they must not run in place: the result goes to scratch (the first output block / PS1) and is
+        // copied back.  Once per upload, and only when eta != NULL.
+        if (m1 > 0) {
+            launch_update_smem(s.Y.p, s.ld, m1, s.n, s.At1.p, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.out.p, s.ld, 0, s.stream);
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.Y.p, s.out.p, (size_t)m1 * s.ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+        }
+        if (h->n_ps > 0) {
+            launch_update(s.PS.p, s.ld, h->n_ps, s.n, s.At1.p + (size_t)m1 * qp, qp, s.eta_t.p, s.ld, q, 1ull << q, slot0, s.PS1.p,
                           s.ld, 0, s.stream);
+            RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.PS.p, s.PS1.p, (size_t)h->n_ps * s.ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+        }
         RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[32 + i], s.status1.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     }
     h->launches += 8 + (h->n_ps > 0 ? 1 : 0);
@@ -308,12 +315,81 @@ void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n
     }
 }
 
+// Spearman's rho of every gene with a sample covariate (supervisedFindNCG.R:214-229 / :270-285 with corr.method = "spearman").
+// The covariate's ranks (ties averaged) are O(m1 log m1) host bookkeeping; ranking the m1 values of every gene is the kernel.
+void do_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, const double* covariate, double* rho_out,
+                      float* ms_out) {
+    const bool resident = X == nullptr;
+    if (resident) {
+        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_gene_spearman on resident data needs a plan and an upload");
+        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_spearman: no such output block");
+        m1 = h->m1;
+        n = h->n_local_total;
+    }
+    if (m1 < 2 || n <= 0 || !covariate || !rho_out) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_spearman: bad arguments");
+    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_spearman: row stride < n");
+    if (m1 > spearman_max_rows())
+        throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_gene_spearman: more than " + std::to_string(spearman_max_rows()) +
+                                                " samples do not fit the shared-memory sort");
+    // average ranks of the covariate
+    std::vector<int> order(m1);
+    for (int i = 0; i < m1; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return covariate[a] < covariate[b]; });
+    std::vector<double> cr(m1);
+    for (int a = 0; a < m1;) {
+        int b = a;
+        while (b + 1 < m1 && covariate[order[b + 1]] == covariate[order[a]]) ++b;
+        for (int t = a; t <= b; ++t) cr[order[t]] = 0.5 * (a + b) + 1.0;
+        a = b + 1;
+    }
+    const double cmean = 0.5 * (m1 + 1.0);
+    long double css = 0.0L;
+    for (int i = 0; i < m1; ++i) css += (long double)(cr[i] - cmean) * (cr[i] - cmean);
+    const int nsh = (int)h->shards.size();
+    h->launches = 0;
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        if (ng <= 0) continue;
+        const int64_t ld = resident ? s.ld : round_up(ng, kRowAlign);
+        s.gCov.alloc(m1, false);
+        s.gR.alloc(ld, false);
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gCov.p, cr.data(), (size_t)m1 * 8, cudaMemcpyHostToDevice, s.stream));
+        const double* src;
+        if (!resident) {
+            s.gX.alloc((size_t)m1 * ld, false);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
+            src = s.gX.p;
+        } else {
+            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        launch_gene_spearman(src, ld, m1, ng, s.gCov.p, cmean, (double)css, s.gR.p, s.stream);
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+        h->launches += 1;
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(rho_out + g0, s.gR.p, (size_t)ng * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    sync_all(h);
+    if (ms_out) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+        cudaEventElapsedTime(ms_out, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
+    }
+}
+
 }  // namespace ruviii
 
 using namespace ruviii;
 
 #pragma GCC visibility push(default)
 extern "C" {
+
+int ruviii_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, const double* covariate,
+                         double* rho_out, float* ms_out) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] { do_gene_spearman(h, X, ldX, m1, n, slot, covariate, rho_out, ms_out); });
+}
 
 int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
                double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,

@@ -147,7 +147,8 @@ struct Shard {
     int64_t ldc = 0;
     DevBuf<double> Y, PS, Y0, G, gram_ws, Vd, U, evals, part, alpha, acT, AG, Linv, colmean, At, at, out, out_ps, W,
         evals_asc, falpha, topk_buf, Zt, avg, Yc, Zstage;
-    DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1;   // ruv::RUV1 pre-step (eta != NULL)
+    DevBuf<double> solve_ws;                    // partial column sums + barrier counters of the fused solve kernel
+    DevBuf<double> eta, eta_t, etacT, AG1, At1, Linv1, cm1, Yc1, PS1;   // ruv::RUV1 pre-step (eta != NULL)
     DevBuf<double> pX, pG, pWs, pU, pEv, pPart, pAlpha, pStat, pMean, pSd, pTopk, pEvAsc;   // computePCA fast path (ruviii_pca)
     DevBuf<double> gX, gPart, gCov, gF, gR;     // gene statistics (ruviii_gene_stats)
     DevBuf<int> gStart, gRows, gGroup;
@@ -224,6 +225,7 @@ struct ruviii_handle {
     std::vector<int> prps_start, prps_rows;
     int prps_n = 0;
     bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
+    bool yc_valid = false;              // the control-gene block Yc holds Y[, ctl] of the CURRENT upload (gathered once per upload)
     double eig_tol = 1e-13;
     ruviii::StageState* stage = nullptr;   // pool of host threads + pinned bounce buffers of the staged host path
 
@@ -244,6 +246,8 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS);
 void eigensolve(ruviii_handle* h, bool allow_subspace = true);
 void do_run(ruviii_handle* h, ruviii_info* info_out);
+void launch_solve(ruviii_handle* h, Shard& s);      // K5c + A~ + a~ on the shard's main stream
+void launch_w_blocks(ruviii_handle* h, Shard& s);   // W_k for every requested k (only when W is downloaded)
 void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullalpha, double* W, double* const* newY_blocks = nullptr);
 // engine_pipeline.cu
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out);

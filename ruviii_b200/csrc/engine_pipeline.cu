@@ -157,11 +157,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
         allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
     }
     for_shards([&](Shard& s) {
-        const double* A = s.AG.p;
-        const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
-        launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
-        launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
-        launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
+        launch_solve(h, s);
         mark("W_known", s, s.stream);
         const int64_t stride = (int64_t)m1 * s.ld;
         // --- K6 per chunk as it lands, download right behind it ---
@@ -185,17 +181,13 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
             if (c == n_chunks / 2) mark("half_downloaded", s, s.d2h_stream);
         }
         mark("all_downloaded", s, s.d2h_stream);
-        size_t off = 0;
-        for (int i = 0; i < nk; ++i) {
-            launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
-            off += (size_t)h->rows_w * h->k_eff[i];
-        }
+        if (W_out && &s == &h->shards[0]) launch_w_blocks(h, s);
         if (fullalpha_out)
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(fullalpha_out + s.g0, n * 8, s.alpha.p, s.ld * 8, (size_t)s.n * 8, h->n_alpha_rows,
                                                 cudaMemcpyDeviceToHost, s.stream));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_UPDATE], s.stream));
     });
-    h->launches += 3 + n_chunks * (h->prm.apply_log ? 2 : 1) + nk;
+    h->launches += n_chunks * (h->prm.apply_log ? 2 : 1);
     if (W_out) {
         Shard& s = h->shards[0];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
@@ -246,6 +238,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
     (void)fast;
     h->uploaded = true;
     h->logged = h->prm.apply_log != 0;
+    h->yc_valid = true;                  // the whole control block was gathered on the way in
     h->ran = true;
     h->pipelined_last = 1;
 }

@@ -14,8 +14,10 @@
 // the device).  One shard per process (the R session with one GPU, or one rank of a torchrun launch).
 #include "engine_internal.cuh"
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
+#include <immintrin.h>
 #include <sched.h>
 #include <thread>
 
@@ -30,11 +32,16 @@ struct HostPool {
     int n_items = 0, next = 0, pending = 0;
     uint64_t gen = 0;
     bool stop = false;
+    // While a one-shot call is in flight the workers poll for the next batch instead of sleeping on the condition variable:
+    // a batch is ~1 ms of copying, a futex wake-up of 15 threads costs a good part of that.
+    std::atomic<bool> hot{false};
+    std::atomic<uint64_t> gen_hint{0};
 
     explicit HostPool(int n) {
         for (int i = 0; i < n; ++i) threads.emplace_back([this] { worker(); });
     }
     ~HostPool() {
+        hot.store(false, std::memory_order_release);
         {
             std::lock_guard<std::mutex> lk(m);
             stop = true;
@@ -42,12 +49,32 @@ struct HostPool {
         cv.notify_all();
         for (auto& t : threads) t.join();
     }
+    void set_hot(bool on) {
+        hot.store(on, std::memory_order_release);
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(m);
+        cv.notify_all();
+    }
     void worker() {
         uint64_t seen = 0;
         for (;;) {
+            bool spun_out = false;
+            if (hot.load(std::memory_order_acquire)) {
+                // poll (with pauses) until a new batch is published or the call ends -- but only for ~100 us: when the cores
+                // are oversubscribed (several ranks of one host, each with its own pool) a spinning thread steals the core a
+                // working one needs (r2m2: the pageable path took 162 ms on two ranks against 80 ms on one)
+                int spins = 0;
+                while (hot.load(std::memory_order_acquire) && gen_hint.load(std::memory_order_acquire) == seen && spins < 40000) {
+                    _mm_pause();
+                    ++spins;
+                }
+                spun_out = spins >= 40000;
+            }
             std::unique_lock<std::mutex> lk(m);
-            cv.wait(lk, [&] { return stop || (gen != seen && next < n_items); });
+            if (!hot.load(std::memory_order_acquire) || spun_out)
+                cv.wait(lk, [&] { return stop || (gen != seen && next < n_items) || (!spun_out && hot.load(std::memory_order_acquire)); });
             if (stop) return;
+            if (gen == seen) continue;
             seen = gen;
             while (next < n_items) {
                 const int i = next++;
@@ -67,6 +94,7 @@ struct HostPool {
         next = 0;
         pending = n;
         ++gen;
+        gen_hint.store(gen, std::memory_order_release);
         cv.notify_all();
         while (next < n_items) {
             const int i = next++;
@@ -75,7 +103,15 @@ struct HostPool {
             lk.lock();
             --pending;
         }
-        cv_done.wait(lk, [&] { return pending == 0; });
+        if (hot.load(std::memory_order_acquire)) {
+            while (pending != 0) {          // the stragglers are at most one item each: poll
+                lk.unlock();
+                _mm_pause();
+                lk.lock();
+            }
+        } else {
+            cv_done.wait(lk, [&] { return pending == 0; });
+        }
     }
 };
 
@@ -104,7 +140,37 @@ int host_threads_default() {
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = std::min(avail > 0 ? avail : 1 << 30, CPU_COUNT(&set));
     if (avail <= 0) avail = 4;
-    return std::max(1, std::min(16, avail));
+    return std::max(1, std::min(32, avail));
+}
+
+// Bulk copy with non-temporal stores: the destination (a pinned slot the DMA engine reads next, or the caller's output
+// that nobody reads soon) should not be pulled into the cache first -- a plain store costs a read-for-ownership of every
+// destination line, i.e. a third more memory traffic on a path that is bound by host memory bandwidth.
+__attribute__((target("avx2"))) void copy_nt_avx2(char* dst, const char* src, size_t bytes) {
+    size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+    if (head > bytes) head = bytes;
+    std::memcpy(dst, src, head);
+    dst += head; src += head; bytes -= head;
+    const size_t blocks = bytes / 128;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 96), d);
+        src += 128; dst += 128;
+    }
+    std::memcpy(dst, src, bytes - blocks * 128);
+    _mm_sfence();
+}
+
+void bulk_copy(char* dst, const char* src, size_t bytes) {
+    static const bool nt = __builtin_cpu_supports("avx2") && env_int("RUVIII_NT_COPY", 1) != 0;
+    if (nt && bytes >= 16384) copy_nt_avx2(dst, src, bytes);
+    else std::memcpy(dst, src, bytes);
 }
 
 void ensure_pinned(double*& p, size_t& have, size_t need) {
@@ -125,14 +191,14 @@ void pool_copy_rows(HostPool& pool, int n_threads, char* dst, size_t dst_pitch, 
         const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads * 2, total >> 20));
         pool.run(parts, [=](int i) {
             const size_t a = (total * (size_t)i / parts) & ~size_t(63), b = i + 1 == parts ? total : (total * (size_t)(i + 1) / parts) & ~size_t(63);
-            std::memcpy(dst + a, src + a, b - a);
+            bulk_copy(dst + a, src + a, b - a);
         });
         return;
     }
     const int parts = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_threads * 2, rows));
     pool.run(parts, [=](int i) {
         const int64_t r0 = rows * i / parts, r1 = rows * (i + 1) / parts;
-        for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + (size_t)r * dst_pitch, src + (size_t)r * src_pitch, row_bytes);
+        for (int64_t r = r0; r < r1; ++r) bulk_copy(dst + (size_t)r * dst_pitch, src + (size_t)r * src_pitch, row_bytes);
     });
 }
 
@@ -163,6 +229,7 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
         st.n_threads = want_threads;
     }
     HostPool& pool = *st.pool;
+    struct HotGuard { HostPool& p; explicit HotGuard(HostPool& q) : p(q) { p.set_hot(true); } ~HotGuard() { p.set_hot(false); } } hot_guard(pool);
     static const bool trace = env_int("RUVIII_PIPE_TRACE", 0) != 0;
     auto now_ms = [&] { return 1e3 * (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_enter); };
     double t_gather = 0, t_ps = 0, t_w = 0;
@@ -172,9 +239,9 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
     for (int i = 0; i < nk; ++i) out_pinned = out_pinned && host_pinned(out_blocks[i]) != nullptr;
     const bool ps_pinned = n_ps == 0 || host_pinned(PS) != nullptr;
 
-    // ---- row chunks: in-slot <= ~48 MB, out-slot (nk blocks) <= ~96 MB ----
+    // ---- row chunks: in-slot <= ~96 MB, out-slot (nk blocks) <= ~192 MB ----
     const size_t row_bytes = (size_t)n * 8;
-    int64_t rows = std::min<int64_t>((int64_t)(48u << 20) / (int64_t)row_bytes, (int64_t)(96u << 20) / (int64_t)(row_bytes * nk));
+    int64_t rows = std::min<int64_t>((int64_t)(96u << 20) / (int64_t)row_bytes, (int64_t)(192u << 20) / (int64_t)(row_bytes * nk));
     rows = std::max<int64_t>(64, rows / 64 * 64);
     const int chunk = (int)std::min<int64_t>(rows, round_up(m1, 64));
     const int n_chunks = ceil_div(m1, chunk);
@@ -231,22 +298,79 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
         launch_gram(s.gp, s.Y0.p, s.ld, s.tile_map.p, s.gram_ws.p, s.G.p, s.tmap, s.stream);
     }
     h->launches += 3;
+    // Two schedules.  DUPLEX (default): one pass of the host threads over Y copies out the control columns first, W is known
+    // early, and upload / update / download of the chunks overlap.  TWO-PHASE (RUVIII_STAGE_TWO_PHASE=1, pageable buffers
+    // only): the control columns are picked up WHILE each row is staged in (no separate pass over Y), W follows the last
+    // chunk, then the chunks are updated and drained.  Measured at C3 on the 16-core host (r2h): duplex 77-81 ms, two-phase
+    // 90-94 ms -- with bounce buffers every byte crosses host memory three times per direction (caller -> slot by the CPU,
+    // slot -> device by the DMA engine), the path is bound by host memory bandwidth (~160 GB/s of traffic), and the duplex
+    // schedule simply keeps both directions' traffic going at once.
+    const bool two_phase = !in_pinned && !out_pinned && env_int("RUVIII_STAGE_TWO_PHASE", 0) != 0;
+    // the in-slots carried the PRPS rows: their DMA must have left them before the first chunks are staged into them
+    if (!ps_pinned && !in_pinned && n_ps > 0) RUVIII_CUDA_CHECK(cudaEventSynchronize(s.ev_chunk[n_chunks]));
+    auto stage_in_chunk = [&](int c, bool with_gather) {          // caller's rows -> pinned slot (+ control columns) -> device
+        const int r0 = c * chunk, rr = std::min(chunk, m1 - r0);
+        const int slot = c % NS;
+        if (c >= NS) RUVIII_CUDA_CHECK(cudaEventSynchronize(s.ev_chunk[c - NS]));     // the slot's previous upload has left it
+        if (!with_gather || s.n_ctl == 0) {
+            pool_copy_rows(pool, st.n_threads, (char*)st.in_slot[slot], row_bytes, (const char*)(Y + (size_t)r0 * ldY + s.g0), (size_t)ldY * 8,
+                           row_bytes, rr);
+        } else {
+            const int nc = s.n_ctl;
+            const int* idx = s.ctl_idx_host.data();
+            double* ycd = st.yc_host + (size_t)r0 * nc;
+            char* dslot = (char*)st.in_slot[slot];
+            const double* src = Y + (size_t)r0 * ldY + s.g0;
+            const int parts = std::max(1, std::min(st.n_threads * 2, rr));
+            pool.run(parts, [=](int i) {
+                const int64_t a = (int64_t)rr * i / parts, b = (int64_t)rr * (i + 1) / parts;
+                for (int64_t r = a; r < b; ++r) {
+                    const double* row = src + (size_t)r * ldY;
+                    bulk_copy(dslot + (size_t)r * row_bytes, (const char*)row, row_bytes);
+                    double* d = ycd + (size_t)r * nc;
+                    for (int q = 0; q < nc; ++q) d[q] = row[idx[q]];          // the row has just been read: cache hits
+                }
+            });
+        }
+        RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, st.in_slot[slot], row_bytes, row_bytes, rr,
+                                            cudaMemcpyHostToDevice, s.copy_stream));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
+    };
+    if (two_phase)
+        for (int c = 0; c < n_chunks; ++c) stage_in_chunk(c, true);
+    // Pinned input: nothing on the host side stands between the caller's memory and the DMA engine, so the first chunk
+    // uploads are queued right behind the PRPS rows and stream while the host threads pick out the control columns.  Only
+    // ~256 MB of them: the copy engine serves its queue in order ACROSS streams, so the control block queued later waits
+    // for everything queued here (with every chunk queued up front W came after the whole upload: 75 ms instead of 51, r2i).
+    int n_early = 0;
+    if (in_pinned) {
+        auto upload_pinned = [&](int c) {
+            const int r0 = c * chunk, rr = std::min(chunk, m1 - r0);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8, row_bytes, rr,
+                                                cudaMemcpyHostToDevice, s.copy_stream));
+            RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
+        };
+        const size_t early_bytes = (size_t)env_int("RUVIII_STAGE_EARLY_MB", 256) << 20;
+        while (n_early < n_chunks && (size_t)n_early * chunk * row_bytes < early_bytes) upload_pinned(n_early++);
+    }
     // control columns of the sample rows: host threads copy Y[r, ctl] into one pinned block (bytes only; the log transform
     // of ruvIII.R:89 is applied to the block on the device)
     if (s.n_ctl > 0) {
         const int nc = s.n_ctl;
-        const int* idx = s.ctl_idx_host.data();
-        double* dst = st.yc_host;
-        const double* src = Y + s.g0;
-        const int parts = std::max(1, std::min(st.n_threads * 4, m1 / 64));
-        pool.run(parts, [=](int i) {
-            const int64_t r0 = (int64_t)m1 * i / parts, r1 = (int64_t)m1 * (i + 1) / parts;
-            for (int64_t r = r0; r < r1; ++r) {
-                const double* row = src + (size_t)r * ldY;
-                double* d = dst + (size_t)r * nc;
-                for (int c = 0; c < nc; ++c) d[c] = row[idx[c]];
-            }
-        });
+        if (!two_phase) {
+            const int* idx = s.ctl_idx_host.data();
+            double* dst = st.yc_host;
+            const double* src = Y + s.g0;
+            const int parts = std::max(1, std::min(st.n_threads * 4, m1 / 64));
+            pool.run(parts, [=](int i) {
+                const int64_t r0 = (int64_t)m1 * i / parts, r1 = (int64_t)m1 * (i + 1) / parts;
+                for (int64_t r = r0; r < r1; ++r) {
+                    const double* row = src + (size_t)r * ldY;
+                    double* d = dst + (size_t)r * nc;
+                    for (int c = 0; c < nc; ++c) d[c] = row[idx[c]];
+                }
+            });
+        }
         RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Yc.p, s.ldc * 8, st.yc_host, (size_t)nc * 8, (size_t)nc * 8, m1, cudaMemcpyHostToDevice,
                                             s.copy_stream));
         if (h->prm.apply_log) launch_log2_inplace(s.Yc.p, s.ldc, m1, nc, h->prm.pseudo_count, s.copy_stream);
@@ -282,20 +406,12 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
         std::vector<double*> b{s.AG.p};
         allreduce_sum(h, b, (size_t)h->rows_w * kp + (size_t)kp * kp);
     }
-    {
-        const double* A = s.AG.p;
-        const double* Gm = s.AG.p + (size_t)h->rows_w * kp;
-        launch_chol_solve(A, h->rows_w, h->mu_rows, Gm, kk, kp, s.Linv.p, s.colmean.p, s.status.p, s.stream);
-        launch_atilde(A, h->rows_w, s.colmean.p, s.Linv.p, kk, kp, s.At.p, s.stream);
-        launch_alpha_tilde(s.alpha.p, s.Linv.p, kk, kp, s.n, s.ld, s.at.p, s.stream);
-    }
-    h->launches += 6;
+    launch_solve(h, s);
+    h->launches += 3;
     t_w = now_ms();
 
     // ================= phase B: stream the assay through =================
     const int64_t stride = (int64_t)m1 * s.ld;
-    // the in-slots carried the PRPS rows: their DMA must have left them before the first chunks are staged into them
-    if (!ps_pinned && !in_pinned && n_ps > 0) RUVIII_CUDA_CHECK(cudaEventSynchronize(s.ev_chunk[n_chunks]));
     auto drain = [&](int c) {                      // pinned out-slot -> the caller's (pageable) output blocks
         if (out_pinned) return;
         const int r0 = c * chunk, rr = std::min(chunk, m1 - r0);
@@ -309,17 +425,14 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
         const int r0 = c * chunk, rr = std::min(chunk, m1 - r0);
         // ---- upload chunk c ----
         if (in_pinned) {
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8, row_bytes, rr,
-                                                cudaMemcpyHostToDevice, s.copy_stream));
-        } else {
-            const int slot = c % NS;
-            if (c >= NS) RUVIII_CUDA_CHECK(cudaEventSynchronize(s.ev_chunk[c - NS]));     // the slot's previous upload has left it
-            pool_copy_rows(pool, st.n_threads, (char*)st.in_slot[slot], row_bytes, (const char*)(Y + (size_t)r0 * ldY + s.g0), (size_t)ldY * 8,
-                           row_bytes, rr);
-            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, st.in_slot[slot], row_bytes, row_bytes, rr,
-                                                cudaMemcpyHostToDevice, s.copy_stream));
+            if (c >= n_early) {
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.Y.p + (size_t)r0 * s.ld, s.ld * 8, Y + (size_t)r0 * ldY + s.g0, ldY * 8, row_bytes, rr,
+                                                    cudaMemcpyHostToDevice, s.copy_stream));
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
+            }
+        } else if (!two_phase) {
+            stage_in_chunk(c, false);
         }
-        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev_chunk[c], s.copy_stream));
         // ---- K6 on the chunk ----
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_chunk[c], 0));
         if (h->prm.apply_log) launch_log2_inplace(s.Y.p + (size_t)r0 * s.ld, s.ld, rr, s.n, h->prm.pseudo_count, s.stream);
@@ -345,11 +458,8 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
     h->launches += n_chunks * (h->prm.apply_log ? 2 : 1);
     {
         size_t off = 0;
-        for (int i = 0; i < nk; ++i) {
-            launch_w_from_atilde(s.At.p, h->rows_w, s.Linv.p, h->k_eff[i], kp, s.W.p + off, s.stream);
-            off += (size_t)h->rows_w * h->k_eff[i];
-        }
-        h->launches += nk;
+        for (int i = 0; i < nk; ++i) off += (size_t)h->rows_w * h->k_eff[i];
+        if (W_out) launch_w_blocks(h, s);
         if (fullalpha_out)
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(fullalpha_out + s.g0, h->n_local_total * 8, s.alpha.p, s.ld * 8, row_bytes, h->n_alpha_rows,
                                                 cudaMemcpyDeviceToHost, s.stream));
@@ -360,8 +470,8 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
     sync_all(h);
     const double t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     if (trace)
-        fprintf(stderr, "[stage trace] threads=%d chunks=%d x %d rows in_pinned=%d out_pinned=%d: ps_issued=%.2f gather_issued=%.2f W_queued=%.2f "
-                        "total=%.2f (ms)\n", st.n_threads, n_chunks, chunk, (int)in_pinned, (int)out_pinned, t_ps, t_gather, t_w, (t_done - t_enter) * 1e3);
+        fprintf(stderr, "[stage trace] %s threads=%d chunks=%d x %d rows in_pinned=%d out_pinned=%d: ps_issued=%.2f gather_issued=%.2f W_queued=%.2f "
+                        "total=%.2f (ms)\n", two_phase ? "two-phase" : "duplex", st.n_threads, n_chunks, chunk, (int)in_pinned, (int)out_pinned, t_ps, t_gather, t_w, (t_done - t_enter) * 1e3);
     if (h->rank0 == 0 && h->h_flags[0] != 0)
         throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
     if (h->h_flags[1] != 0)
@@ -385,6 +495,7 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
     }
     h->uploaded = true;
     h->logged = h->prm.apply_log != 0;
+    h->yc_valid = true;                  // the whole control block was gathered on the way in
     h->ran = true;
     h->pipelined_last = I.pipelined;
 }

@@ -130,6 +130,12 @@ void launch_atilde(const double* A, int rows_w, const double* colmean, const dou
 // at[q][g] = sum_{j<=q} Linv[q][j] alpha[j][g]               (a~ = L^-1 alpha)
 void launch_alpha_tilde(const double* alpha, const double* Linv, int kk, int kp, int n, int64_t ld,
                         double* at, cudaStream_t s);
+// The three steps above in ONE cooperative launch (solve.cu): every CTA sums a slice of the rows, one grid barrier, every CTA
+// factors redundantly and writes its rows of A~ / its genes of a~.  ws: solve_fused_ws_doubles(n_sms) doubles, zeroed once.
+size_t solve_fused_ws_doubles(int n_sms);
+void launch_solve_fused(const double* A, int rows_w, int mu_rows, const double* Gm, int kk, int kp, const double* alpha, int n,
+                        int64_t ld, double* ws, double* Linv, double* colmean, int* status, double* At, double* at, int n_sms,
+                        cudaStream_t s);
 // W_k = A~[:, :k] Linv[:k, :k]  (rows_w x k, row-major, dense)  -- the W of ruvIII.R:144 for one k
 void launch_w_from_atilde(const double* At, int rows_w, const double* Linv, int k, int kp, double* W,
                           cudaStream_t s);
@@ -162,6 +168,11 @@ int gene_stats_piece_rows(int n, int n_rows, int n_sms);
 void launch_gene_stats(const double* X, int64_t ld, int n, const int* piece_start, const int* piece_rows, const int* piece_group,
                        int n_pieces, int n_groups, int n_rows, const double* cov, double cov_ss, int log_first, double pseudo_count,
                        double* part, int64_t ldp, double* F, double* r, cudaStream_t s);
+
+// K11b supervisedFindNCG.R:214-229 with corr.method = "spearman": per-gene Spearman rho (spearman.cu); m1 <= spearman_max_rows()
+int spearman_max_rows();
+void launch_gene_spearman(const double* X, int64_t ld, int m1, int n, const double* crank, double cmean, double css, double* rho,
+                          cudaStream_t s);
 
 // micro-benchmarks (ceilings quoted beside the roofline)
 float probe_copy_gbs(size_t bytes, cudaStream_t s);

@@ -1,9 +1,11 @@
 """Negative-control-gene selection -- the other step immediately before the RUV-III path.
 
-Host side of ``supervisedFindNCG`` (R/supervisedFindNCG.R:44-461) for its default configuration
-(``regress.out.* = FALSE``, ``apply.normalization = FALSE``, ``corr.method = "pearson"``): the same arguments, the same
-sequence of tests, ranks and rank product.  The per-gene statistics -- one-way ANOVA F across every categorical
-variable, Pearson correlation with every continuous one -- are the streaming kernel K11 through ``ruviii_gene_stats``;
+Host side of ``supervisedFindNCG`` (R/supervisedFindNCG.R:44-461) with ``regress.out.* = FALSE`` and
+``apply.normalization = FALSE`` (the reference itself marks the regress.out branch "NEED to BE tEStED", :110), for
+``corr.method`` "pearson" (default) and "spearman": the same arguments, the same sequence of tests, ranks and rank
+product.  The per-gene statistics -- one-way ANOVA F across every categorical variable, Pearson correlation with every
+continuous one -- are the streaming kernel K11 through ``ruviii_gene_stats``; Spearman's rho is K11b
+(``ruviii_gene_spearman``: a shared-memory sort of every gene's samples);
 ``rank()``, the ``round(., 2)`` the reference applies to the correlations, and the rank product are O(genes) host
 bookkeeping.  Plotting (:359-425) is not reproduced.
 
@@ -60,8 +62,8 @@ def supervisedFindNCG(se_obj, assay_name, bio_variables, uv_variables, no_ncg=10
     _printColoredMessage("------------The supervisedFindNCG function starts:", verbose)
     if regress_out_uv_variables or regress_out_bio_variables or apply_normalization:
         raise NotImplementedError("regress.out.* / apply.normalization (supervisedFindNCG.R:111-146) are outside the CUDA path")
-    if corr_method != "pearson":
-        raise NotImplementedError("corr.method = '%s': only the default Pearson correlation is built" % corr_method)
+    if corr_method not in ("pearson", "spearman"):
+        raise NotImplementedError("corr.method = '%s': Pearson and Spearman correlations are built" % corr_method)
     bio_variables = [bio_variables] if isinstance(bio_variables, str) else list(bio_variables or [])
     uv_variables = [uv_variables] if isinstance(uv_variables, str) else list(uv_variables or [])
     assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)            # genes x samples
@@ -73,18 +75,25 @@ def supervisedFindNCG(se_obj, assay_name, bio_variables, uv_variables, no_ncg=10
     con_bio = [v for v in bio_variables if not _is_categorical(se_obj.col_data[v])]
     kw = dict(apply_log=apply_log, pseudo_count=pseudo_count)
     all_tests, ranks = {}, []
+
+    def corr(v):                                  # correls(y, x, type = corr.method)[, "correlation"], :214-229 / :270-285
+        cov = np.asarray(se_obj.col_data[v], dtype=np.float64)
+        if corr_method == "spearman":             # ranks are invariant under log2(x + pseudo.count)
+            return eng.gene_spearman(Y, covariate=cov)["rho"]
+        return eng.gene_stats(Y, covariate=cov, **kw)["r"]
+
     _printColoredMessage("### Finding genes that are highly affected by unwanted variation:", verbose)
     for v in cat_uv:                                                                     # :179-191
         F = eng.gene_stats(Y, groups=_codes(se_obj.col_data[v], min_count=3), **kw)["F"]
         all_tests.setdefault("anova.gene.uv", {})[v] = dict(statistic=F, ranked_genes=r_rank(F))
         ranks.append(all_tests["anova.gene.uv"][v]["ranked_genes"])
     for v in con_uv:                                                                     # :214-229
-        r = np.round(eng.gene_stats(Y, covariate=np.asarray(se_obj.col_data[v], dtype=np.float64), **kw)["r"], 2)
+        r = np.round(corr(v), 2)
         all_tests.setdefault("corr.genes.uv", {})[v] = dict(correlation=r, ranked_genes=r_rank(np.abs(r)))
         ranks.append(all_tests["corr.genes.uv"][v]["ranked_genes"])
     _printColoredMessage("### Finding genes that are not highly affected by biology", verbose)
     for v in con_bio:                                                                    # :270-285
-        r = np.round(eng.gene_stats(Y, covariate=np.asarray(se_obj.col_data[v], dtype=np.float64), **kw)["r"], 2)
+        r = np.round(corr(v), 2)
         all_tests.setdefault("corr.genes.bio", {})[v] = dict(correlation=r, ranked_genes=r_rank(-np.abs(r)))
         ranks.append(all_tests["corr.genes.bio"][v]["ranked_genes"])
     for v in cat_bio:                                                                    # :302-316

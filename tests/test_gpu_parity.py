@@ -505,3 +505,23 @@ def test_config_C3_full_size_and_properties(engine):
     p2 = dataclasses.replace(p, assay=(p.Y + shift[None, :]).T, replicate_data=p.replicate_data + shift[None, :])
     res2 = run_engine(engine, p2, [10], want_all=False)
     assert O.rel_frob(res2["newY"][0] - shift[None, :], res["newY"][1]) < 1e-10
+
+
+def test_user_fullalpha_row_counts(engine):
+    """ruvIII.R:138,142: a supplied fullalpha skips residop / Gram / svd and alpha = fullalpha[1:min(k, nrow(fullalpha)), ] --
+    whatever r is.  Fewer rows than k (W shrinks to nrow(fullalpha) columns; ADVICE r01: W came back partly uninitialised) and
+    more rows than r = min(m - ncol(M), sum(ctl)) (used to be rejected)."""
+    p = make_problem(m1=300, n=2000, groups=5, rep=3, n_ctl=150, k=6, seed=41)          # r = min(15 - 5, 150) = 10
+    api.set_engine(engine)
+    se = rv.SummarizedExperiment(assays={"logcounts": p.assay}, col_names=p.sample_names)
+    rd = rv.ReplicateData(p.replicate_data, p.replicate_names)
+    rng = np.random.default_rng(3)
+    for rows, k in ((4, 6), (12, 12), (12, 7)):
+        fa = rng.standard_normal((rows, 2000))
+        out = rv.ruvIII(se, "logcounts", apply_log=False, replicate_data=rd, ctl=p.ctl, k=k, fullalpha=fa, return_info=True,
+                        save_se_obj=False, verbose=False)
+        ref = O.ruvIII_literal(p.assay, p.sample_names, p.replicate_data, p.replicate_names, p.ctl, k, apply_log=False, fullalpha=fa)
+        assert out["W"].shape == ref["W"].shape == (315, min(k, rows))
+        assert O.rel_frob(out["W"], ref["W"]) < 1e-9
+        assert O.rel_frob(out["newY"], ref["newY"]) < TOL_NEWY
+    api.set_engine(None)

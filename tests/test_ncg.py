@@ -36,7 +36,7 @@ def test_unbuilt_options_are_loud():
     with pytest.raises(NotImplementedError):
         supervisedFindNCG(se, "a", ["b"], ["b"], regress_out_uv_variables=True, verbose=False)
     with pytest.raises(NotImplementedError):
-        supervisedFindNCG(se, "a", ["b"], ["b"], corr_method="spearman", verbose=False)
+        supervisedFindNCG(se, "a", ["b"], ["b"], corr_method="kendall", verbose=False)
 
 
 @pytest.mark.gpu
@@ -86,3 +86,37 @@ def test_supervised_find_ncg_selects_the_oracle_genes(engine):
     ref = NO.supervised_find_ncg(counts, cd, ["subtype", "purity"], ["plate", "libsize"], 150, True, 1.0)
     assert got.dtype == bool and got.sum() == ref.sum()
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m1", [330, 1500, 2049])
+def test_spearman_kernel_matches_oracle(engine, m1):
+    """K11b: shared-memory sort + tie-averaged ranks + Pearson of the ranks, against scipy's rankdata.  Counts have long runs
+    of ties (zeros, small integers); m1 = 2049 crosses a power of two (padding keys)."""
+    counts, cd = _design(m1=m1, n=611)
+    counts[:40] = np.minimum(counts[:40], 3.0)                     # genes that are almost all ties
+    counts[5] = 0.0                                                 # a constant gene: rho is 0 / 0
+    lib = np.asarray(cd["libsize"])
+    lib[::7] = lib[0]                                               # ties in the covariate too
+    res = engine.gene_spearman(counts.T, covariate=lib)
+    ref = NO.correls_spearman(lib, counts.T)
+    ok = np.isfinite(ref)
+    assert ok.sum() >= 600 and not np.isfinite(res["rho"][5])
+    assert np.max(np.abs(res["rho"][ok] - ref[ok])) < 1e-12
+    # ranks do not change under log2(x + 1)
+    res2 = engine.gene_spearman(np.log2(counts.T + 1.0), covariate=lib)
+    assert np.max(np.abs(res2["rho"][ok] - ref[ok])) < 1e-12
+
+
+@pytest.mark.gpu
+def test_supervised_find_ncg_spearman(engine):
+    counts, cd = _design()
+    se = rv.SummarizedExperiment(assays={"counts": counts}, col_names=["s%d" % i for i in range(counts.shape[1])], col_data=cd)
+    api.set_engine(engine)
+    try:
+        se = supervisedFindNCG(se, "counts", ["subtype", "purity"], ["plate", "libsize"], no_ncg=150, apply_log=True,
+                               pseudo_count=1, corr_method="spearman", verbose=False)
+    finally:
+        api.set_engine(None)
+    ref = NO.supervised_find_ncg(counts, cd, ["subtype", "purity"], ["plate", "libsize"], 150, True, 1.0, corr_method="spearman")
+    assert np.array_equal(se.metadata["NCG"], ref)
