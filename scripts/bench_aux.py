@@ -55,6 +55,8 @@ def main():
                      ("anova+pearson", dict(groups=batch, covariate=cov))):
         ms = [eng.gene_stats(None, slot=0, **kw)["ms"] for _ in range(args.steps + 1)][1:]
         gs[name] = {"ms": float(np.median(ms)), "gbs": 8.0 * m1 * n / (float(np.median(ms)) * 1e-3) / 1e9}
+    ms = [eng.gene_spearman(None, covariate=cov, slot=0)["ms"] for _ in range(3)][1:]
+    gs["spearman"] = {"ms": float(np.median(ms)), "note": "K11b: one CTA per gene, shared-memory bitonic sort of 11,000 samples"}
     out["gene_stats_resident"] = gs
     # K0 PRPS: 1,200 pseudo-samples of 3 samples each, host matrix in, host PS out (only member rows are uploaded)
     rng = np.random.default_rng(1)

@@ -101,7 +101,7 @@ def test_spearman_kernel_matches_oracle(engine, m1):
     res = engine.gene_spearman(counts.T, covariate=lib)
     ref = NO.correls_spearman(lib, counts.T)
     ok = np.isfinite(ref)
-    assert ok.sum() >= 600 and not np.isfinite(res["rho"][5])
+    assert ok.sum() >= 500 and not np.isfinite(res["rho"][5])          # some of the clipped genes are constant too
     assert np.max(np.abs(res["rho"][ok] - ref[ok])) < 1e-12
     # ranks do not change under log2(x + 1)
     res2 = engine.gene_spearman(np.log2(counts.T + 1.0), covariate=lib)
