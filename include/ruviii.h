@@ -60,7 +60,10 @@ typedef struct ruviii_params {
                               * -1 = r = min(m - ncol(M), sum(ctl)) as ruvIII.R:140 keeps (return.info = TRUE)  */
     int32_t gram_side;       /* 0 = auto (smaller side), 1 = sample side Y0 Y0', 2 = gene side Y0' Y0          */
     int32_t want_ps_rows;    /* also produce newY for the PRPS rows (STACKED, return.info & !save.se.obj)       */
-    int32_t reserved[7];
+    int32_t keep_resident;   /* ruviii_plan only: the matrices uploaded under the PREVIOUS plan of this handle stay (same m1, n,  *
+                              * n_ps, apply_log / pseudo_count): re-plan with another ctl / k / grouping without another upload  *
+                              * -- normalise() learns ctl from statistics of the assay it has already uploaded                   */
+    int32_t reserved[6];
 } ruviii_params;
 
 /* what one run did; times are device times (CUDA events on the compute stream of shard 0), in ms */
@@ -159,6 +162,9 @@ int ruviii_download(ruviii_handle* h, double* newY_out, double* newY_ps_out,
 /* apply.average.rep (ruvIII.R:148-149): nk blocks of p x n (row stride n), row g = mean of the rows of newY in
  * replicate group g, groups in ascending id order (= factor level order when ids are as.integer(factor(names))). */
 int ruviii_download_averaged(ruviii_handle* h, double* averaged_out);
+/* replicate.data as it sits on the device (n_ps x n, row stride ldPS): uploaded, or built from the assay by the sets given to
+ * ruviii_set_prps_sets (what normalise() stores in metadata$PRPS, normalise.R:143 / supervisedPRPS.R). */
+int ruviii_download_replicate_data(ruviii_handle* h, double* PS_out, int64_t ldPS);
 /* Small replicated results of the last run: eigenvalues (descending, `count` of them are written). */
 int ruviii_eigenvalues(ruviii_handle* h, double* out, int32_t count);
 
@@ -196,7 +202,8 @@ int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32
  * after centring every gene over the samples (and dividing by its sd when scale, as base::scale does).
  *   X != NULL : host matrix, m1 x n row-major (the assay bytes), log2(X + pseudo_count) first when apply_log (computePCA.R:124-127)
  *   X == NULL : data already on the device -- slot >= 0: output block `slot` (the newY of ks[slot]) of the last ruviii_run;
- *               slot == -1: the uploaded assay (after its own log transform).  m1, n, ldX are ignored.
+ *               slot == -1: the uploaded assay after the plan's own log transform (applied in place now if no run has done it
+ *               yet; apply_log / pseudo_count of this call are ignored).  m1, n, ldX are ignored.
  *   u_out  m1 x k row-major (sing.val$u), d_out k (sing.val$d), v_out NULL or k x n row-major (= the bytes of R's n x k v).
  *   Signs: each u_j has its largest-magnitude component positive; v_j follows.  k <= 32 and k < m1.
  *   stage_ms6: NULL or 6 floats (device ms): upload+log, centre, Gram, allreduce+eigensolve, broadcast+projection, total. */

@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_normalise_blocks", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats", "ruviii_gene_spearman",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_download_replicate_data", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats", "ruviii_gene_spearman",
     "ruviii_fast_residop", "ruviii_probe", "ruviii_mat_mult", "ruviii_mat_subtract", "ruviii_mat_transpose", "ruviii_mat_inverse",
 ]
 
@@ -28,7 +28,7 @@ SYMBOLS = [
 class Params(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("apply_log", C.c_int32),
                 ("average_rep", C.c_int32), ("pseudo_count", C.c_double), ("n_alpha_rows", C.c_int32),
-                ("gram_side", C.c_int32), ("want_ps_rows", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("gram_side", C.c_int32), ("want_ps_rows", C.c_int32), ("keep_resident", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Info(C.Structure):
@@ -89,6 +89,7 @@ def load_library():
     lib.ruviii_run.argtypes = [H, C.POINTER(Info)]
     lib.ruviii_download.argtypes = [H, vp, vp, vp, vp]
     lib.ruviii_download_averaged.argtypes = [H, vp]
+    lib.ruviii_download_replicate_data.argtypes = [H, vp, C.c_int64]
     lib.ruviii_barrier.argtypes = [H]
     lib.ruviii_host_alloc.argtypes = [C.c_size_t]
     lib.ruviii_host_alloc.restype = C.c_void_p
@@ -132,7 +133,7 @@ def _rowmajor(a, name):
 
 
 def make_params(mode=MODE_STACKED, apply_log=False, pseudo_count=1.0, average_rep=False, n_alpha_rows=0,
-                want_ps_rows=False, gram_side=0):
+                want_ps_rows=False, gram_side=0, keep_resident=False):
     p = Params()
     p.struct_size = C.sizeof(Params)
     p.mode = mode
@@ -142,6 +143,7 @@ def make_params(mode=MODE_STACKED, apply_log=False, pseudo_count=1.0, average_re
     p.n_alpha_rows = int(n_alpha_rows)
     p.want_ps_rows = int(bool(want_ps_rows))
     p.gram_side = int(gram_side)
+    p.keep_resident = int(bool(keep_resident))
     return p
 
 
@@ -343,6 +345,13 @@ class Engine:
     def eigenvalues(self, count):
         out = np.empty(count, dtype=np.float64)
         self._check(self._lib.ruviii_eigenvalues(self._h, _ptr(out), count))
+        return out
+
+    def download_replicate_data(self):
+        """replicate.data as the device holds it (uploaded, or built from the assay by ``set_prps_sets``): n_ps x n."""
+        pl = self._plan
+        out = np.empty((pl["n_ps"], pl["n"]), dtype=np.float64)
+        self._check(self._lib.ruviii_download_replicate_data(self._h, _ptr(out), out.shape[1]))
         return out
 
     def download_averaged(self):

@@ -289,6 +289,16 @@ def normalise(se_obj, assay_name, apply_log=True, pseudo_count=1, bio_variable_p
         raise ValueError("No assay name has been provided.")
     if isinstance(assay_name, (list, tuple)):
         raise ValueError("The function can only take a single assay.name.")
+    # One pipeline, one upload (normalise.R:111,127,143-161): when the three steps work on the same assay the engine keeps it on
+    # the device -- the pseudo-samples are built there from the index sets (K0), the control-gene statistics run on it in place
+    # (K11), the plan is redone with the selected ctl (keep_resident) and RUV-III follows; the assay crosses PCIe once.
+    import os
+    if (eta is None and fullalpha is None and not apply_average_rep and norm_assay_name_ncg in (None, assay_name)
+            and not (regress_out_uv_variables_ncg or regress_out_bio_variables_ncg or apply_normalization_ncg)
+            and os.environ.get("RUVIII_NORMALISE_RESIDENT", "1") != "0"):
+        return _normalise_resident(se_obj, assay_name, apply_log, pseudo_count, bio_variable_prps, uv_variables_prps,
+                                   batch_variable_prps, min_sample_for_prps, min_sample_per_batch_prps, norm_assay_name_ncg,
+                                   bio_variables_ncg, uv_variables_ncg, no_ncg, k, inputcheck, assess_se_obj, verbose)
     se_obj = prps.supervisedPRPS(se_obj, assay_name, bio_variable_prps, uv_variables_prps, batch_variable_prps,
                                  min_sample_for_prps, min_sample_per_batch_prps, apply_log, pseudo_count, assess_se_obj,
                                  assess_cor_variables_prps, save_se_obj=True, verbose=verbose)          # :110-124
@@ -308,5 +318,51 @@ def normalise(se_obj, assay_name, apply_log=True, pseudo_count=1, bio_variable_p
                              include_intercept=include_intercept, apply_average_rep=apply_average_rep, fullalpha=fullalpha,
                              return_info=False, inputcheck=inputcheck, assess_se_obj=assess_se_obj,
                              remove_na="measurements", save_se_obj=True, verbose=verbose)                 # :144-161
+    _printColoredMessage("------------The normalise function finished.", verbose)
+    return se_obj
+
+
+def _normalise_resident(se_obj, assay_name, apply_log, pseudo_count, bio_variable_prps, uv_variables_prps, batch_variable_prps,
+                        min_sample_for_prps, min_sample_per_batch_prps, norm_assay_name_ncg, bio_variables_ncg, uv_variables_ncg,
+                        no_ncg, k, inputcheck, assess_se_obj, verbose):
+    """normalise() with the assay resident on the device from the first step to the last (see :func:`normalise`)."""
+    from . import prps
+    from .ncg import supervisedFindNCG
+    blocks = prps.supervisedPRPS(se_obj, assay_name, bio_variable_prps, uv_variables_prps, batch_variable_prps, min_sample_for_prps,
+                                 min_sample_per_batch_prps, apply_log, pseudo_count, assess_se_obj, False, save_se_obj=True,
+                                 verbose=verbose, sets_only=True)                                       # normalise.R:110-124
+    sets = [ix for b in blocks.values() for ix in b[0]]
+    set_names = [nm for b in blocks.values() for nm in b[1]]
+    assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)                                      # genes x samples
+    n, m1 = assay.shape
+    ks = [int(x) for x in np.atleast_1d(k)]
+    groups = group_codes(list(se_obj.col_names) + set_names)                                            # ruvIII.R:93,101
+    eng = get_engine()
+    eng.set_prps_sets(sets)
+    try:
+        eng.plan(make_params(mode=MODE_STACKED, apply_log=apply_log, pseudo_count=pseudo_count), m1, n, len(sets), groups,
+                 np.zeros(n, dtype=bool), ks)                                # provisional plan: no control genes known yet
+        eng.upload(assay.T, None)                                            # the ONE upload; PS = NULL: built on the device
+        if norm_assay_name_ncg is None and "NCG" not in se_obj.metadata:
+            raise ValueError("norm.assay.name.ncg is empty. Please select an assay to use for the Negative Control Genes selection")
+        if norm_assay_name_ncg is not None:                                                             # :127-141
+            se_obj = supervisedFindNCG(se_obj, norm_assay_name_ncg, bio_variables_ncg, uv_variables_ncg, no_ncg=no_ncg,
+                                       apply_log=apply_log, pseudo_count=pseudo_count, assess_se_obj=assess_se_obj,
+                                       save_se_obj=True, verbose=verbose, resident=True)
+        ctl = _tological(se_obj.metadata["NCG"], n)                                                     # ruvIII.R:80-84,102
+        eng.plan(make_params(mode=MODE_STACKED, apply_log=apply_log, pseudo_count=pseudo_count, keep_resident=True), m1, n,
+                 len(sets), groups, ctl, ks)
+        eng.run()
+        res = eng.download()
+        PS = eng.download_replicate_data()
+    finally:
+        eng.set_prps_sets([])
+    # metadata$PRPS$supervised[[key]]: one block per unwanted-variation variable (prpsForCategoricalUV.R:176-189)
+    row = 0
+    for key, (bsets, bnames) in blocks.items():
+        se_obj.metadata.setdefault("PRPS", {}).setdefault("supervised", {})[key] = ReplicateData(PS[row:row + len(bsets)], bnames)
+        row += len(bsets)
+    for i, kv in enumerate(ks):                                                                         # ruvIIIMultipleK.R:75-94
+        _save(se_obj, assay_name, kv, res["newY"][i], False, None, None)
     _printColoredMessage("------------The normalise function finished.", verbose)
     return se_obj

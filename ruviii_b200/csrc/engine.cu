@@ -63,6 +63,7 @@ ruviii_handle::~ruviii_handle() {
     if (h_flags) cudaFreeHost(h_flags);
     if (h_dflag) cudaFreeHost(h_dflag);
     if (stage) ruviii::stage_state_destroy(stage);
+    if (p2p) { if (!shards.empty()) cudaSetDevice(shards[0].device); ruviii::p2p_state_destroy(p2p); }
 }
 
 namespace ruviii {
@@ -121,6 +122,8 @@ void finish_create(ruviii_handle* h) {
 // ---- collectives over all shards of all processes ------------------------------------------------------
 void allreduce_sum(ruviii_handle* h, std::vector<double*> bufs, size_t count) {
     if (h->world == 1) return;
+    // one process per GPU: the exchange runs as one kernel over NVLink peer memory (p2p.cu) when the buffers are mapped
+    if (h->multi_process && p2p_allreduce(h, bufs[0], count)) { h->launches += 1; return; }
     RUVIII_NCCL_CHECK(ncclGroupStart());
     for (size_t i = 0; i < h->shards.size(); ++i)
         RUVIII_NCCL_CHECK(ncclAllReduce(bufs[i], bufs[i], count, ncclDouble, ncclSum, h->shards[i].comm,
@@ -171,6 +174,19 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         throw Error(RUVIII_ERR_INVALID, "apply.average.rep in fastruvIII multiplies t(M) (n_ps rows) with newY (m1 rows): "
                                         "non-conformable arguments (fastruvIII.R:179-180)");
     if (m1 + n_ps <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_plan: no rows");
+    // keep_resident: the matrices of the previous plan stay where they are (same shapes and the same log transform, no RUV1
+    // pre-step applied to them yet): only the ctl- / k- / grouping-dependent state is rebuilt
+    const bool keep = prm->keep_resident != 0;
+    if (keep) {
+        if (!h->uploaded) throw Error(RUVIII_ERR_STATE, "keep_resident: nothing has been uploaded under a previous plan");
+        if (h->m1 != m1 || h->n_local_total != n || h->n_ps != n_ps)
+            throw Error(RUVIII_ERR_STATE, "keep_resident: the shapes differ from those of the resident matrices");
+        if (h->prm.apply_log != prm->apply_log || (prm->apply_log && h->prm.pseudo_count != prm->pseudo_count))
+            throw Error(RUVIII_ERR_STATE, "keep_resident: apply.log / pseudo.count differ from those of the resident assay");
+        if (h->eta_applied || h->eta_q > 0)
+            throw Error(RUVIII_ERR_STATE, "keep_resident: a RUV1 pre-step (eta) rewrites the resident assay; upload again");
+    }
+    const bool kept_logged = keep && h->logged, kept_ps_pending = keep && h->ps_pending;
     h->prm = *prm;
     h->planned = h->uploaded = h->ran = h->logged = h->have_user_alpha = h->eta_applied = h->ps_pending = h->yc_valid = false;
     if (h->eta_q > 0 && h->eta_n != n)
@@ -317,8 +333,8 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             if (ctl[s.g0 + g]) cidx.push_back(g);
         s.n_ctl = (int)cidx.size();
         s.ctl_idx_host = cidx;
-        s.Y.alloc((size_t)std::max(m1, 1) * s.ld);
-        s.PS.alloc((size_t)std::max(n_ps, 1) * s.ld);
+        s.Y.alloc((size_t)std::max(m1, 1) * s.ld, !keep);
+        s.PS.alloc((size_t)std::max(n_ps, 1) * s.ld, !keep);
         s.out.alloc((size_t)nk * std::max(m1, 1) * s.ld, false);
         if (want_ps) s.out_ps.alloc((size_t)nk * n_ps * s.ld, false);
         s.status.alloc(4);
@@ -387,7 +403,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             fill_gram_tile_map(s.gp, tm.data());
             s.tile_map.alloc(tm.size());
             RUVIII_CUDA_CHECK(cudaMemcpy(s.tile_map.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            s.G.alloc((size_t)GO * GO);
+            s.G.alloc((size_t)GO * GO + 2);
             s.evals_asc.alloc(GO);
             s.evals.alloc(std::max(h->n_keep, kp) + 2);
             s.U.alloc((size_t)GO * kp);
@@ -397,7 +413,7 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.alpha.alloc((size_t)kp * s.ld);
             s.at.alloc((size_t)kp * s.ld);
             s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
-            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp + 1);   // [A | ac ac' | eigensolver flag]
+            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp + 4);   // [A | ac ac' | eigensolver flag]
             s.Yc.alloc((size_t)h->rows_w * s.ldc, false);
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
@@ -410,6 +426,13 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             }
             if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
+    }
+    // ---- peer-memory allreduce (one process per GPU): exchange buffers for the larger of the two matrices of the pass ----
+    // (latency-bound sizes only: a 20,000^2 gene-side Gram is bandwidth-bound and stays with NCCL's ring)
+    if (!skip && h->multi_process) {
+        const size_t lim = (size_t)8 << 20, cg = (size_t)h->gorder * h->gorder, ca = (size_t)h->rows_w * kp + (size_t)kp * kp + 1;
+        const size_t cap = std::max(cg <= lim ? cg : 0, ca <= lim ? ca : 0);
+        if (cap > 0) p2p_setup(h, cap + 2);
     }
     // ---- eigensolver: subspace iteration on every shard that runs it, cuSOLVER on global rank 0 only ----
     h->use_topk = false;
@@ -459,6 +482,23 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
         }
     }
     h->planned = true;
+    if (keep) {
+        h->uploaded = true;
+        h->logged = kept_logged;
+        // PRPS rows: those uploaded from the host stay; those built from registered sets are rebuilt on the next run (K0 is
+        // idempotent and costs 0.15 ms)
+        h->ps_pending = kept_ps_pending || h->ps_from_sets;
+    }
+}
+
+// ruvIII.R:88-89 on the resident assay, once per upload (ruviii_run does the same on its first pass)
+void ensure_logged(ruviii_handle* h) {
+    if (!h->prm.apply_log || h->logged) return;
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        launch_log2_inplace(s.Y.p, s.ld, h->m1, s.n, h->prm.pseudo_count, s.stream);
+    }
+    h->logged = true;
 }
 
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS) {
@@ -468,6 +508,7 @@ void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS,
     if ((h->m1 > 0 && (!Y || ldY < h->n_local_total)) || (h->n_ps > 0 && !build_ps && (!PS || ldPS < h->n_local_total)))
         throw Error(RUVIII_ERR_INVALID, "ruviii_upload: NULL matrix or row stride < n");
     h->ps_pending = build_ps;
+    h->ps_from_sets = build_ps;
     for (auto& s : h->shards) {
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
@@ -566,10 +607,10 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
             fn(s);
         }
     };
+    NvtxRange nvtx_run("ruviii_run");
     rec(E_START);
     if (h->prm.apply_log && !h->logged) {             // ruvIII.R:88-89, once per upload
-        for_shards([&](Shard& s) { launch_log2_inplace(s.Y.p, s.ld, h->m1, s.n, h->prm.pseudo_count, s.stream); });
-        h->logged = true;
+        ensure_logged(h);
         h->launches += 1;
     }
     if (h->ps_pending) {
@@ -634,6 +675,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         static const int gather_at = env_int("RUVIII_GATHER_AT", 0);
         if (h->have_user_alpha) fork_gather();
         if (!h->have_user_alpha) {
+            NvtxRange nvtx_k12("K1 residop + K2 Gram + allreduce");
             for_shards([&](Shard& s) {
                 RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, h->m1};
                 launch_helmert(src, s.grp_start.p, s.grp_rows.p, h->n_groups_active, h->max_group, s.n, s.Y0.p, s.ld, s.stream);
@@ -729,6 +771,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
         const int GO = h->gorder;
         const size_t flag_off = (size_t)h->rows_w * kp + (size_t)kp * kp;
         persist_used = !classic && !h->have_user_alpha && h->use_topk && h->persist_rb > 0;
+        NvtxRange nvtx_tail("K3 eigensolve + K4 projection + K5 control products + solve + K6 update");
         if (!h->have_user_alpha) {
             if (persist_used) {
                 for (size_t i = 0; i < h->shards.size(); ++i) {
@@ -915,6 +958,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
     }
     sync_all(h);
     const double host_t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (h->multi_process) p2p_check(h);
     if (!skip) {
         if (h->rank0 == 0 && !h->have_user_alpha && h->h_flags[0] != 0)
             throw Error(RUVIII_ERR_SOLVER, "cuSOLVER syevd devInfo = " + std::to_string(h->h_flags[0]));
@@ -1164,6 +1208,30 @@ int ruviii_download_averaged(ruviii_handle* h, double* out) {
             for (int i = 0; i < nk; ++i)
                 RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(out + (size_t)i * h->p * n + s.g0, n * 8, s.avg.p + (size_t)i * h->p * s.ld,
                                                     s.ld * 8, (size_t)s.n * 8, h->p, cudaMemcpyDeviceToHost, s.stream));
+        }
+        sync_all(h);
+    });
+}
+
+int ruviii_download_replicate_data(ruviii_handle* h, double* PS_out, int64_t ldPS) {
+    if (!h || !PS_out) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_download_replicate_data needs a plan and an upload");
+        if (h->n_ps <= 0) return;
+        if (ldPS < h->n_local_total) throw Error(RUVIII_ERR_INVALID, "row stride < n");
+        if (h->ps_pending) {               // the sets are registered but no run has built the rows yet
+            ensure_logged(h);
+            for (auto& s : h->shards) {
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                RowSrc src{s.Y.p, s.ld, nullptr, 0, h->m1};
+                launch_group_mean(src, s.set_start.p, s.set_rows.p, h->n_ps, s.n, s.PS.p, s.ld, s.stream);
+            }
+            h->ps_pending = false;
+        }
+        for (auto& s : h->shards) {
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(PS_out + s.g0, ldPS * 8, s.PS.p, s.ld * 8, (size_t)s.n * 8, h->n_ps, cudaMemcpyDeviceToHost,
+                                                s.stream));
         }
         sync_all(h);
     });

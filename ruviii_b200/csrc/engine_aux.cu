@@ -68,6 +68,7 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
         if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_pca: no such output block");
         m1 = h->m1;
         n = h->n_local_total;
+        if (slot < 0) { ensure_logged(h); apply_log = 0; }       // the resident assay after the plan's own log transform
     }
     if (m1 < 2 || n <= 0 || k <= 0 || !u_out || !d_out) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: bad arguments");
     if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: row stride < n");
@@ -227,6 +228,7 @@ void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n
         if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats: no such output block");
         m1 = h->m1;
         n = h->n_local_total;
+        if (slot < 0) { ensure_logged(h); apply_log = 0; }       // the resident assay after the plan's own log transform
     }
     if (m1 < 2 || n <= 0 || (!group && !covariate) || (group && !F_out) || (covariate && !r_out))
         throw Error(RUVIII_ERR_INVALID, "ruviii_gene_stats: bad arguments");

@@ -9,6 +9,7 @@
 #include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is dlopen()ed, see NcclApi
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <chrono>
@@ -34,6 +35,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -59,6 +61,7 @@ struct NcclApi {
             api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
             api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
             api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
             api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
             api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
             api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
@@ -75,6 +78,7 @@ struct NcclApi {
 #define ncclCommDestroy ::ruviii::NcclApi::get().CommDestroy
 #define ncclAllReduce ::ruviii::NcclApi::get().AllReduce
 #define ncclBroadcast ::ruviii::NcclApi::get().Broadcast
+#define ncclAllGather ::ruviii::NcclApi::get().AllGather
 #define ncclSend ::ruviii::NcclApi::get().Send
 #define ncclRecv ::ruviii::NcclApi::get().Recv
 #define ncclGroupStart ::ruviii::NcclApi::get().GroupStart
@@ -94,6 +98,15 @@ struct NcclApi {
             throw ::ruviii::Error(RUVIII_ERR_SOLVER, std::string(#expr) + ": cusolver status " +         \
                                                          std::to_string((int)_r));                       \
     } while (0)
+
+// NVTX range around the host-side enqueue of one stage of the pass (K1..K6 of DESIGN.md): a timeline tool (Nsight Systems)
+// shows the stages by name above the kernels they launch.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 inline int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
@@ -130,6 +143,8 @@ struct DevBuf {
 
 struct StageState;
 void stage_state_destroy(StageState* st);
+struct P2PState;
+void p2p_state_destroy(P2PState* p);
 
 struct Shard {
     int device = 0;
@@ -225,8 +240,10 @@ struct ruviii_handle {
     std::vector<int> prps_start, prps_rows;
     int prps_n = 0;
     bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
+    bool ps_from_sets = false;          // the resident PRPS rows come from ruviii_set_prps_sets, not from the host
     bool yc_valid = false;              // the control-gene block Yc holds Y[, ctl] of the CURRENT upload (gathered once per upload)
     double eig_tol = 1e-13;
+    ruviii::P2PState* p2p = nullptr;       // peer-memory exchange buffers of the one-process-per-GPU allreduce (p2p.cu)
     ruviii::StageState* stage = nullptr;   // pool of host threads + pinned bounce buffers of the staged host path
 
     ~ruviii_handle();
@@ -243,6 +260,7 @@ void spin_sync(cudaStream_t st);
 void sync_all(ruviii_handle* h);
 void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps, const int32_t* group_of_row,
              const uint8_t* ctl, const int32_t* ks, int nk);
+void ensure_logged(ruviii_handle* h);
 void do_upload(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS);
 void eigensolve(ruviii_handle* h, bool allow_subspace = true);
 void do_run(ruviii_handle* h, ruviii_info* info_out);
@@ -253,6 +271,10 @@ void do_download(ruviii_handle* h, double* newY, double* newY_ps, double* fullal
 bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const double* newY_out, const double* newY_ps_out);
 void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* newY_out,
                             double* fullalpha_out, double* W_out);
+// p2p.cu
+bool p2p_setup(ruviii_handle* h, size_t cap_doubles);
+bool p2p_allreduce(ruviii_handle* h, double* buf, size_t count);
+void p2p_check(ruviii_handle* h);
 // engine_stage.cu
 bool can_stage(ruviii_handle* h, const double* PS, const double* newY_ps_out);
 void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* const* out_blocks,

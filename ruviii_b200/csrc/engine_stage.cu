@@ -469,6 +469,7 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
     }
     sync_all(h);
     const double t_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (h->multi_process) p2p_check(h);
     if (trace)
         fprintf(stderr, "[stage trace] %s threads=%d chunks=%d x %d rows in_pinned=%d out_pinned=%d: ps_issued=%.2f gather_issued=%.2f W_queued=%.2f "
                         "total=%.2f (ms)\n", two_phase ? "two-phase" : "duplex", st.n_threads, n_chunks, chunk, (int)in_pinned, (int)out_pinned, t_ps, t_gather, t_w, (t_done - t_enter) * 1e3);

@@ -58,7 +58,10 @@ def _codes(col, min_count=1):
 def supervisedFindNCG(se_obj, assay_name, bio_variables, uv_variables, no_ncg=1000, regress_out_uv_variables=False,
                       regress_out_bio_variables=False, apply_normalization=False, normalization="CPM", apply_log=True,
                       pseudo_count=1, corr_method="pearson", a=0.05, rho=0, anova_method="aov", assess_se_obj=True,
-                      assess_variables=False, remove_na="both", plot_output=False, fast_pca=True, save_se_obj=True, verbose=True):
+                      assess_variables=False, remove_na="both", plot_output=False, fast_pca=True, save_se_obj=True, verbose=True,
+                      resident=False):
+    """``resident`` (not in R): the assay is the one the engine already holds (uploaded under the current plan, its log
+    transform included) -- the statistics run on it in place and nothing crosses PCIe but the per-gene results."""
     _printColoredMessage("------------The supervisedFindNCG function starts:", verbose)
     if regress_out_uv_variables or regress_out_bio_variables or apply_normalization:
         raise NotImplementedError("regress.out.* / apply.normalization (supervisedFindNCG.R:111-146) are outside the CUDA path")
@@ -66,9 +69,12 @@ def supervisedFindNCG(se_obj, assay_name, bio_variables, uv_variables, no_ncg=10
         raise NotImplementedError("corr.method = '%s': Pearson and Spearman correlations are built" % corr_method)
     bio_variables = [bio_variables] if isinstance(bio_variables, str) else list(bio_variables or [])
     uv_variables = [uv_variables] if isinstance(uv_variables, str) else list(uv_variables or [])
-    assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)            # genes x samples
-    Y = np.ascontiguousarray(assay.T)
     eng = get_engine()
+    if resident:
+        Y = None                                                                  # slot = -1: the resident assay
+    else:
+        assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)            # genes x samples
+        Y = np.ascontiguousarray(assay.T)
     cat_uv = [v for v in uv_variables if _is_categorical(se_obj.col_data[v])]            # :153-154
     con_uv = [v for v in uv_variables if not _is_categorical(se_obj.col_data[v])]
     cat_bio = [v for v in bio_variables if _is_categorical(se_obj.col_data[v])]          # :246-247

@@ -80,8 +80,9 @@ def _store(se_obj, bio_variable, uv_variable, assay_name, block):
 
 
 def prpsForCategoricalUV(se_obj, assay_name, uv_variable, bio_variable, min_sample_for_prps=3, apply_log=True,
-                         pseudo_count=1, remove_na="both", assess_se_obj=True, save_se_obj=True, verbose=True):
-    """R/prpsForCategoricalUV.R:36-215."""
+                         pseudo_count=1, remove_na="both", assess_se_obj=True, save_se_obj=True, verbose=True, sets_only=False):
+    """R/prpsForCategoricalUV.R:36-215.  ``sets_only`` (not in R): return ``(index sets, set ids)`` -- the colData bookkeeping
+    alone -- for callers that let the engine build the pseudo-samples from an assay it already holds (normalise())."""
     _printColoredMessage("------------The prpsForCategoricalUV function starts:", verbose)
     if isinstance(assay_name, (list, tuple)):
         raise ValueError("The function can only take a single assay.name.")
@@ -100,6 +101,8 @@ def prpsForCategoricalUV(se_obj, assay_name, uv_variable, bio_variable, min_samp
     if len(set(bio)) == 1:
         raise ValueError("The bio.variable should have at least two groups.")
     sets, names = prps_sets_categorical(bio, uv, uv_variable, min_sample_for_prps)
+    if sets_only:
+        return sets, names
     assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)
     values = get_engine().prps(assay.T, sets, apply_log=apply_log, pseudo_count=pseudo_count)   # K0 on the device
     block = ReplicateData(values, names)
@@ -113,8 +116,8 @@ def prpsForCategoricalUV(se_obj, assay_name, uv_variable, bio_variable, min_samp
 
 def prpsForContinuousUV(se_obj, assay_name, apply_log=True, pseudo_count=1, uv_variable=None, bio_variable=None,
                         batch_variable=None, min_sample_for_prps=3, min_sample_per_batch=10, assess_se_obj=True,
-                        remove_na="both", save_se_obj=True, verbose=True):
-    """R/prpsForContinuousUV.R:47-262."""
+                        remove_na="both", save_se_obj=True, verbose=True, sets_only=False):
+    """R/prpsForContinuousUV.R:47-262.  ``sets_only``: see :func:`prpsForCategoricalUV`."""
     _printColoredMessage("------------The prpsForContinuousUV function starts.", verbose)
     if isinstance(assay_name, (list, tuple)):
         raise ValueError("The function can only take a single assay.name.")
@@ -125,6 +128,8 @@ def prpsForContinuousUV(se_obj, assay_name, apply_log=True, pseudo_count=1, uv_v
         raise ValueError("'names' attribute [4] must be the same length as the vector [3] (batch.variable = NULL)")
     sets, names = prps_sets_continuous(se_obj.col_data[uv_variable], se_obj.col_data[bio_variable],
                                        se_obj.col_data[batch_variable], min_sample_for_prps, min_sample_per_batch)
+    if sets_only:
+        return sets, names
     assay = np.asarray(se_obj.assay(assay_name), dtype=np.float64)
     values = get_engine().prps(assay.T, sets, apply_log=apply_log, pseudo_count=pseudo_count)
     block = ReplicateData(values, names)
@@ -138,9 +143,10 @@ def prpsForContinuousUV(se_obj, assay_name, apply_log=True, pseudo_count=1, uv_v
 
 def supervisedPRPS(se_obj, assay_name, bio_variable, uv_variables, batch_variable=None, min_sample_for_prps=3,
                    min_sample_per_batch=6, apply_log=True, pseudo_count=1, assess_se_obj=True,
-                   assess_cor_variables=False, remove_na="both", save_se_obj=True, verbose=True):
+                   assess_cor_variables=False, remove_na="both", save_se_obj=True, verbose=True, sets_only=False):
     """R/supervisedPRPS.R:62-260: one PRPS block per unwanted-variation variable, categorical ones (character columns)
-    through ``prpsForCategoricalUV``, numeric ones through ``prpsForContinuousUV``."""
+    through ``prpsForCategoricalUV``, numeric ones through ``prpsForContinuousUV``.  ``sets_only``: dict block key ->
+    (index sets, set ids), nothing computed."""
     if uv_variables is None:
         raise ValueError("The uv.variables cannot be empty.")
     uv_variables = [uv_variables] if isinstance(uv_variables, str) else list(uv_variables)
@@ -149,13 +155,16 @@ def supervisedPRPS(se_obj, assay_name, bio_variable, uv_variables, batch_variabl
         col = se_obj.col_data[uv]
         if all(isinstance(v, str) for v in col):
             out = prpsForCategoricalUV(se_obj, assay_name, uv, bio_variable, min_sample_for_prps, apply_log, pseudo_count,
-                                       remove_na, False, save_se_obj, verbose)
+                                       remove_na, False, save_se_obj, verbose, sets_only)
         else:
             out = prpsForContinuousUV(se_obj, assay_name, apply_log, pseudo_count, uv, bio_variable, batch_variable,
-                                      min_sample_for_prps, min_sample_per_batch, False, remove_na, save_se_obj, verbose)
+                                      min_sample_for_prps, min_sample_per_batch, False, remove_na, save_se_obj, verbose, sets_only)
+        if sets_only:
+            blocks["bio:%s||uv:%s||data:%s" % (bio_variable, uv, assay_name)] = out
+            continue
         if not save_se_obj:
             blocks["bio:%s||uv:%s||data:%s" % (bio_variable, uv, assay_name)] = out
-    return se_obj if save_se_obj else blocks
+    return blocks if sets_only else (se_obj if save_se_obj else blocks)
 
 
 def replicate_data_from_metadata(se_obj):

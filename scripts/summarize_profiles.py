@@ -35,12 +35,15 @@ if os.path.exists(lp):
     hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
     hdr = rows[hi]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    agg, cnt, tot = collections.OrderedDict(), collections.Counter(), 0.0
+    agg, cnt, tot, probes = collections.OrderedDict(), collections.Counter(), 0.0, {}
     for r in rows[hi + 2:]:
         if len(r) <= vi:
             continue
         k = r[ki][:100]
         v = float(r[vi].replace(",", ""))
+        if "cutlass" in k or "dmma_peak_kernel" in k or "cublas" in k.lower():      # FP64 ceiling probes: outside the timed passes
+            probes[k] = probes.get(k, 0.0) + v
+            continue
         agg[k] = agg.get(k, 0.0) + v
         cnt[k] += 1
         tot += v
@@ -49,10 +52,14 @@ if os.path.exists(lp):
     lines.append("%10s %6s %8s %6s  kernel" % ("total_us", "count", "us/launch", "share"))
     for k, v in sorted(agg.items(), key=lambda x: -x[1]):
         lines.append("%10.1f %6d %8.1f %5.1f%%  %s" % (v / 1e3, cnt[k], v / 1e3 / cnt[k], 100 * v / tot, k))
+    for k, v in probes.items():
+        lines.append("# not counted (FP64 ceiling probe after the timed passes): %10.1f us  %s" % (v / 1e3, k))
     open(os.path.join(dst, "%s_launches.txt" % name), "w").write("\n".join(lines) + "\n")
 
-rp = os.path.join(src, "prof.ncu-rep")
-if os.path.exists(rp):
+for rep, suffix in (("prof", "ncu_full"), ("prof_eig", "ncu_eig")):
+    rp = os.path.join(src, rep + ".ncu-rep")
+    if not os.path.exists(rp):
+        continue
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -64,7 +71,7 @@ if os.path.exists(rp):
         for m in METRICS:
             if m in idx:
                 out.append("  %-78s %s %s" % (m, r[idx[m]], units[idx[m]]))
-    open(os.path.join(dst, "%s_ncu_full.txt" % name), "w").write("\n".join(out) + "\n")
+    open(os.path.join(dst, "%s_%s.txt" % (name, suffix)), "w").write("\n".join(out) + "\n")
 
 for f in sorted(os.listdir(src)):
     if f.startswith("bench") and f.endswith(".json"):

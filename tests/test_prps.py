@@ -117,3 +117,35 @@ def test_normalise_end_to_end(engine):
     for k in (1, 3):
         ref = O.ruvIII_literal(counts, se.col_names, ps.T, names, ncg, k, apply_log=True, pseudo_count=1.0)
         assert O.rel_frob(out.assays["RUV_K%d_on_counts" % k], ref["newY"][:300].T) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("corr_method_vars", [(["plate"], ["subtype"]), (["plate", "libsize"], ["subtype"])])
+def test_normalise_resident_matches_stepwise(engine, corr_method_vars, monkeypatch):
+    """normalise.R:61-167 as ONE device-resident pipeline (PRPS sets -> K0, control-gene statistics on the resident assay,
+    re-plan with the selected ctl, RUV-III) against the step-by-step route that uploads the assay for every step: the same
+    metadata$PRPS blocks, the same metadata$NCG, the same RUV_K* assays."""
+    uv_ncg, bio_ncg = corr_method_vars
+    outs = []
+    for resident in ("1", "0"):
+        monkeypatch.setenv("RUVIII_NORMALISE_RESIDENT", resident)
+        se, bio, batch, libsize, counts = _design(m1=300, n=1203, seed=9)
+        api.set_engine(engine)
+        try:
+            out = rv.normalise(se, "counts", apply_log=True, pseudo_count=1, bio_variable_prps="subtype", uv_variables_prps=["plate"],
+                               batch_variable_prps="plate", norm_assay_name_ncg="counts", bio_variables_ncg=bio_ncg,
+                               uv_variables_ncg=uv_ncg, no_ncg=200, k=[2, 4], verbose=False)
+        finally:
+            api.set_engine(None)
+        outs.append(out)
+    a, b = outs
+    assert np.array_equal(a.metadata["NCG"], b.metadata["NCG"]) and a.metadata["NCG"].sum() >= 200
+    assert list(a.metadata["PRPS"]["supervised"]) == list(b.metadata["PRPS"]["supervised"])
+    for key in a.metadata["PRPS"]["supervised"]:
+        pa, pb = a.metadata["PRPS"]["supervised"][key], b.metadata["PRPS"]["supervised"][key]
+        assert pa.row_names == pb.row_names and O.rel_frob(pa.values, pb.values) < 1e-13
+    for k in (2, 4):
+        assert O.rel_frob(a.assays["RUV_K%d_on_counts" % k], b.assays["RUV_K%d_on_counts" % k]) < 1e-11
+    ps, names = PO.prps_categorical(counts, bio, batch, "plate", 3, True, 1.0)
+    ref = O.ruvIII_literal(counts, se.col_names, ps.T, names, a.metadata["NCG"], 4, apply_log=True, pseudo_count=1.0)
+    assert O.rel_frob(a.assays["RUV_K4_on_counts"], ref["newY"][:300].T) < 1e-9
