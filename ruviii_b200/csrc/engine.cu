@@ -322,6 +322,24 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
 
     // ---- device buffers ----
     const int kp = h->kp, R = h->R;
+    // Peer-memory allreduce (one process per GPU, p2p.cu): the two matrices that are summed over the ranks -- the Gram and
+    // [A | ac ac' | flag] -- are carved out of an exchange buffer every peer has mapped, so that the owner of a slice can
+    // store its sum straight into every rank's copy.  Latency-bound sizes only: a 20,000^2 gene-side Gram is bandwidth-bound
+    // and stays with NCCL's ring.
+    bool p2p_g = false, p2p_ag = false;
+    {
+        const bool skip0 = h->no_replicates || h->kk == 0;
+        if (!skip0 && h->multi_process) {
+            const size_t lim = (size_t)8 << 20, cg = (size_t)h->gorder * h->gorder + 2, ca = (size_t)h->rows_w * kp + (size_t)kp * kp + 4;
+            p2p_g = cg <= lim;
+            p2p_ag = ca <= lim;
+            if (p2p_g || p2p_ag) {
+                const bool ok = p2p_setup(h, std::max(p2p_g ? cg : 0, p2p_ag ? ca : 0), (p2p_g ? cg + 64 : 0) + (p2p_ag ? ca + 64 : 0));
+                p2p_g = p2p_g && ok;
+                p2p_ag = p2p_ag && ok;
+            }
+        }
+    }
     const bool want_ps = (prm->want_ps_rows || prm->average_rep) && !fast && n_ps > 0;
     size_t w_total = 0;
     for (int i = 0; i < nk; ++i) w_total += (size_t)h->rows_w * h->k_eff[i];
@@ -403,7 +421,10 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             fill_gram_tile_map(s.gp, tm.data());
             s.tile_map.alloc(tm.size());
             RUVIII_CUDA_CHECK(cudaMemcpy(s.tile_map.p, tm.data(), tm.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            s.G.alloc((size_t)GO * GO + 2);
+            {
+                double* q = p2p_g ? p2p_carve(h, (size_t)GO * GO + 2) : nullptr;
+                if (q) s.G.alias(q, (size_t)GO * GO + 2); else s.G.alloc((size_t)GO * GO + 2);
+            }
             s.evals_asc.alloc(GO);
             s.evals.alloc(std::max(h->n_keep, kp) + 2);
             s.U.alloc((size_t)GO * kp);
@@ -413,7 +434,10 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             s.alpha.alloc((size_t)kp * s.ld);
             s.at.alloc((size_t)kp * s.ld);
             s.acT.alloc((size_t)std::max(s.n_ctl, 1) * kp);
-            s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp + 4);   // [A | ac ac' | eigensolver flag]
+            {                                                            // [A | ac ac' | eigensolver flag]
+                double* q = p2p_ag ? p2p_carve(h, (size_t)h->rows_w * kp + (size_t)kp * kp + 4) : nullptr;
+                if (q) s.AG.alias(q, (size_t)h->rows_w * kp + (size_t)kp * kp + 4); else s.AG.alloc((size_t)h->rows_w * kp + (size_t)kp * kp + 4);
+            }
             s.Yc.alloc((size_t)h->rows_w * s.ldc, false);
             s.At.alloc((size_t)h->rows_w * kp);
             s.Linv.alloc((size_t)kp * kp);
@@ -426,13 +450,6 @@ void do_plan(ruviii_handle* h, const ruviii_params* prm, int m1, int n, int n_ps
             }
             if (h->upd_impl == 2 && m1 > 0) update_tma_prepare(s.Y.p, s.ld, m1, s.tmap_y);
         }
-    }
-    // ---- peer-memory allreduce (one process per GPU): exchange buffers for the larger of the two matrices of the pass ----
-    // (latency-bound sizes only: a 20,000^2 gene-side Gram is bandwidth-bound and stays with NCCL's ring)
-    if (!skip && h->multi_process) {
-        const size_t lim = (size_t)8 << 20, cg = (size_t)h->gorder * h->gorder, ca = (size_t)h->rows_w * kp + (size_t)kp * kp + 1;
-        const size_t cap = std::max(cg <= lim ? cg : 0, ca <= lim ? ca : 0);
-        if (cap > 0) p2p_setup(h, cap + 2);
     }
     // ---- eigensolver: subspace iteration on every shard that runs it, cuSOLVER on global rank 0 only ----
     h->use_topk = false;

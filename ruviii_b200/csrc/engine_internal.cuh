@@ -117,6 +117,13 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t count = 0;
+    bool owned = true;            // false: p points into memory owned by somebody else (the peer-mapped exchange buffer)
+    void alias(T* q, size_t n) {
+        release();
+        p = q;
+        count = n;
+        owned = false;
+    }
     // The clear runs on the legacy default stream, which does NOT order against the engine's non-blocking streams: wait for
     // it, otherwise an asynchronous copy queued right after alloc() can be overwritten by the late memset.
     static void clear(void* q, size_t bytes) {
@@ -124,6 +131,7 @@ struct DevBuf {
         RUVIII_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
     }
     void alloc(size_t n, bool zero = true) {
+        if (!owned) { p = nullptr; count = 0; owned = true; }
         if (n <= count && p) {
             if (zero) clear(p, n * sizeof(T));
             return;
@@ -135,9 +143,10 @@ struct DevBuf {
         if (zero) clear(p, n * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         count = 0;
+        owned = true;
     }
 };
 
@@ -272,7 +281,8 @@ bool can_pipeline(ruviii_handle* h, const double* Y, const double* PS, const dou
 void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, const double* PS, int64_t ldPS, double* newY_out,
                             double* fullalpha_out, double* W_out);
 // p2p.cu
-bool p2p_setup(ruviii_handle* h, size_t cap_doubles);
+bool p2p_setup(ruviii_handle* h, size_t inbox_doubles, size_t mat_doubles);
+double* p2p_carve(ruviii_handle* h, size_t count);
 bool p2p_allreduce(ruviii_handle* h, double* buf, size_t count);
 void p2p_check(ruviii_handle* h);
 // engine_stage.cu

@@ -6,9 +6,9 @@
 // through NCCL) and runs a two-shot allreduce by posted P2P STORES only -- no remote loads on the critical path:
 //   phase 0  rank r pushes its contribution to slice q (the q-th 1/W of the elements) into rank q's inbox[r]    (W - 1 stores)
 //   signal / wait A   (system-scope counters in the owner's memory, one increment per CTA)
-//   phase 1  rank q adds the W contributions of its slice in rank order 0..W-1 (its own one straight from the source
-//            buffer) and pushes the sum into every rank's result area                                             (W stores)
-//   signal / wait B, then every rank copies the complete result over its source buffer (in place, like ncclAllReduce).
+//   phase 1  rank q adds the W contributions of its slice in rank order 0..W-1 (its own one straight from the matrix)
+//            and pushes the sum straight into every rank's copy of the matrix                                     (W - 1 stores)
+//   signal / wait B: the matrix (which lives in the exchange buffer, so that peers can store into it) is complete.
 // Every element is summed by exactly ONE rank in a FIXED order and then distributed, so all ranks hold the same bits -- which
 // is what lets every rank run the eigensolver redundantly instead of waiting for a broadcast (engine.cu).
 // Buffers alternate between two inbox parities, so a fast rank can start the next exchange while a slow one still reads.
@@ -19,19 +19,16 @@ namespace ruviii {
 
 namespace {
 
-constexpr int kP2PCtas = 32;
 constexpr int kP2PThreads = 256;
 constexpr int kMaxPeers = 8;
 
 struct P2PArgs {
-    double* inbox[kMaxPeers];        // rank q's inbox area of the current parity: W slots of `slice` doubles
-    double* result[kMaxPeers];       // rank q's result area
-    unsigned* flag_a[kMaxPeers];     // rank q's counters: [me] incremented by every CTA of mine
-    unsigned* flag_b[kMaxPeers];
+    unsigned char* base[kMaxPeers];  // mapped exchange buffer of every rank (base[me] is local)
+    size_t inbox_off;                // byte offset of the inbox area of the current parity: W slots of `slice` doubles
+    size_t buf_off;                  // byte offset of the matrix being reduced (the same in every rank's buffer)
     int W, me;
     int64_t count, slice;            // elements, elements per owner (multiple of 2)
-    unsigned target;                 // counter value every peer's slot reaches when all its CTAs of this call have signalled
-    double* buf;                     // local source, overwritten with the result
+    unsigned calls;                  // exchanges so far incl. this one: every rank's counter reaches it once per exchange
     int* error;                      // local: set when a wait timed out
 };
 
@@ -40,8 +37,13 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys(unsigned* p) {
-    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_relaxed_sys(unsigned* p) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -55,74 +57,98 @@ __device__ __forceinline__ bool wait_all(const unsigned* mine, int W, unsigned t
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
     if (threadIdx.x < W) {
+        // relaxed polls (an acquire at system scope on every iteration costs a fence each time), one acquire fence at the end
         const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(mine + threadIdx.x) - target) < 0) {
-            if (globaltimer_ns() - t0 > 4000000000ull) { ok = 0; *error = 1; break; }
+        unsigned spins = 0;
+        while ((int)(ld_relaxed_sys(mine + threadIdx.x) - target) < 0) {
+            if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { ok = 0; *error = 1; break; }
         }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
     __syncthreads();
     return ok != 0;
 }
 
+// One arrival per RANK crosses NVLink, not one per CTA: the CTAs of a rank meet at a local counter (each after a system-scope
+// fence of its own peer stores) and the last one to arrive signals every peer.  (With every CTA signalling every peer, 148
+// remote atomics per peer piled up on one address: the 1.6 MB exchange took 38 us on two GPUs against NCCL's 22, r2p2b.)
+__device__ __forceinline__ void signal_peers(const P2PArgs& a, size_t flag_off, size_t local_off, unsigned local_target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                      // this CTA's peer stores are performed
+        unsigned* local = reinterpret_cast<unsigned*>(a.base[a.me] + local_off);
+        const unsigned old = atomicAdd(local, 1u);
+        if (old + 1 == local_target) {                               // last CTA of this rank
+            // ONE system-scope fence, then the W increments as posted relaxed atomics (fence + relaxed write = a release
+            // pattern).  A release on each of them made every increment wait for the previous remote one to be performed:
+            // 8 x ~5 us per signal, 92 us for the 1.6 MB exchange on 8 GPUs against NCCL's 39 (r2p8).
+            __threadfence_system();
+            for (int q = 0; q < a.W; ++q) red_relaxed_sys(reinterpret_cast<unsigned*>(a.base[q] + flag_off) + a.me);
+        }
+    }
+}
+
+// flags (first 4 KB of every exchange buffer): [0, 1024) counters A, one unsigned per source rank, written by the peers;
+// [1024, 2048) local arrival counter A; [2048, 3072) counters B; [3072, 4096) local arrival counter B
 __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PArgs a) {
-    const int tid = threadIdx.x, cta = blockIdx.x, W = a.W, me = a.me;
+    const int tid = threadIdx.x, cta = blockIdx.x, nct = gridDim.x, W = a.W, me = a.me;
     const int64_t slice2 = a.slice / 2;                          // double2 elements per owner
-    const int64_t per = (slice2 + kP2PCtas - 1) / kP2PCtas;     // per CTA within a slice
+    const int64_t per = (slice2 + nct - 1) / nct;                // per CTA within a slice
     const int64_t v0 = (int64_t)cta * per, v1 = min(slice2, v0 + per);
-    const int64_t count2 = (a.count + 1) / 2;                    // buf is padded to an even element count by the caller
-    // ---- phase 0: push my contribution to every other owner's inbox ----
+    const int64_t count2 = (a.count + 1) / 2;                    // the buffers extend to an even element count
+    double2* mine = reinterpret_cast<double2*>(a.base[me] + a.buf_off);
+    // ---- phase 0: push my contribution to every other owner's inbox (posted stores over NVLink) ----
     for (int dq = 1; dq < W; ++dq) {
         const int q = (me + dq) % W;                             // staggered so that the ranks do not all hit the same peer first
-        const double2* src = reinterpret_cast<const double2*>(a.buf) + (int64_t)q * slice2;
-        double2* dst = reinterpret_cast<double2*>(a.inbox[q]) + (int64_t)me * slice2;
-        for (int64_t i = v0 + tid; i < v1; i += kP2PThreads)
-            if ((int64_t)q * slice2 + i < count2) dst[i] = src[i];
+        const double2* src = mine + (int64_t)q * slice2;
+        double2* dst = reinterpret_cast<double2*>(a.base[q] + a.inbox_off) + (int64_t)me * slice2;
+        const int64_t lim = min(v1, count2 - (int64_t)q * slice2);
+        int64_t i = v0 + tid;
+        for (; i + 3 * kP2PThreads < lim; i += 4 * kP2PThreads) {
+            const double2 x0 = src[i], x1 = src[i + kP2PThreads], x2 = src[i + 2 * kP2PThreads], x3 = src[i + 3 * kP2PThreads];
+            dst[i] = x0; dst[i + kP2PThreads] = x1; dst[i + 2 * kP2PThreads] = x2; dst[i + 3 * kP2PThreads] = x3;
+        }
+        for (; i < lim; i += kP2PThreads) dst[i] = src[i];
     }
-    __syncthreads();
-    if (tid < W && tid != me) { __threadfence_system(); red_release_sys(a.flag_a[tid] + me); }
-    if (tid == me) red_release_sys(a.flag_a[me] + me);
-    if (!wait_all(a.flag_a[me], W, a.target, a.error)) return;
-    // ---- phase 1: sum my slice in rank order, push the result everywhere ----
+    signal_peers(a, 0, 1024, a.calls * (unsigned)nct);
+    if (!wait_all(reinterpret_cast<unsigned*>(a.base[me]), W, a.calls, a.error)) return;
+    // ---- phase 1: sum my slice in rank order 0..W-1 and push the sum straight into every rank's copy of the matrix ----
     {
-        const double2* own = reinterpret_cast<const double2*>(a.buf) + (int64_t)me * slice2;
-        const double2* in = reinterpret_cast<const double2*>(a.inbox[me]);
-        for (int64_t i = v0 + tid; i < v1; i += kP2PThreads) {
-            if ((int64_t)me * slice2 + i >= count2) break;
+        double2* own = mine + (int64_t)me * slice2;
+        const double2* in = reinterpret_cast<const double2*>(a.base[me] + a.inbox_off);
+        const int64_t lim = min(v1, count2 - (int64_t)me * slice2);
+        for (int64_t i = v0 + tid; i < lim; i += kP2PThreads) {
             double2 s = make_double2(0.0, 0.0);
             for (int p = 0; p < W; ++p) {
                 const double2 v = p == me ? own[i] : __ldcg(in + (int64_t)p * slice2 + i);
                 s.x += v.x;
                 s.y += v.y;
             }
-            for (int q = 0; q < W; ++q) (reinterpret_cast<double2*>(a.result[q]) + (int64_t)me * slice2)[i] = s;
+            own[i] = s;
+            for (int dq = 1; dq < W; ++dq) {
+                const int q = (me + dq) % W;
+                (reinterpret_cast<double2*>(a.base[q] + a.buf_off) + (int64_t)me * slice2)[i] = s;
+            }
         }
     }
-    __syncthreads();
-    if (tid < W && tid != me) { __threadfence_system(); red_release_sys(a.flag_b[tid] + me); }
-    if (tid == me) { __threadfence(); red_release_sys(a.flag_b[me] + me); }
-    if (!wait_all(a.flag_b[me], W, a.target, a.error)) return;
-    // ---- copy the complete result over the source (this CTA's share of the whole array) ----
-    {
-        const int64_t per_all = (count2 + kP2PCtas - 1) / kP2PCtas;
-        const int64_t c0 = (int64_t)cta * per_all, c1 = min(count2, c0 + per_all);
-        const double2* res = reinterpret_cast<const double2*>(a.result[me]);
-        double2* out = reinterpret_cast<double2*>(a.buf);
-        for (int64_t i = c0 + tid; i < c1; i += kP2PThreads) out[i] = __ldcg(res + i);
-    }
+    signal_peers(a, 2048, 3072, a.calls * (unsigned)nct);
+    wait_all(reinterpret_cast<unsigned*>(a.base[me] + 2048), W, a.calls, a.error);
 }
 
 }  // namespace
 
 struct P2PState {
-    void* xbuf = nullptr;            // [flags 4 KB | inbox parity 0 | inbox parity 1 | result], each area `cap` doubles
-    size_t cap = 0;                  // doubles per area
+    void* xbuf = nullptr;            // [flags 4 KB | inbox parity 0 | inbox parity 1 | matrix areas ...]
+    size_t cap_inbox = 0;            // doubles per inbox area
+    size_t cap_mat = 0;              // doubles of the matrix areas together
+    size_t mat_used = 0;             // doubles handed out by p2p_carve since the last setup
     void* peer[kMaxPeers] = {};      // mapped exchange buffers of all ranks (peer[me] = xbuf)
     DevBuf<unsigned char> handles;   // W x 64 bytes, gathered
     int* h_error = nullptr;          // pinned, mapped: the kernel writes it only when a wait times out; the host reads it directly
     int* d_error = nullptr;
     unsigned calls = 0;              // exchanges done so far (the same on every rank)
+    int n_ctas = 64;
     bool ready = false;
-    int device = 0;
     ~P2PState() {
         for (int i = 0; i < kMaxPeers; ++i)
             if (peer[i] && peer[i] != xbuf) cudaIpcCloseMemHandle(peer[i]);
@@ -132,17 +158,21 @@ struct P2PState {
 };
 void p2p_state_destroy(P2PState* p) { delete p; }
 
-// (Re)creates the exchange buffers for `cap_doubles` per area and swaps the IPC handles.  COLLECTIVE: every rank calls it from
-// do_plan with the same argument.  Returns false (and leaves NCCL in charge) when peer mapping is not possible.
-bool p2p_setup(ruviii_handle* h, size_t cap_doubles) {
+// (Re)creates the exchange buffer -- inboxes of `inbox_doubles` each and `mat_doubles` for the matrices that are reduced in
+// place (they LIVE in the exchange buffer, p2p_carve, so that a peer can store into them) -- and swaps the IPC handles.
+// COLLECTIVE: every rank calls it from do_plan with the same arguments.  Returns false (NCCL stays in charge) when peer
+// mapping is not possible.
+bool p2p_setup(ruviii_handle* h, size_t inbox_doubles, size_t mat_doubles) {
     static const bool off = env_int("RUVIII_P2P", 1) == 0;
     if (off || !h->multi_process || h->world < 2 || h->world > kMaxPeers) return false;
     Shard& s = h->shards[0];
     RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
     if (!h->p2p) h->p2p = new P2PState();
     P2PState& st = *h->p2p;
-    cap_doubles = (size_t)round_up((int64_t)cap_doubles + 2 * h->world, 512);
-    if (st.ready && cap_doubles <= st.cap) return true;
+    inbox_doubles = (size_t)round_up((int64_t)inbox_doubles + 2 * h->world, 512);
+    mat_doubles = (size_t)round_up((int64_t)mat_doubles + 64, 512);
+    st.mat_used = 0;
+    if (st.ready && inbox_doubles <= st.cap_inbox && mat_doubles <= st.cap_mat) return true;
     // every rank reaches this point with the same capacities (they derive from the plan), so all of them reallocate together
     sync_all(h);
     for (int i = 0; i < kMaxPeers; ++i) {
@@ -152,8 +182,8 @@ bool p2p_setup(ruviii_handle* h, size_t cap_doubles) {
     if (st.xbuf) { cudaFree(st.xbuf); st.xbuf = nullptr; }
     st.ready = false;
     st.calls = 0;
-    st.device = s.device;
-    const size_t bytes = 4096 + 3 * cap_doubles * sizeof(double);
+    st.n_ctas = std::max(8, std::min(h->n_sms, env_int("RUVIII_P2P_CTAS", h->n_sms)));
+    const size_t bytes = 4096 + (2 * inbox_doubles + mat_doubles) * sizeof(double);
     int ok_local = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -195,39 +225,50 @@ bool p2p_setup(ruviii_handle* h, size_t cap_doubles) {
     RUVIII_CUDA_CHECK(cudaStreamSynchronize(s.stream));
     RUVIII_CUDA_CHECK(cudaMemcpy(&flag, agree.p, 8, cudaMemcpyDeviceToHost));
     agree.release();
-    st.cap = cap_doubles;
+    st.cap_inbox = inbox_doubles;
+    st.cap_mat = mat_doubles;
     st.ready = flag == 0.0;
     return st.ready;
 }
 
-// In-place sum over all ranks of `count` doubles at `buf` (device memory of this rank; the allocation must extend to an even
-// element count).  Returns false when the P2P route is not set up or too small: the caller then uses NCCL.
+// `count` doubles of the exchange buffer's matrix area (zeroed), or nullptr when the route is not available / the area is full
+double* p2p_carve(ruviii_handle* h, size_t count) {
+    P2PState* st = h->p2p;
+    if (!st || !st->ready) return nullptr;
+    count = (size_t)round_up((int64_t)count + 2, 64);
+    if (st->mat_used + count > st->cap_mat) return nullptr;
+    double* p = reinterpret_cast<double*>(static_cast<unsigned char*>(st->xbuf) + 4096) + 2 * st->cap_inbox + st->mat_used;
+    st->mat_used += count;
+    RUVIII_CUDA_CHECK(cudaMemset(p, 0, count * sizeof(double)));
+    RUVIII_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    return p;
+}
+
+// In-place sum over all ranks of `count` doubles at `buf`, which must lie in the exchange buffer's matrix area (p2p_carve).
+// Returns false when it does not, or the route is not set up: the caller then uses NCCL.
 bool p2p_allreduce(ruviii_handle* h, double* buf, size_t count) {
     P2PState* st = h->p2p;
     if (!st || !st->ready || !h->multi_process) return false;
     const int W = h->world;
     const int64_t slice = round_up(ceil_div((int64_t)count, W), 2);
-    if ((size_t)slice * W > st->cap) return false;
+    if ((size_t)slice * W > st->cap_inbox) return false;
+    unsigned char* base = static_cast<unsigned char*>(st->xbuf);
+    unsigned char* mat0 = base + 4096 + 2 * st->cap_inbox * sizeof(double);
+    unsigned char* b = reinterpret_cast<unsigned char*>(buf);
+    if (b < mat0 || b + (count + 1) * sizeof(double) > mat0 + st->cap_mat * sizeof(double)) return false;
     Shard& s = h->shards[0];
     P2PArgs a{};
     a.W = W;
     a.me = h->rank0;
     a.count = (int64_t)count;
     a.slice = slice;
-    a.buf = buf;
     a.error = st->d_error;
     st->calls += 1;
-    a.target = st->calls * (unsigned)kP2PCtas;
-    const int parity = (int)(st->calls & 1u);
-    for (int r = 0; r < W; ++r) {
-        unsigned char* base = static_cast<unsigned char*>(st->peer[r]);
-        a.flag_a[r] = reinterpret_cast<unsigned*>(base);
-        a.flag_b[r] = reinterpret_cast<unsigned*>(base + 2048);
-        double* areas = reinterpret_cast<double*>(base + 4096);
-        a.inbox[r] = areas + (size_t)parity * st->cap;
-        a.result[r] = areas + 2 * st->cap;
-    }
-    p2p_allreduce_kernel<<<kP2PCtas, kP2PThreads, 0, s.stream>>>(a);
+    a.calls = st->calls;
+    a.inbox_off = 4096 + (size_t)(st->calls & 1u) * st->cap_inbox * sizeof(double);
+    a.buf_off = (size_t)(b - base);
+    for (int r = 0; r < W; ++r) a.base[r] = static_cast<unsigned char*>(st->peer[r]);
+    p2p_allreduce_kernel<<<st->n_ctas, kP2PThreads, 0, s.stream>>>(a);
     RUVIII_LAUNCH_CHECK();
     return true;
 }
