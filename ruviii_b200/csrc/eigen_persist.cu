@@ -51,7 +51,7 @@ struct PersistArgs {
     int kk, kp, n_keep;
     int ldg;                      // row pitch of the shared-memory copy of this CTA's rows of G (GS kernels)
     double tol;
-    int max_iter, first, period, cheb, chol32, jac32;
+    int max_iter, first, period, cheb;
     unsigned* bar;                // [0] barrier counter, [1] exit counter
     int* state;                   // [0] converged, [1] G products, [2] Cholesky breakdown, [3] Jacobi sweeps, [4] RR count,
                                   // [5] second CholQR rounds, [6] Chebyshev products
@@ -204,41 +204,6 @@ __device__ __forceinline__ void reduce_phase(const PersistArgs& a, int len, Smem
 // One warp, lane i holds row i of the scaled matrix in registers; right-looking, column j of L travels by shuffles, so the
 // 32 dependent steps cost one rsqrt + two shuffles + one FMA of latency each and no CTA barrier (a CTA-wide version with
 // one barrier per column measured 35 k cycles per factorisation, five times the product with G).
-// Single-precision variant for the passes whose orthogonalisation only has to keep the block well conditioned (the span of
-// Q = Z D L^-T does not depend on how accurate L is; only the pass right before a Rayleigh-Ritz step needs Q'Q = I to
-// rounding).  FP32 operations have a quarter of the FP64 latency here (4 vs ~27 cycles per dependent operation), and the
-// factorisation is a chain of 32 x ~10 of them.  A pivot below 1e-5 (the scaled matrix is too ill conditioned for single
-// precision: the first product of the random start block) sets sm.bad = -1 and the caller repeats the phase in FP64.
-__device__ __forceinline__ void cholesky_phase_f32(Smem& sm) {
-    const int tid = threadIdx.x;
-    if (tid < PB) {
-        const unsigned full = 0xffffffffu;
-        const int i = tid;
-        const double sii = sm.S[i][i];
-        const double di = sii > 0.0 ? rsqrt(sii) : 1.0;
-        sm.dscale[i] = di;
-        __syncwarp();
-        float a[PB];
-#pragma unroll
-        for (int c = 0; c < PB; ++c) a[c] = (float)(0.5 * (sm.S[i][c] + sm.S[c][i]) * di * sm.dscale[c]);
-        int bad = 0;
-        float minp = 1.0f;
-#pragma unroll
-        for (int j = 0; j < PB; ++j) {
-            const float pj = __shfl_sync(full, a[j], j);
-            float rd = rsqrtf(pj);
-            if (!(pj > 1e-5f)) { bad = -1; rd = 1.0f; }
-            minp = fminf(minp, pj);
-            const float lij = a[j] * rd;
-            sm.L[i][j] = i > j ? (double)lij : (i == j ? (double)rd : 0.0);
-#pragma unroll
-            for (int c = j + 1; c < PB; ++c) a[c] = fmaf(-lij, __shfl_sync(full, lij, c), a[c]);
-        }
-        if (i == 0) { sm.bad = bad; sm.minp = (double)minp; }
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ void cholesky_phase(Smem& sm) {
     const int tid = threadIdx.x;
     if (tid < PB) {
@@ -303,7 +268,7 @@ __device__ __forceinline__ void store_rows(const PersistArgs& a, double* __restr
 // of A, that of pair ia comes by shuffle from lane ia of the same warp (lane l holds pair l % 16), and the rotated block
 // is written to the OTHER copy of A, so nothing read in a round is written in it.  (The version with a 16-thread
 // rotation phase and two barriers per round cost 1,200 cycles per round, 93 us for the 5 sweeps of C3.)
-__device__ __forceinline__ int jacobi_phase(Smem& sm, int jac32) {
+__device__ __forceinline__ int jacobi_phase(Smem& sm) {
     const int tid = threadIdx.x;
     const int ia = tid / (PB / 2), ib = tid % (PB / 2);
     double (*Ab[2])[PS] = {sm.A, sm.L};
@@ -328,34 +293,13 @@ __device__ __forceinline__ int jacobi_phase(Smem& sm, int jac32) {
             const double x00 = A[pa][pb], x01 = A[pa][qb], x10 = A[qa][pb], x11 = A[qa][qb];
             double cb = 1.0, sb = 0.0;
             if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
+                // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
                 const double zeta = aqq - app, beta = 2.0 * apq;
-                if (jac32) {
-                    // The rotation ANGLE only has to be good to single precision (what it leaves of a_pq, ~1e-7 |a_pq|, goes in
-                    // the next sweep); the ROTATION has to be orthogonal to double precision.  So: tan(theta) =
-                    // sgn(zeta) beta / (|zeta| + sqrt(zeta^2 + beta^2)) in FP32 on operands scaled by a power of two, then
-                    // c = (1 + t^2)^-1/2 from an FP32 seed and two Newton steps in FP64, s = t c.  Half the dependent FP64
-                    // operations of the all-FP64 form (two library rsqrt).
-                    const double mx = fmax(fabs(zeta), fabs(beta));
-                    const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
-                    const double sc = __hiloint2double((2046 - min(max(ex, 1), 2045)) << 20, 0);        // 2^(1023 - ex)
-                    const float zf = (float)(zeta * sc), bf = (float)(beta * sc);
-                    const float rr = sqrtf(fmaf(zf, zf, bf * bf));
-                    float tf = __fdividef(bf, fabsf(zf) + rr);
-                    tf = zeta >= 0.0 ? tf : -tf;
-                    const double t = (double)tf, x = fma(t, t, 1.0);
-                    double y = (double)rsqrtf((float)x);
-                    y = y * fma(-0.5 * x, y * y, 1.5);
-                    y = y * fma(-0.5 * x, y * y, 1.5);
-                    cb = y;
-                    sb = t * y;
-                } else {
-                    // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
-                    const double irr = rsqrt(fma(zeta, zeta, beta * beta));
-                    const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
-                    const double ic = rsqrt(c2);
-                    cb = c2 * ic;
-                    sb = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
-                }
+                const double irr = rsqrt(fma(zeta, zeta, beta * beta));
+                const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
+                const double ic = rsqrt(c2);
+                cb = c2 * ic;
+                sb = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
                 if (ia == 0) {
                     sm.flag = 1;
                     if (apq * apq > 1e-20 * fabs(app * aqq)) sm.flag_big = 1;
@@ -444,7 +388,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
 
     // One round of column-scaled Cholesky QR of the rows in `src` (partials -> reduce -> Cholesky -> substitution);
     // with `have_S` the reduced S is already in sm.S.  Leaves Q_blk in sm.Q; returns false on a Cholesky breakdown.
-    auto ortho = [&](const double (*src)[PS], bool have_S, bool precise) -> bool {
+    auto ortho = [&](const double (*src)[PS], bool have_S) -> bool {
         for (int round = 0; round < 2; ++round) {
             if (!(round == 0 && have_S)) {
                 partials_phase(a, round == 0 ? src : sm.Q, false, sm);
@@ -456,12 +400,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = __ldcg(a.Pred + e);
                 __syncthreads();
             }
-            if (precise || !a.chol32) {
-                cholesky_phase(sm);
-            } else {
-                cholesky_phase_f32(sm);
-                if (sm.bad < 0) cholesky_phase(sm);              // too ill conditioned for single precision
-            }
+            cholesky_phase(sm);
             trace_mark(a, ntrace, PH_CHOL);
             if (sm.bad) return false;
             apply_phase(a, round == 0 ? src : sm.Q, sm);
@@ -506,7 +445,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
         trace_mark(a, ntrace, PH_PRODUCT);
         const bool rr = it >= next_rr;
         if (!rr) {
-            ok = ortho(sm.Z, false, it + 1 >= next_rr);          // the block of a Rayleigh-Ritz product must be orthonormal to rounding
+            ok = ortho(sm.Z, false);
             if (!ok) break;
             store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
             gbar();
@@ -528,7 +467,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 sm.A[i][j] = 0.5 * (sm.L[i][j] + sm.L[j][i]);
             }
             __syncthreads();
-            const int sweeps = jacobi_phase(sm, a.jac32);
+            const int sweeps = jacobi_phase(sm);
             for (int e = tid; e < PB * PB; e += PT) __stcg(a.Vm + e, sm.V[e / PB][e % PB]);
             if (tid < PB) __stcg(a.theta + tid, sm.th[tid]);
             if (tid == 0) a.state[3] = sweeps;
@@ -635,7 +574,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             __syncthreads();
             for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = sm.L[e / PB][e % PB];
             __syncthreads();
-            ok = ortho(sm.Z, true, a.period <= 1);
+            ok = ortho(sm.Z, true);
             next_rr = it + a.period;
         } else {
             const double need = log(fmax(10.0 * worst / (a.tol * th0), 2.0));
@@ -678,7 +617,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 gain += log(cosh((double)d * ak));
                 for (int e = tid; e < RB * PB; e += PT) { const int r = e / PB, c = e - r * PB; sm.Z[r][c] = sm.Q[r][c]; }
                 __syncthreads();
-                ok = ortho(sm.Z, false, !(gain < need && it < a.max_iter));   // the last round feeds the Rayleigh-Ritz product
+                ok = ortho(sm.Z, false);
                 if (!ok) break;
             }
             next_rr = it + 1;                                // Rayleigh-Ritz right after the next product
@@ -772,10 +711,6 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
     a.first = std::max(2, first_env > 0 ? first_env : 6);   // the start block is not orthonormal: no Rayleigh-Ritz on pass 1
     a.period = 3;
     a.cheb = cheb_env;
-    static const int chol32_env = [] { const char* v = std::getenv("RUVIII_EIG_CHOL32"); return v && *v ? std::atoi(v) : 1; }();
-    static const int jac32_env = [] { const char* v = std::getenv("RUVIII_EIG_JAC32"); return v && *v ? std::atoi(v) : 1; }();
-    a.chol32 = chol32_env;
-    a.jac32 = jac32_env;
     a.bar = reinterpret_cast<unsigned*>(w.state + 8);
     a.state = w.state;
     // RB = 8: the CTA's 8 rows of G (8 R doubles, pitch = 4 mod 16 doubles so that the 8 x 4 fragment loads of a warp spread
