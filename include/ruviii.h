@@ -231,6 +231,19 @@ int ruviii_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1
 int ruviii_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, const double* covariate,
                          double* rho_out, float* ms_out);
 
+/* regress.out.uv.variables / regress.out.bio.variables: supervisedFindNCG.R:111-133,
+ *     y <- lm(t(expr.data) ~ se.obj$v1 + se.obj$v2 + ...);  expr.data.reg <- t(y$residuals)
+ * X / slot / apply_log as in ruviii_pca.  design: the m1 x p model matrix of the formula, row-major, HOST memory (intercept
+ * column, treatment dummies of every factor, the continuous variables as they are): residuals depend on its column space only.
+ * The device builds an orthonormal basis with lm's own rank rule (a column whose norm falls below 1e-7 of its original norm
+ * once the earlier columns are removed is aliased and dropped; *rank_out = columns kept) and removes it from every gene.
+ * The residuals (m1 x n) stay on the device: ruviii_gene_stats / ruviii_gene_spearman read them with X = NULL, slot = -2
+ * until the next ruviii_regress_out; residuals_out (NULL, or m1 x n row-major with pitch ld_out) also receives them.
+ * p <= 256 and p < m1. */
+int ruviii_regress_out(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+                       double pseudo_count, const double* design, int32_t p, double* residuals_out, int64_t ld_out, int32_t* rank_out,
+                       float* ms_out);
+
 /* ---- the six primitives RcppExports.R:4-26 declares, backed by the same device kernels ------------------
  * Column-major (R) matrices, host pointers.  fastResidop(A, B) = A - B (B'B)^-1 B'A where B is a 0/1
  * replicate matrix (fastruvIII.R:88-95): B is passed as its factor codes. */

@@ -50,22 +50,45 @@ def rank_average(x):
     return (0.5 * (starts + ends - 1) + 1.0)[inv]
 
 
-def supervised_find_ncg(assay, col_data, bio_variables, uv_variables, no_ncg, apply_log=True, pseudo_count=1.0, corr_method="pearson"):
-    """The default-configuration flow of supervisedFindNCG.R:148-357 (see ruviii_b200/ncg.py for the two quirks)."""
+def lm_residuals(expr, col_data, variables):
+    """t(lm(t(expr) ~ v1 + v2 + ...)$residuals), supervisedFindNCG.R:111-133: least squares by SVD (numpy.linalg.lstsq: the
+    minimum-norm solution, so a rank-deficient model matrix gives the residuals lm's pivoted QR gives).  expr: genes x samples."""
+    m = expr.shape[1]
+    cols = [np.ones(m)]
+    for v in variables:
+        c = col_data[v]
+        if all(isinstance(t, str) for t in c):
+            c = np.asarray(c)
+            cols += [(c == lev).astype(np.float64) for lev in sorted(set(c.tolist()))[1:]]
+        else:
+            cols.append(np.asarray(c, dtype=np.float64))
+    D = np.stack(cols, axis=1)
+    beta = np.linalg.lstsq(D, expr.T, rcond=1e-10)[0]
+    return (expr.T - D @ beta).T
+
+
+def supervised_find_ncg(assay, col_data, bio_variables, uv_variables, no_ncg, apply_log=True, pseudo_count=1.0, corr_method="pearson",
+                        regress_out_uv=False, regress_out_bio=False):
+    """The flow of supervisedFindNCG.R:104-357 without apply.normalization (see ruviii_b200/ncg.py for the quirks)."""
     correls_pearson = globals()["correls_spearman" if corr_method == "spearman" else "correls_pearson"]
     expr = np.log2(np.asarray(assay, dtype=np.float64) + pseudo_count) if apply_log else np.asarray(assay, dtype=np.float64)
+    uv_data = bio_data = expr
+    if regress_out_uv:                                                        # :111-121 -> used by the biology tests (:248-254)
+        bio_data = lm_residuals(expr, col_data, uv_variables)
+    elif regress_out_bio:                                                     # :122-133 -> used by the UV tests (:163-167)
+        uv_data = lm_residuals(expr, col_data, bio_variables)
     is_cat = lambda v: all(isinstance(t, str) for t in col_data[v])
     ranks = []
     for v in [u for u in uv_variables if is_cat(u)]:
         g = np.asarray(col_data[v])
         lev, cnt = np.unique(g, return_counts=True)
         keep = ~np.isin(g, lev[cnt < 3])
-        ranks.append(rank_average(row_oneway_equalvar_statistic(expr[:, keep], g[keep])))
+        ranks.append(rank_average(row_oneway_equalvar_statistic(uv_data[:, keep], g[keep])))
     for v in [u for u in uv_variables if not is_cat(u)]:
-        ranks.append(rank_average(np.abs(np.round(correls_pearson(col_data[v], expr.T), 2))))
+        ranks.append(rank_average(np.abs(np.round(correls_pearson(col_data[v], uv_data.T), 2))))
     for v in [b for b in bio_variables if not is_cat(b)]:
-        ranks.append(rank_average(-np.abs(np.round(correls_pearson(col_data[v], expr.T), 2))))
+        ranks.append(rank_average(-np.abs(np.round(correls_pearson(col_data[v], bio_data.T), 2))))
     for v in [b for b in bio_variables if is_cat(b)]:
-        ranks.append(rank_average(-row_oneway_equalvar_statistic(expr, np.asarray(col_data[v]))))
+        ranks.append(rank_average(-row_oneway_equalvar_statistic(bio_data, np.asarray(col_data[v]))))
     prod = np.prod(np.stack(ranks, axis=1), axis=1)
     return rank_average(-prod) < no_ncg + 1

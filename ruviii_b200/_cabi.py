@@ -20,7 +20,7 @@ MODE_STACKED, MODE_FAST = 0, 1
 SYMBOLS = [
     "ruviii_abi_version", "ruviii_device_count", "ruviii_create", "ruviii_nccl_unique_id", "ruviii_create_rank",
     "ruviii_destroy", "ruviii_last_error", "ruviii_normalise", "ruviii_normalise_blocks", "ruviii_plan", "ruviii_upload", "ruviii_run",
-    "ruviii_download", "ruviii_download_averaged", "ruviii_download_replicate_data", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats", "ruviii_gene_spearman",
+    "ruviii_download", "ruviii_download_averaged", "ruviii_download_replicate_data", "ruviii_host_alloc", "ruviii_host_free", "ruviii_barrier", "ruviii_eigenvalues", "ruviii_set_fullalpha", "ruviii_set_eta", "ruviii_prps", "ruviii_set_prps_sets", "ruviii_pca", "ruviii_gene_stats", "ruviii_gene_spearman", "ruviii_regress_out",
     "ruviii_fast_residop", "ruviii_probe", "ruviii_mat_mult", "ruviii_mat_subtract", "ruviii_mat_transpose", "ruviii_mat_inverse",
 ]
 
@@ -102,6 +102,8 @@ def load_library():
     lib.ruviii_set_prps_sets.argtypes = [H, vp, vp, C.c_int32]
     lib.ruviii_gene_stats.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
     lib.ruviii_gene_spearman.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
+    lib.ruviii_regress_out.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, vp, C.c_int32, vp, C.c_int64,
+                                       vp, vp]
     lib.ruviii_pca.argtypes = [H, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                C.c_int32, vp, vp, vp, vp]
     lib.ruviii_fast_residop.argtypes = [H, vp, C.c_int32, C.c_int32, vp, vp]
@@ -186,6 +188,7 @@ class Engine:
         if rc != OK:
             raise RuviiiError(rc, self._lib.ruviii_last_error(None).decode())
         self._plan = None
+        self._regressed = None
 
     @staticmethod
     def nccl_unique_id():
@@ -298,12 +301,39 @@ class Engine:
         return dict(u=u, d=d, v=None if v is None else v.T, stage_ms=dict(zip(
             ["upload_log", "center", "gram", "eigen", "project", "total"], [float(x) for x in ms])))
 
+    def regress_out(self, X=None, design=None, slot=-1, apply_log=False, pseudo_count=1.0, return_residuals=False):
+        """K12 + K4 + K6: residuals of lm(X ~ design) for every gene (supervisedFindNCG.R:111-133).  ``design``: samples x p model
+        matrix.  The residuals stay on the device -- ``gene_stats`` / ``gene_spearman`` read them with ``slot=-2`` -- and are
+        also returned (samples x genes) with ``return_residuals``.  Returns dict(rank, ms[, residuals])."""
+        D = np.ascontiguousarray(design, dtype=np.float64)
+        if D.ndim != 2:
+            raise RuviiiError(ERR_INVALID, "design must be a samples x p matrix")
+        if X is not None:
+            X = _rowmajor(X, "X")
+            m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        else:
+            m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
+        if D.shape[0] != m1:
+            raise RuviiiError(ERR_INVALID, "design needs one row per sample")
+        res = np.empty((m1, n), dtype=np.float64) if return_residuals else None
+        rank, ms = C.c_int32(0), C.c_float(0.0)
+        self._check(self._lib.ruviii_regress_out(self._h, ptr, ldx, m1, n, int(slot), int(bool(apply_log)), float(pseudo_count), _ptr(D),
+                                                 D.shape[1], None if res is None else _ptr(res), n, C.cast(C.byref(rank), C.c_void_p),
+                                                 C.cast(C.byref(ms), C.c_void_p)))
+        self._regressed = (m1, n)
+        out = dict(rank=int(rank.value), ms=float(ms.value))
+        if res is not None:
+            out["residuals"] = res
+        return out
+
     def gene_stats(self, X=None, groups=None, covariate=None, slot=-1, apply_log=False, pseudo_count=1.0):
         """K11: per-gene one-way ANOVA F across ``groups`` (ids < 0 are left out) and / or Pearson correlation with
         ``covariate`` (supervisedFindNCG.R:179-191,214-229).  Returns dict(F, r, ms)."""
         if X is not None:
             X = _rowmajor(X, "X")
             m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        elif slot == -2:
+            (m1, n), ldx, ptr = self._regressed, 0, None
         else:
             m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
         g = None if groups is None else np.ascontiguousarray(groups, dtype=np.int32)
@@ -324,6 +354,8 @@ class Engine:
         if X is not None:
             X = _rowmajor(X, "X")
             m1, n, ldx, ptr = X.shape[0], X.shape[1], X.strides[0] // 8, _ptr(X)
+        elif slot == -2:
+            (m1, n), ldx, ptr = self._regressed, 0, None
         else:
             m1, n, ldx, ptr = self._plan["m1"], self._plan["n"], 0, None
         c = np.ascontiguousarray(covariate, dtype=np.float64)

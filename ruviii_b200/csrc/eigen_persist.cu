@@ -20,6 +20,7 @@
 //
 // Convergence is decided on the device; the host never waits inside the solve.  Deterministic: fixed start block, fixed
 // summation orders, no floating-point atomics (the barrier counter is the only atomic).
+#include <cstddef>
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -51,7 +52,7 @@ struct PersistArgs {
     int kk, kp, n_keep;
     int ldg;                      // row pitch of the shared-memory copy of this CTA's rows of G (GS kernels)
     double tol;
-    int max_iter, first, period, cheb;
+    int max_iter, first, period, cheb, jorder;
     unsigned* bar;                // [0] barrier counter, [1] exit counter
     int* state;                   // [0] converged, [1] G products, [2] Cholesky breakdown, [3] Jacobi sweeps, [4] RR count,
                                   // [5] second CholQR rounds, [6] Chebyshev products
@@ -200,6 +201,14 @@ __device__ __forceinline__ void reduce_phase(const PersistArgs& a, int len, Smem
     }
 }
 
+// 1 / sqrt(x) for a normal, positive x: the hardware seed and one cubic step (error^3), no range branch.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
 // ---- column-scaled Cholesky of sm.S (B x B): L with 1 / L[j][j] on the diagonal, sm.dscale, sm.minp, sm.bad ------------
 // One warp, lane i holds row i of the scaled matrix in registers; right-looking, column j of L travels by shuffles, so the
 // 32 dependent steps cost one rsqrt + two shuffles + one FMA of latency each and no CTA barrier (a CTA-wide version with
@@ -221,7 +230,7 @@ __device__ __forceinline__ void cholesky_phase(Smem& sm) {
 #pragma unroll
         for (int j = 0; j < PB; ++j) {
             const double pj = __shfl_sync(full, a[j], j);
-            double rd = rsqrt(pj);
+            double rd = rsqrt_fast(pj);
             if (!(pj > 1e-30)) { bad = j + 1; rd = 1.0; }
             minp = fmin(minp, pj);
             const double lij = a[j] * rd;                    // L[i][j] for i >= j
@@ -262,89 +271,143 @@ __device__ __forceinline__ void store_rows(const PersistArgs& a, double* __restr
 }
 
 // ---- H (sm.A, symmetric B x B) = V diag(theta) V': parallel cyclic Jacobi, round-robin pairing -------------------------
-// Result: sm.V = V with its columns sorted by descending theta, sm.th = theta.  One CTA; uses sm.L and sm.S as scratch.
-// One CTA barrier per round: thread (ia, ib) owns the 2 x 2 block rows (pair ia) x columns (pair ib) of A and rows
-// 2 ia, 2 ia + 1 x columns (pair ib) of V; the rotation of pair ib is computed by the lane itself from the CURRENT copy
-// of A, that of pair ia comes by shuffle from lane ia of the same warp (lane l holds pair l % 16), and the rotated block
-// is written to the OTHER copy of A, so nothing read in a round is written in it.  (The version with a 16-thread
-// rotation phase and two barriers per round cost 1,200 cycles per round, 93 us for the 5 sweeps of C3.)
-__device__ __forceinline__ int jacobi_phase(Smem& sm) {
+// Result: sm.V = V with its columns sorted by descending theta, sm.th = theta.  One CTA; sm.A and sm.L are the two copies of
+// the matrix, one CTA barrier per round.
+//
+// The phase is bound by shared-memory bandwidth, not by the rotation's latency chain (scripts/jacobi_probe.cu: with A and V
+// as 32 x 33 arrays indexed by the pair of the round, a round moved 39 KB through a 128 B/clk pipe with 2-4-way bank conflicts
+// on the pair-indexed accesses: 950-1,190 cycles, 150-184 k cycles for the five sweeps of C3).  So the matrix lives in "chair"
+// order, as in a Brent-Luk systolic array: the 32 indices sit on chairs T[0..15] (top row) and B[0..15] (bottom row), pair i is
+// (T[i], B[i]) in EVERY round, and after a round the values move one chair round the circle (T[0] stays):
+//     T[i] -> T[i+1] (1 <= i <= 14),  T[15] -> B[15],  B[i] -> B[i-1] (i >= 1),  B[0] -> T[1].
+// Thread (ia, ib) always owns rows (T[ia], B[ia]) x columns (T[ib], B[ib]):
+//   * A is four 16 x 16 planes (row side, column side); the thread reads plane[.][.][ia][ib] -- lanes of a half-warp are
+//     consecutive in ib, no bank conflict -- and writes each rotated entry to the chair it moves to (ib +- 1: again consecutive);
+//   * the rotation of pair ib comes from the diagonal entries plane[.][.][ib][ib] (pitch 16: ib * 17, conflict-free), that of
+//     pair ia by shuffle from lane ia (lane l holds pair l % 16);
+//   * V (rows 2 ia, 2 ia + 1 x the two chairs of pair ib) stays in REGISTERS: its columns move to the neighbouring lane of the
+//     same half-warp by shuffle, it never touches shared memory until the end.
+// 1 / sqrt via rsqrt_fast, the rotation computed unconditionally and selected (no branch in the round).
+#ifndef RUVIII_JSTAMP
+#define RUVIII_JSTAMP(k)          // scripts/jacobi_probe.cu defines these to time the sections of a round
+#define RUVIII_JSTAMP_DECL
+#define RUVIII_JSTAMP_FLUSH
+#endif
+
+__device__ __forceinline__ int jacobi_phase(Smem& sm, int jorder = 0) {
+    constexpr int H = PB / 2;                                    // pairs (16)
+    constexpr int PL = H * H;                                    // doubles per plane
+    static_assert(4 * PL <= PB * PS, "the four planes must fit one B x (B + 1) array");
     const int tid = threadIdx.x;
-    const int ia = tid / (PB / 2), ib = tid % (PB / 2);
-    double (*Ab[2])[PS] = {sm.A, sm.L};
-    double (*Vacc)[PS] = sm.S;
-    for (int e = tid; e < PB * PB; e += PT) Vacc[e / PB][e % PB] = (e / PB == e % PB) ? 1.0 : 0.0;
+    const int ia = tid / H, ib = tid % H;
+    double* const buf0 = &sm.A[0][0];
+    constexpr int dAL = (int)((offsetof(Smem, L) - offsetof(Smem, A)) / sizeof(double));
+    RUVIII_JSTAMP_DECL
+    // chair (side s, position i) starts with index idx(s, i); plane (sr, sc) at (2 sr + sc) * PL
+    auto idx = [jorder](int s_, int i) { return jorder == 1 ? (s_ ? PB - 1 - i : i) : jorder == 2 ? (s_ ? H + i : i) : 2 * i + s_; };
+    const int ra0 = idx(0, ia), ra1 = idx(1, ia), cb0 = idx(0, ib), cb1 = idx(1, ib);
+    {
+        const double h00 = sm.A[ra0][cb0], h01 = sm.A[ra0][cb1];
+        const double h10 = sm.A[ra1][cb0], h11 = sm.A[ra1][cb1];
+        double* b1 = buf0 + dAL;
+        b1[0 * PL + ia * H + ib] = h00;
+        b1[1 * PL + ia * H + ib] = h01;
+        b1[2 * PL + ia * H + ib] = h10;
+        b1[3 * PL + ia * H + ib] = h11;
+    }
+    // V = I in chair order: v[u][s] = V[row 2 ia + u][chair (s, ib)]
+    double vt0 = (2 * ia == cb0) ? 1.0 : 0.0, vb0 = (2 * ia == cb1) ? 1.0 : 0.0;
+    double vt1 = (2 * ia + 1 == cb0) ? 1.0 : 0.0, vb1 = (2 * ia + 1 == cb1) ? 1.0 : 0.0;
+    // where this thread's four entries move: next chair of T[i] / B[i] as (side, index)
+    const int ntS_a = ia == H - 1 ? 1 : 0, ntI_a = ia == 0 ? 0 : (ia == H - 1 ? H - 1 : ia + 1);
+    const int nbS_a = ia == 0 ? 0 : 1,     nbI_a = ia == 0 ? 1 : ia - 1;
+    const int ntS_b = ib == H - 1 ? 1 : 0, ntI_b = ib == 0 ? 0 : (ib == H - 1 ? H - 1 : ib + 1);
+    const int nbS_b = ib == 0 ? 0 : 1,     nbI_b = ib == 0 ? 1 : ib - 1;
+    const int d00 = (2 * ntS_a + ntS_b) * PL + ntI_a * H + ntI_b;      // (T[ia], T[ib])
+    const int d01 = (2 * ntS_a + nbS_b) * PL + ntI_a * H + nbI_b;      // (T[ia], B[ib])
+    const int d10 = (2 * nbS_a + ntS_b) * PL + nbI_a * H + ntI_b;      // (B[ia], T[ib])
+    const int d11 = (2 * nbS_a + nbS_b) * PL + nbI_a * H + nbI_b;      // (B[ia], B[ib])
+    const int own = ia * H + ib, diag = ib * (H + 1);
     __syncthreads();
-    int cur = 0, sweeps_run = 0;
+    int cur = 1, sweeps_run = 0;
     for (int sweep = 0; sweep < 16; ++sweep) {
         ++sweeps_run;
         if (tid == 0) { sm.flag = 0; sm.flag_big = 0; }
-        __syncthreads();
-        // round-robin tournament: pair 0 = (B - 1, round); pair i = ((round + i) mod (B - 1), (round - i) mod (B - 1))
-        int ua = ia % (PB - 1), va = (PB - 1 - ia) % (PB - 1), ub = ib % (PB - 1), vb = (PB - 1 - ib) % (PB - 1);
+        int any = 0, big = 0;
         for (int round = 0; round < PB - 1; ++round) {
-            int pa = ia == 0 ? PB - 1 : ua, qa = ia == 0 ? round : va;
-            int pb = ib == 0 ? PB - 1 : ub, qb = ib == 0 ? round : vb;
-            if (pa > qa) { const int t = pa; pa = qa; qa = t; }
-            if (pb > qb) { const int t = pb; pb = qb; qb = t; }
-            const double (*A)[PS] = Ab[cur];
-            double (*An)[PS] = Ab[cur ^ 1];
-            const double app = A[pb][pb], aqq = A[qb][qb], apq = A[pb][qb];
-            const double x00 = A[pa][pb], x01 = A[pa][qb], x10 = A[qa][pb], x11 = A[qa][qb];
-            double cb = 1.0, sb = 0.0;
-            if (apq * apq > 1e-33 * fabs(app * aqq) && apq != 0.0) {
-                // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
-                const double zeta = aqq - app, beta = 2.0 * apq;
-                const double irr = rsqrt(fma(zeta, zeta, beta * beta));
-                const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
-                const double ic = rsqrt(c2);
-                cb = c2 * ic;
-                sb = (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic;
-                if (ia == 0) {
-                    sm.flag = 1;
-                    if (apq * apq > 1e-20 * fabs(app * aqq)) sm.flag_big = 1;
-                }
-            }
+            RUVIII_JSTAMP(0);
+            const double* A = buf0 + cur * dAL;
+            double* An = buf0 + (cur ^ 1) * dAL;
+            const double app = A[diag], apq = A[PL + diag], aqq = A[3 * PL + diag];
+            const double x00 = A[own], x01 = A[PL + own], x10 = A[2 * PL + own], x11 = A[3 * PL + own];
+            // cos(2 theta) = |zeta| / rr, |theta| <= pi / 4, two rsqrt and no division
+            const double zeta = aqq - app, beta = 2.0 * apq;
+            const double n2 = fma(zeta, zeta, beta * beta);
+            const double lim = fabs(app * aqq), q2 = apq * apq;
+            const bool rot = q2 > 1e-33 * lim && n2 > 1e-280;
+            RUVIII_JSTAMP(1);
+            const double irr = rsqrt_fast(n2);
+            const double c2 = fma(0.5 * fabs(zeta), irr, 0.5);
+            const double ic = rsqrt_fast(c2);
+            const double cb = rot ? c2 * ic : 1.0;
+            const double sb = rot ? (zeta >= 0.0 ? 0.5 : -0.5) * beta * irr * ic : 0.0;
+            any |= rot;
+            big |= rot && q2 > 1e-20 * lim;
+            RUVIII_JSTAMP(2);
             const double ca = __shfl_sync(0xffffffffu, cb, ia), sa = __shfl_sync(0xffffffffu, sb, ia);
+            RUVIII_JSTAMP(3);
             const double r00 = ca * x00 - sa * x10, r01 = ca * x01 - sa * x11;      // rows:    J_a' X
             const double r10 = sa * x00 + ca * x10, r11 = sa * x01 + ca * x11;
-            An[pa][pb] = cb * r00 - sb * r01;                                        // columns: (.) J_b
-            An[pa][qb] = sb * r00 + cb * r01;
-            An[qa][pb] = cb * r10 - sb * r11;
-            An[qa][qb] = sb * r10 + cb * r11;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {                                            // V <- V J_b on this thread's two rows
-                const int j = 2 * ia + u;
-                const double vx = Vacc[j][pb], vy = Vacc[j][qb];
-                Vacc[j][pb] = cb * vx - sb * vy;
-                Vacc[j][qb] = sb * vx + cb * vy;
+            An[d00] = cb * r00 - sb * r01;                                           // columns: (.) J_b, stored one chair on
+            An[d01] = sb * r00 + cb * r01;
+            An[d10] = cb * r10 - sb * r11;
+            An[d11] = sb * r10 + cb * r11;
+            // V <- V J_b, then the columns move with their chairs: to lane + 1 goes the top value (from lane 0: the bottom
+            // one, B[0] -> T[1]); to lane - 1 the bottom value; T[0] stays and T[15] -> B[15] are the lane's own values
+            {
+                const double t0 = cb * vt0 - sb * vb0, b0 = sb * vt0 + cb * vb0;
+                const double t1 = cb * vt1 - sb * vb1, b1 = sb * vt1 + cb * vb1;
+                const double fl0 = __shfl_up_sync(0xffffffffu, ib == 0 ? b0 : t0, 1, H);
+                const double fl1 = __shfl_up_sync(0xffffffffu, ib == 0 ? b1 : t1, 1, H);
+                const double fr0 = __shfl_down_sync(0xffffffffu, b0, 1, H);
+                const double fr1 = __shfl_down_sync(0xffffffffu, b1, 1, H);
+                vt0 = ib == 0 ? t0 : fl0;  vb0 = ib == H - 1 ? t0 : fr0;
+                vt1 = ib == 0 ? t1 : fl1;  vb1 = ib == H - 1 ? t1 : fr1;
             }
-            ua = ua + 1 == PB - 1 ? 0 : ua + 1;  va = va + 1 == PB - 1 ? 0 : va + 1;
-            ub = ub + 1 == PB - 1 ? 0 : ub + 1;  vb = vb + 1 == PB - 1 ? 0 : vb + 1;
             cur ^= 1;
+            RUVIII_JSTAMP(4);
             __syncthreads();
+            RUVIII_JSTAMP(5);
         }
+        if (ia == 0) {                                    // the 16 threads ia == 0 see every pair (ib = pair)
+            if (any) sm.flag = 1;
+            if (big) sm.flag_big = 1;
+        }
+        __syncthreads();
         // quadratic convergence: a sweep whose largest relative off-diagonal entry was below 1e-10 leaves them below rounding
         const bool stop = !sm.flag || !sm.flag_big;
         __syncthreads();
         if (stop) break;
     }
-    const double (*A)[PS] = Ab[cur];
-    // sort descending (rank sort): sm.th, sm.V = V with permuted columns
+    RUVIII_JSTAMP_FLUSH
+    // sort descending (rank sort over the chairs): sm.th, sm.V = V with its columns permuted
+    const double* A = buf0 + cur * dAL;
+    int* rank_of_chair = &sm.pr[0][0];
     if (tid < PB) {
-        const double t = A[tid][tid];
+        const double t = A[(tid < H ? 0 : 3 * PL) + (tid % H) * (H + 1)];
         int rank = 0;
-        for (int i = 0; i < PB; ++i) {
-            const double u = A[i][i];
-            rank += (u > t) || (u == t && i < tid);
+        for (int c = 0; c < PB; ++c) {
+            const double u = A[(c < H ? 0 : 3 * PL) + (c % H) * (H + 1)];
+            rank += (u > t) || (u == t && c < tid);
         }
-        sm.pr[tid % (PB / 2)][tid / (PB / 2)] = rank;
+        rank_of_chair[tid] = rank;
         sm.th[rank] = t;
     }
     __syncthreads();
-    for (int e = tid; e < PB * PB; e += PT) {
-        const int i = e / PB, j = e % PB;
-        sm.V[i][sm.pr[j % (PB / 2)][j / (PB / 2)]] = Vacc[i][j];
+    {
+        const int rt = rank_of_chair[ib], rb = rank_of_chair[H + ib];
+        sm.V[2 * ia][rt] = vt0;      sm.V[2 * ia][rb] = vb0;
+        sm.V[2 * ia + 1][rt] = vt1;  sm.V[2 * ia + 1][rb] = vb1;
     }
     __syncthreads();
     return sweeps_run;
@@ -467,7 +530,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 sm.A[i][j] = 0.5 * (sm.L[i][j] + sm.L[j][i]);
             }
             __syncthreads();
-            const int sweeps = jacobi_phase(sm);
+            const int sweeps = jacobi_phase(sm, a.jorder);
             for (int e = tid; e < PB * PB; e += PT) __stcg(a.Vm + e, sm.V[e / PB][e % PB]);
             if (tid < PB) __stcg(a.theta + tid, sm.th[tid]);
             if (tid == 0) a.state[3] = sweeps;
@@ -711,6 +774,8 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
     a.first = std::max(2, first_env > 0 ? first_env : 6);   // the start block is not orthonormal: no Rayleigh-Ritz on pass 1
     a.period = 3;
     a.cheb = cheb_env;
+    static const int jorder_env = [] { const char* v = std::getenv("RUVIII_EIG_JORDER"); return v && *v ? std::atoi(v) : 0; }();
+    a.jorder = jorder_env;
     a.bar = reinterpret_cast<unsigned*>(w.state + 8);
     a.state = w.state;
     // RB = 8: the CTA's 8 rows of G (8 R doubles, pitch = 4 mod 16 doubles so that the 8 x 4 fragment loads of a warp spread

@@ -216,6 +216,94 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
     }
 }
 
+// ---- regress.out.*  ------------------------------------------------------------------------------------
+// supervisedFindNCG.R:111-133: y <- lm(t(expr.data) ~ variables); expr.data.reg <- t(y$residuals).  The model matrix (m1 x p:
+// intercept, treatment dummies of the factors, the continuous variables) comes from the host; K12 turns it into an orthonormal
+// basis Q with lm's rank rule, then per chunk of <= 32 columns K4 gives Q'Y and K6 gives Y - Q (Q'Y).  The residuals stay on the
+// device (the statistics address them as slot = -2) and are downloaded only when `out` is given.
+void do_regress_out(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
+                    const double* design, int p, double* out, int64_t ld_out, int* rank_out, float* ms_out) {
+    const bool resident = X == nullptr;
+    if (resident) {
+        if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_regress_out on resident data needs a plan and an upload");
+        if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_regress_out: no such output block");
+        if (slot < -1) throw Error(RUVIII_ERR_INVALID, "ruviii_regress_out: slot must be -1 or an output block");
+        m1 = h->m1;
+        n = h->n_local_total;
+        if (slot < 0) { ensure_logged(h); apply_log = 0; }       // the resident assay after the plan's own log transform
+    }
+    if (m1 < 2 || n <= 0 || !design || p <= 0) throw Error(RUVIII_ERR_INVALID, "ruviii_regress_out: bad arguments");
+    if (p > 256 || p >= m1) throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_regress_out: the model matrix must have <= 256 columns and fewer columns than samples");
+    if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_regress_out: row stride < n");
+    if (out && ld_out < n) throw Error(RUVIII_ERR_INVALID, "ruviii_regress_out: output row stride < n");
+    const int nsh = (int)h->shards.size(), n_chunks = ceil_div(p, 32);
+    int slot0[kMaxK + 1] = {0};
+    h->reg_valid = false;
+    h->launches = 0;
+    for (int i = 0; i < nsh; ++i) {
+        Shard& s = h->shards[i];
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
+        s.reg_g0 = g0; s.reg_n = ng; s.reg_ld = ld;
+        if (ng <= 0) continue;
+        s.rD.alloc((size_t)m1 * p, false);
+        s.rW.alloc((size_t)m1 * p, false);
+        s.rQ.alloc((size_t)n_chunks * m1 * 32, false);
+        s.rRank.alloc(1);
+        const int rsplit = project_rsplit(m1, ng, h->n_sms);
+        s.rPart.alloc((size_t)rsplit * 32 * ld, false);
+        s.rAlpha.alloc((size_t)32 * ld, false);
+        s.gReg.alloc((size_t)m1 * ld, false);
+        if (n_chunks > 1) s.gReg2.alloc((size_t)m1 * ld, false);
+        RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.rD.p, design, (size_t)m1 * p * 8, cudaMemcpyHostToDevice, s.stream));
+        const double* src;
+        if (!resident) {
+            s.gX.alloc((size_t)m1 * ld, false);
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
+            if (apply_log) { launch_log2_inplace(s.gX.p, ld, m1, ng, pseudo_count, s.stream); h->launches += 1; }
+            src = s.gX.p;
+        } else {
+            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+            if (apply_log) {                              // an output block is copied before it is transformed
+                s.gX.alloc((size_t)m1 * ld, false);
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gX.p, src, (size_t)m1 * ld * 8, cudaMemcpyDeviceToDevice, s.stream));
+                launch_log2_inplace(s.gX.p, ld, m1, ng, pseudo_count, s.stream);
+                h->launches += 1;
+                src = s.gX.p;
+            }
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
+        launch_design_qr(s.rD.p, p, m1, p, 1e-7, s.rW.p, s.rQ.p, s.rRank.p, s.stream);          // lm's default tol = 1e-07
+        h->launches += 1;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int kc = std::min(32, p - 32 * c), kp = pad_k(kc);
+            const double* q = s.rQ.p + (size_t)c * m1 * 32;
+            double* dst = ((n_chunks - 1 - c) % 2 == 0) ? s.gReg.p : s.gReg2.p;                  // the last chunk lands in gReg
+            launch_project(src, ld, m1, ng, q, kp, rsplit, s.rPart.p, ld, s.stream);
+            launch_alpha_finalize(s.rPart.p, rsplit, kp, ng, ld, s.rAlpha.p, nullptr, 0, nullptr, s.stream);
+            launch_update_smem(src, ld, m1, ng, q, kp, s.rAlpha.p, ld, kc, 1ull << kc, slot0, dst, ld, 0, s.stream);
+            h->launches += 3;
+            src = dst;
+        }
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_LOG], s.stream));
+        if (out)
+            RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(out + g0, (size_t)ld_out * 8, s.gReg.p, ld * 8, (size_t)ng * 8, m1, cudaMemcpyDeviceToHost,
+                                                s.stream));
+        if (i == 0) RUVIII_CUDA_CHECK(cudaMemcpyAsync(&h->h_flags[56], s.rRank.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    }
+    sync_all(h);
+    h->reg_valid = true;
+    h->reg_m1 = m1;
+    h->reg_n = n;
+    if (rank_out) *rank_out = h->h_flags[56];
+    if (ms_out) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(h->shards[0].device));
+        cudaEventElapsedTime(ms_out, h->shards[0].ev[E_START], h->shards[0].ev[E_LOG]);
+    }
+}
+
 // ---- negative-control-gene statistics ---------------------------------------------------------------
 // supervisedFindNCG.R:179-191,326-341 (row_oneway_equalvar(x, g)$statistic) and :214-229,270-285 (correls(y, x, "pearson")).
 // One streaming pass per call (K11, stats.cu).  Samples with group id < 0 are left out (the reference drops levels with
@@ -223,7 +311,13 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
 void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
                    const int32_t* group, const double* covariate, double* F_out, double* r_out, float* ms_out) {
     const bool resident = X == nullptr;
-    if (resident) {
+    const bool regressed = resident && slot == -2;               // the residuals the last ruviii_regress_out left on the device
+    if (regressed) {
+        if (!h->reg_valid) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats: slot -2 needs a ruviii_regress_out first");
+        m1 = h->reg_m1;
+        n = h->reg_n;
+        apply_log = 0;
+    } else if (resident) {
         if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats on resident data needs a plan and an upload");
         if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_stats: no such output block");
         m1 = h->m1;
@@ -276,10 +370,10 @@ void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n
     for (int i = 0; i < nsh; ++i) {
         Shard& s = h->shards[i];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
-        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        const int g0 = regressed ? s.reg_g0 : resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = regressed ? s.reg_n : resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
         if (ng <= 0) continue;
-        const int64_t ld = resident ? s.ld : round_up(ng, kRowAlign);
+        const int64_t ld = regressed ? s.reg_ld : resident ? s.ld : round_up(ng, kRowAlign);
         s.gStart.alloc(pstart.size(), false);
         s.gRows.alloc(prow.size(), false);
         s.gGroup.alloc(pgroup.size(), false);
@@ -299,7 +393,7 @@ void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
             src = s.gX.p;
         } else {
-            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+            src = regressed ? s.gReg.p : slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
         }
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
         launch_gene_stats(src, ld, ng, s.gStart.p, s.gRows.p, s.gGroup.p, n_pieces, n_groups, n_rows, covariate ? s.gCov.p : nullptr,
@@ -322,11 +416,17 @@ void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n
 void do_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, const double* covariate, double* rho_out,
                       float* ms_out) {
     const bool resident = X == nullptr;
-    if (resident) {
+    const bool regressed = resident && slot == -2;
+    if (regressed) {
+        if (!h->reg_valid) throw Error(RUVIII_ERR_STATE, "ruviii_gene_spearman: slot -2 needs a ruviii_regress_out first");
+        m1 = h->reg_m1;
+        n = h->reg_n;
+    } else if (resident) {
         if (!h->planned || !h->uploaded) throw Error(RUVIII_ERR_STATE, "ruviii_gene_spearman on resident data needs a plan and an upload");
         if (slot >= 0 && (!h->ran || slot >= (int)h->ks.size())) throw Error(RUVIII_ERR_STATE, "ruviii_gene_spearman: no such output block");
         m1 = h->m1;
         n = h->n_local_total;
+        if (slot < 0) ensure_logged(h);
     }
     if (m1 < 2 || n <= 0 || !covariate || !rho_out) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_spearman: bad arguments");
     if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_gene_spearman: row stride < n");
@@ -352,10 +452,10 @@ void do_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int m1, in
     for (int i = 0; i < nsh; ++i) {
         Shard& s = h->shards[i];
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
-        const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
-        const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+        const int g0 = regressed ? s.reg_g0 : resident ? s.g0 : (int)((int64_t)n * i / nsh);
+        const int ng = regressed ? s.reg_n : resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
         if (ng <= 0) continue;
-        const int64_t ld = resident ? s.ld : round_up(ng, kRowAlign);
+        const int64_t ld = regressed ? s.reg_ld : resident ? s.ld : round_up(ng, kRowAlign);
         s.gCov.alloc(m1, false);
         s.gR.alloc(ld, false);
         RUVIII_CUDA_CHECK(cudaMemcpyAsync(s.gCov.p, cr.data(), (size_t)m1 * 8, cudaMemcpyHostToDevice, s.stream));
@@ -365,7 +465,7 @@ void do_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int m1, in
             RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(s.gX.p, ld * 8, X + g0, ldX * 8, (size_t)ng * 8, m1, cudaMemcpyHostToDevice, s.stream));
             src = s.gX.p;
         } else {
-            src = slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
+            src = regressed ? s.gReg.p : slot >= 0 ? s.out.p + (size_t)slot * m1 * s.ld : s.Y.p;
         }
         RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_START], s.stream));
         launch_gene_spearman(src, ld, m1, ng, s.gCov.p, cmean, (double)css, s.gR.p, s.stream);
@@ -386,6 +486,15 @@ using namespace ruviii;
 
 #pragma GCC visibility push(default)
 extern "C" {
+
+int ruviii_regress_out(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
+                       double pseudo_count, const double* design, int32_t p, double* residuals_out, int64_t ld_out, int32_t* rank_out,
+                       float* ms_out) {
+    if (!h) return RUVIII_ERR_INVALID;
+    return guarded(h, [&] {
+        do_regress_out(h, X, ldX, m1, n, slot, apply_log, pseudo_count, design, p, residuals_out, ld_out, rank_out, ms_out);
+    });
+}
 
 int ruviii_gene_spearman(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, const double* covariate,
                          double* rho_out, float* ms_out) {

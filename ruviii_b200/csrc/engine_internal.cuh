@@ -176,6 +176,10 @@ struct Shard {
     DevBuf<double> pX, pG, pWs, pU, pEv, pPart, pAlpha, pStat, pMean, pSd, pTopk, pEvAsc;   // computePCA fast path (ruviii_pca)
     DevBuf<double> gX, gPart, gCov, gF, gR;     // gene statistics (ruviii_gene_stats)
     DevBuf<int> gStart, gRows, gGroup;
+    DevBuf<double> rD, rW, rQ, rPart, rAlpha, gReg, gReg2;   // regress-out (ruviii_regress_out): design, basis, residuals
+    DevBuf<int> rRank;
+    int reg_g0 = 0, reg_n = 0;                  // genes [reg_g0, reg_g0 + reg_n) of the regressed matrix live in gReg
+    int64_t reg_ld = 0;
     DevBuf<int2> pTiles;
     DevBuf<int> pState;
     TopkWork ptopk{};
@@ -250,6 +254,8 @@ struct ruviii_handle {
     int prps_n = 0;
     bool ps_pending = false;            // the PRPS rows still have to be built from the resident assay
     bool ps_from_sets = false;          // the resident PRPS rows come from ruviii_set_prps_sets, not from the host
+    bool reg_valid = false;             // gReg holds the residuals of the last ruviii_regress_out (slot = -2 of the statistics)
+    int reg_m1 = 0, reg_n = 0;
     bool yc_valid = false;              // the control-gene block Yc holds Y[, ctl] of the CURRENT upload (gathered once per upload)
     double eig_tol = 1e-13;
     ruviii::P2PState* p2p = nullptr;       // peer-memory exchange buffers of the one-process-per-GPU allreduce (p2p.cu)
@@ -293,6 +299,8 @@ void do_normalise_staged(ruviii_handle* h, const double* Y, int64_t ldY, const d
 void apply_ruv1(ruviii_handle* h);
 void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
             int center, int scale, int k, double* u_out, double* d_out, double* v_out, float* stage_ms);
+void do_regress_out(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
+                    const double* design, int p, double* out, int64_t ld_out, int* rank_out, float* ms_out);
 void do_gene_stats(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int slot, int apply_log, double pseudo_count,
                    const int32_t* group, const double* covariate, double* F_out, double* r_out, float* ms_out);
 

@@ -174,6 +174,10 @@ int spearman_max_rows();
 void launch_gene_spearman(const double* X, int64_t ld, int m1, int n, const double* crank, double cmean, double css, double* rho,
                           cudaStream_t s);
 
+// K12 supervisedFindNCG.R:111-133  orthonormal basis of an m1 x p model matrix (regress.cu): W = p x m1 scratch,
+// Q = ceil(p / 32) chunks, chunk c a row-major m1 x pad_k(columns) block at Q + c * m1 * 32; aliased columns are zero.
+void launch_design_qr(const double* D, int64_t ldd, int m1, int p, double tol, double* W, double* Q, int* rank_out, cudaStream_t s);
+
 // micro-benchmarks (ceilings quoted beside the roofline)
 float probe_copy_gbs(size_t bytes, cudaStream_t s);
 float probe_dmma_tflops(int n_sms, cudaStream_t s);
