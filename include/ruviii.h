@@ -205,7 +205,9 @@ int ruviii_set_prps_sets(ruviii_handle* h, const int32_t* set_start, const int32
  *               slot == -1: the uploaded assay after the plan's own log transform (applied in place now if no run has done it
  *               yet; apply_log / pseudo_count of this call are ignored).  m1, n, ldX are ignored.
  *   u_out  m1 x k row-major (sing.val$u), d_out k (sing.val$d), v_out NULL or k x n row-major (= the bytes of R's n x k v).
- *   Signs: each u_j has its largest-magnitude component positive; v_j follows.  k <= 32 and k < m1.
+ *   Signs: each u_j has its largest-magnitude component positive; v_j follows.  k < m1 up to 32 (the device's own top-k
+ *   eigensolver); 32 < k <= min(m1, n) takes the library eigensolver for the k leading pairs and projects in chunks of 32:
+ *   k = min(m1, n) is the full svd(scale(t(x))) of computePCA.R:150-190 (fast.pca = FALSE).
  *   stage_ms6: NULL or 6 floats (device ms): upload+log, centre, Gram, allreduce+eigensolve, broadcast+projection, total. */
 int ruviii_pca(ruviii_handle* h, const double* X, int64_t ldX, int32_t m1, int32_t n, int32_t slot, int32_t apply_log,
                double pseudo_count, int32_t center, int32_t scale, int32_t k, double* u_out, double* d_out, double* v_out,

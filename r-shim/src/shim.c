@@ -244,6 +244,27 @@ SEXP _RUVIIIPRPS_geneStats(SEXP assay, SEXP groups, SEXP covariate, SEXP applyLo
     return out;
 }
 
+/* expr.data.reg <- t(lm(t(expr.data) ~ ...)$residuals), supervisedFindNCG.R:111-133.
+ *   assay   numeric genes x samples (n x m1, column-major = m1 x n row-major)
+ *   design  numeric m1 x p: model.matrix(~ v1 + v2 + ..., colData) built in R
+ * returns the residuals as a genes x samples matrix (they also stay on the device for geneStats-like calls with slot = -2) */
+SEXP _RUVIIIPRPS_regressOut(SEXP assay, SEXP design, SEXP applyLog, SEXP pseudoCount) {
+    const int n = Rf_nrows(assay), m1 = Rf_ncols(assay), p = Rf_ncols(design);
+    if (Rf_nrows(design) != m1) Rf_error("the model matrix needs one row per sample");
+    ruviii_handle* h = engine();
+    double* d = (double*)R_alloc((size_t)m1 * p, sizeof(double));      /* column-major -> the row-major m1 x p the ABI takes */
+    for (int j = 0; j < p; ++j)
+        for (int i = 0; i < m1; ++i) d[(size_t)i * p + j] = REAL(design)[(size_t)j * m1 + i];
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, m1));
+    if (ruviii_regress_out(h, REAL(assay), n, m1, n, -1, Rf_asLogical(applyLog), Rf_asReal(pseudoCount), d, p, REAL(out), n, NULL, NULL) !=
+        RUVIII_OK) {
+        UNPROTECT(1);
+        Rf_error("RUVIIIPRPS: %s", ruviii_last_error(h));
+    }
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"_RUVIIIPRPS_ruvIIICore", (DL_FUNC)&_RUVIIIPRPS_ruvIIICore, 9},
     {"_RUVIIIPRPS_fastResidop", (DL_FUNC)&_RUVIIIPRPS_fastResidop, 2},
@@ -256,6 +277,7 @@ static const R_CallMethodDef call_methods[] = {
     {"_RUVIIIPRPS_prpsMeans", (DL_FUNC)&_RUVIIIPRPS_prpsMeans, 5},
     {"_RUVIIIPRPS_fastPCA", (DL_FUNC)&_RUVIIIPRPS_fastPCA, 6},
     {"_RUVIIIPRPS_geneStats", (DL_FUNC)&_RUVIIIPRPS_geneStats, 5},
+    {"_RUVIIIPRPS_regressOut", (DL_FUNC)&_RUVIIIPRPS_regressOut, 4},
     {NULL, NULL, 0}};
 
 void R_init_RUVIIIPRPS(DllInfo* dll) {

@@ -856,7 +856,7 @@ void do_run(ruviii_handle* h, ruviii_info* info_out) {
                     launch_alpha_from_v(s.U.p + (size_t)h->goff[j] * kp, s.evals.p, s.n, kk, kp, s.ld, s.alpha.p, s.stream);
                     launch_alpha_finalize(s.alpha.p, 1, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
                 } else {
-                    launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
+                    launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream, kk);
                     launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
                 }
             });

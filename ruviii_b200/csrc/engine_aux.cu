@@ -54,6 +54,62 @@ void apply_ruv1(ruviii_handle* h) {
     }
 }
 
+// The k > 32 tail of ruviii_pca: the k leading eigenpairs sit in pG (column-major, ascending) / pEvAsc on rank 0; per chunk of
+// 32: sign-fixed descending columns (pick_top) -> broadcast -> K4 projection -> v = t(alpha) / d.
+static void do_pca_wide_tail(ruviii_handle* h, bool resident, int m1, int n, int k, double* u_out, double* d_out, double* v_out) {
+    const int nsh = (int)h->shards.size(), kp = kMaxK;
+    std::vector<double> ev(k);
+    for (int c0 = 0; c0 < k; c0 += kp) {
+        const int kc = std::min(kp, k - c0);
+        if (h->rank0 == 0) {
+            Shard& s = h->shards[0];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            launch_pick_top(s.pG.p, m1, s.pEvAsc.p, k - c0, m1, kc, kc, kp, nullptr, s.pU.p, s.pEv.p, s.stream);
+            h->launches += 1;
+        }
+        if (c0 == 0)
+            for (auto& s : h->shards) {
+                RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+                RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_EIG], s.stream));
+            }
+        {
+            std::vector<double*> b;
+            for (auto& s : h->shards) b.push_back(s.pU.p);
+            broadcast0(h, b, (size_t)m1 * kp);
+            b.clear();
+            for (auto& s : h->shards) b.push_back(s.pEv.p);
+            broadcast0(h, b, (size_t)kp);
+        }
+        for (int i = 0; i < nsh; ++i) {
+            Shard& s = h->shards[i];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            const int g0 = resident ? s.g0 : (int)((int64_t)n * i / nsh);
+            const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
+            const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
+            const int rsplit = project_rsplit(m1, ng, h->n_sms);
+            launch_project(s.pX.p, ld, m1, ng, s.pU.p, kp, rsplit, s.pPart.p, ld, s.stream, kc);
+            launch_alpha_finalize(s.pPart.p, rsplit, kp, ng, ld, s.pAlpha.p, nullptr, 0, nullptr, s.stream);
+            launch_v_from_alpha(s.pAlpha.p, s.pEv.p, kc, ld, nullptr, s.stream);
+            h->launches += 3;
+            if (v_out && ng > 0)
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(v_out + (size_t)c0 * n + g0, (size_t)n * 8, s.pAlpha.p, ld * 8, (size_t)ng * 8, kc,
+                                                    cudaMemcpyDeviceToHost, s.stream));
+            if (i == 0) {
+                RUVIII_CUDA_CHECK(cudaMemcpy2DAsync(u_out + c0, (size_t)k * 8, s.pU.p, (size_t)kp * 8, (size_t)kc * 8, m1,
+                                                    cudaMemcpyDeviceToHost, s.stream));
+                RUVIII_CUDA_CHECK(cudaMemcpyAsync(ev.data() + c0, s.pEv.p, (size_t)kc * 8, cudaMemcpyDeviceToHost, s.stream));
+            }
+        }
+        sync_all(h);                      // pU / pEv / pAlpha are reused by the next chunk
+    }
+    for (auto& s : h->shards) {
+        RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+        RUVIII_CUDA_CHECK(cudaEventRecord(s.ev[E_PROJECT], s.stream));
+    }
+    sync_all(h);
+    for (int j = 0; j < k; ++j) d_out[j] = std::sqrt(std::max(ev[j], 0.0));
+}
+
 // ---- computePCA fast path --------------------------------------------------------------------------
 // computePCA.R:120-134: runSVD(t(assay), k = nb.pcs, center, scale) -- the top-k singular triplets of the centred samples x
 // genes matrix.  Sample-side route with the engine's own kernels: K10 centre -> K2 Gram Xc Xc' (genes sharded, allreduced)
@@ -72,10 +128,15 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
     }
     if (m1 < 2 || n <= 0 || k <= 0 || !u_out || !d_out) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: bad arguments");
     if (!resident && ldX < n) throw Error(RUVIII_ERR_INVALID, "ruviii_pca: row stride < n");
-    if (k > kMaxK || k >= m1) throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_pca: nb.pcs must be <= 32 and < the number of samples");
-    const int kp = pad_k(k), nsh = (int)h->shards.size();
-    const int n_keep = std::min(m1, k + 1);
-    const bool topk_ok = k <= kTopkMaxK && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
+    // k <= 32: the fast path of computePCA (runSVD, :120-134).  Wider requests -- up to min(m1, n), which is the full svd() of
+    // computePCA.R:150-190 (fast.pca = FALSE) -- take the same route with the library eigensolver for the k leading pairs
+    // and the projection in chunks of 32 columns.
+    const bool wide = k > kMaxK;
+    if (k > std::min(m1, n) || (!wide && k >= m1))
+        throw Error(RUVIII_ERR_UNSUPPORTED, "ruviii_pca: nb.pcs must be < the number of samples (<= min(samples, genes) beyond 32)");
+    const int kp = wide ? kMaxK : pad_k(k), nsh = (int)h->shards.size();
+    const int n_keep = wide ? k : std::min(m1, k + 1);
+    const bool topk_ok = !wide && k <= kTopkMaxK && m1 >= 4 * kTopkBlock && h->eig_impl != 1 && h->eig_impl != 2;
     h->launches = 0;
     std::vector<GramPlan> gps(nsh);
     for (int i = 0; i < nsh; ++i) {
@@ -163,9 +224,22 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
                                                   m1, s.pG.p, m1, 0.0, 0.0, m1 - n_keep + 1, m1, &meig, s.pEvAsc.p,
                                                   h->solver_work.p, (int)h->solver_work.count, h->solver_info.p));
             if (meig != n_keep) throw Error(RUVIII_ERR_SOLVER, "syevdx returned an unexpected number of eigenpairs");
-            launch_pick_top(s.pG.p, m1, s.pEvAsc.p, meig, m1, n_keep, k, kp, nullptr, s.pU.p, s.pEv.p, s.stream);
-            h->launches += 1;
+            if (!wide) {
+                launch_pick_top(s.pG.p, m1, s.pEvAsc.p, meig, m1, n_keep, k, kp, nullptr, s.pU.p, s.pEv.p, s.stream);
+                h->launches += 1;
+            }
         }
+    }
+    if (wide) {
+        do_pca_wide_tail(h, resident, m1, n, k, u_out, d_out, v_out);
+        if (stage_ms) {
+            Shard& s = h->shards[0];
+            RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
+            auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
+            stage_ms[0] = el(E_START, E_LOG); stage_ms[1] = el(E_LOG, E_RESIDOP); stage_ms[2] = el(E_RESIDOP, E_GRAM);
+            stage_ms[3] = el(E_GRAM, E_EIG); stage_ms[4] = el(E_EIG, E_PROJECT); stage_ms[5] = el(E_START, E_PROJECT);
+        }
+        return;
     }
     for (auto& s : h->shards) {
         RUVIII_CUDA_CHECK(cudaSetDevice(s.device));
@@ -187,7 +261,7 @@ void do_pca(ruviii_handle* h, const double* X, int64_t ldX, int m1, int n, int s
         const int ng = resident ? s.n : (int)((int64_t)n * (i + 1) / nsh) - g0;
         const int64_t ld = resident ? s.ld : round_up(std::max(ng, 1), kRowAlign);
         const int rsplit = project_rsplit(m1, ng, h->n_sms);
-        launch_project(s.pX.p, ld, m1, ng, s.pU.p, kp, rsplit, s.pPart.p, ld, s.stream);
+        launch_project(s.pX.p, ld, m1, ng, s.pU.p, kp, rsplit, s.pPart.p, ld, s.stream, k);
         launch_alpha_finalize(s.pPart.p, rsplit, kp, ng, ld, s.pAlpha.p, nullptr, 0, nullptr, s.stream);
         launch_v_from_alpha(s.pAlpha.p, s.pEv.p, k, ld, nullptr, s.stream);
         h->launches += 3;
@@ -281,7 +355,7 @@ void do_regress_out(ruviii_handle* h, const double* X, int64_t ldX, int m1, int 
             const int kc = std::min(32, p - 32 * c), kp = pad_k(kc);
             const double* q = s.rQ.p + (size_t)c * m1 * 32;
             double* dst = ((n_chunks - 1 - c) % 2 == 0) ? s.gReg.p : s.gReg2.p;                  // the last chunk lands in gReg
-            launch_project(src, ld, m1, ng, q, kp, rsplit, s.rPart.p, ld, s.stream);
+            launch_project(src, ld, m1, ng, q, kp, rsplit, s.rPart.p, ld, s.stream, kc);
             launch_alpha_finalize(s.rPart.p, rsplit, kp, ng, ld, s.rAlpha.p, nullptr, 0, nullptr, s.stream);
             launch_update_smem(src, ld, m1, ng, q, kp, s.rAlpha.p, ld, kc, 1ull << kc, slot0, dst, ld, 0, s.stream);
             h->launches += 3;

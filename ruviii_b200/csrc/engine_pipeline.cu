@@ -142,7 +142,7 @@ void do_normalise_pipelined(ruviii_handle* h, const double* Y, int64_t ldY, cons
         broadcast0(h, b, (size_t)std::max(h->n_keep, kp) + 2);
     }
     for_shards([&](Shard& s) {
-        launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream);
+        launch_project(s.Y0.p, s.ld, R, s.n, s.U.p, kp, s.rsplit, s.part.p, s.ld, s.stream, kk);
         launch_alpha_finalize(s.part.p, s.rsplit, kp, s.n, s.ld, s.alpha.p, s.ctl_idx.p, s.n_ctl, s.acT.p, s.stream);
         RowSrc src{s.Y.p, s.ld, s.PS.p, s.ld, m1};
         RUVIII_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.ev_gather, 0));

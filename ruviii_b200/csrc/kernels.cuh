@@ -104,8 +104,9 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
 // K4  ruvIII.R:140  fullalpha = t(U) %*% Y  (rows 1..kk; = t(U) %*% Y0 because U is orthogonal to col(M)).
 // part: rsplit x kp x ld partial sums over row chunks of Y0 (summed by launch_alpha_finalize).
 int  project_rsplit(int R, int n, int n_sms);
+// k_used (optional): columns of U beyond it are zero padding and are skipped (their rows of `part` are written as zeros).
 void launch_project(const double* Y0, int64_t ldY0, int R, int n, const double* U_rowmajor, int kp,
-                    int rsplit, double* part, int64_t ld, cudaStream_t s);
+                    int rsplit, double* part, int64_t ld, cudaStream_t s, int k_used = 0);
 // alpha[j][g] = sum_split part; acT[c][j] = alpha[j][ctl_idx[c]]   (ruvIII.R:142-143)
 void launch_alpha_finalize(const double* part, int rsplit, int kp, int n, int64_t ld, double* alpha,
                            const int* ctl_idx, int n_ctl, double* acT, cudaStream_t s);

@@ -60,42 +60,48 @@ pick_top_kernel(const double* __restrict__ V, int64_t ldv, const double* __restr
 constexpr int kProjThreads = 128;
 constexpr int kProjRows = 32;                      // rows staged per step
 
-template <int KP>
-__global__ void __launch_bounds__(kProjThreads)
+// KU <= KP: columns of U that are not padding (a multiple of 4): the others are neither accumulated nor read.
+// Eight rows are requested before any of them is used -- 8 x 16 B in flight per thread, four CTAs per SM: the kernel is a
+// stream over Y0 with 2 KU DFMA per 16 bytes, and with four rows in flight at three CTAs per SM it reached 2.0 TB/s.
+template <int KP, int KU>
+__global__ void __launch_bounds__(kProjThreads, KU <= 16 ? 4 : (KU <= 24 ? 3 : 2))
 project_kernel(const double* __restrict__ Y0, int64_t ldY0, int R, int n_pairs, const double* __restrict__ U,
                int rows_per_split, double* __restrict__ part, int64_t ld) {
-    __shared__ double sU[kProjRows][KP];
+    __shared__ __align__(16) double sU[kProjRows][KU];
     const int pair = blockIdx.x * kProjThreads + threadIdx.x;
     const bool active = pair < n_pairs;
     const int64_t col = 2 * (int64_t)pair;
     const int r0 = blockIdx.y * rows_per_split;
     const int r1 = min(r0 + rows_per_split, R);
-    double2 acc[KP];
+    double2 acc[KU];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int j = 0; j < KU; ++j) acc[j] = make_double2(0.0, 0.0);
     for (int rb = r0; rb < r1; rb += kProjRows) {
         const int nr = min(kProjRows, r1 - rb);
         __syncthreads();
-        for (int e = threadIdx.x; e < kProjRows * KP; e += kProjThreads) {
-            const int rr = e / KP, j = e - rr * KP;
+        for (int e = threadIdx.x; e < kProjRows * KU; e += kProjThreads) {
+            const int rr = e / KU, j = e - rr * KU;
             sU[rr][j] = rr < nr ? U[(int64_t)(rb + rr) * KP + j] : 0.0;
         }
         __syncthreads();
         if (active) {
-#pragma unroll 4
-            for (int rr = 0; rr < kProjRows; rr += 4) {
-                double2 y[4];
+#pragma unroll 1
+            for (int rr = 0; rr < kProjRows; rr += 8) {
+                if (rr >= nr) break;
+                double2 y[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
                     y[u] = (rr + u < nr) ? ld_stream(Y0 + (int64_t)(rb + rr + u) * ldY0 + col)
                                          : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) {
-                        const double w = sU[rr + u][j];
-                        acc[j].x = fma(w, y[u].x, acc[j].x);
-                        acc[j].y = fma(w, y[u].y, acc[j].y);
+                    for (int j = 0; j < KU; j += 2) {
+                        const double2 w = *reinterpret_cast<const double2*>(&sU[rr + u][j]);
+                        acc[j].x = fma(w.x, y[u].x, acc[j].x);
+                        acc[j].y = fma(w.x, y[u].y, acc[j].y);
+                        acc[j + 1].x = fma(w.y, y[u].x, acc[j + 1].x);
+                        acc[j + 1].y = fma(w.y, y[u].y, acc[j + 1].y);
                     }
             }
         }
@@ -103,7 +109,8 @@ project_kernel(const double* __restrict__ Y0, int64_t ldY0, int R, int n_pairs, 
     if (active) {
         double* out = part + (int64_t)blockIdx.y * KP * ld + col;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) *reinterpret_cast<double2*>(out + (int64_t)j * ld) = acc[j];
+        for (int j = 0; j < KP; ++j)
+            *reinterpret_cast<double2*>(out + (int64_t)j * ld) = j < KU ? acc[j < KU ? j : 0] : make_double2(0.0, 0.0);
     }
 }
 
@@ -498,16 +505,24 @@ int project_rsplit(int R, int n, int n_sms) {
 }
 
 void launch_project(const double* Y0, int64_t ldY0, int R, int n, const double* U, int kp, int rsplit,
-                    double* part, int64_t ld, cudaStream_t s) {
+                    double* part, int64_t ld, cudaStream_t s, int k_used) {
     const int n_pairs = (n + 1) / 2;
     const int rows_per_split = (int)round_up(ceil_div(R, rsplit), kProjRows);
     dim3 grid(ceil_div(n_pairs, kProjThreads), rsplit);
+    const int ku = k_used > 0 ? std::min(kp, (int)round_up(k_used, 4)) : kp;      // columns of U beyond k_used are zero padding
+#define RUVIII_PROJ(KP_, KU_) project_kernel<KP_, KU_><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld)
     switch (kp) {
-        case 4: project_kernel<4><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
-        case 8: project_kernel<8><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
-        case 16: project_kernel<16><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
-        default: project_kernel<32><<<grid, kProjThreads, 0, s>>>(Y0, ldY0, R, n_pairs, U, rows_per_split, part, ld); break;
+        case 4: RUVIII_PROJ(4, 4); break;
+        case 8: if (ku <= 4) RUVIII_PROJ(8, 4); else RUVIII_PROJ(8, 8); break;
+        case 16: if (ku <= 12) RUVIII_PROJ(16, 12); else RUVIII_PROJ(16, 16); break;
+        default:
+            if (ku <= 20) RUVIII_PROJ(32, 20);
+            else if (ku <= 24) RUVIII_PROJ(32, 24);
+            else if (ku <= 28) RUVIII_PROJ(32, 28);
+            else RUVIII_PROJ(32, 32);
+            break;
     }
+#undef RUVIII_PROJ
     RUVIII_LAUNCH_CHECK();
 }
 

@@ -1,8 +1,10 @@
-"""computePCA's fast path -- the step right after the RUV-III path (normAssessment.R:113 runs it on
-every ``RUV_K*`` assay).  Host side of ``computePCA`` (R/computePCA.R:38-262) with ``fast.pca = TRUE``: same
-arguments, messages and result layout (``metadata$metric[[assay]]$fastPCA = list(sing.val = list(u, d, v),
-variation)``); the decomposition is ``ruviii_pca`` (centre -> Gram -> top-k eigensolver -> projection on the
-device).  ``fast.pca = FALSE`` (a full ``svd`` of every assay, computePCA.R:150-190) is not part of the rebuilt path.
+"""computePCA -- the step right after the RUV-III path (normAssessment.R:113 runs it on every ``RUV_K*``
+assay).  Host side of ``computePCA`` (R/computePCA.R:38-262): same arguments, messages and result layout
+(``metadata$metric[[assay]]$fastPCA`` or ``$PCA`` ``= list(sing.val = list(u, d, v), variation)``); the decomposition is
+``ruviii_pca`` (centre -> Gram -> eigensolver -> projection on the device).  ``fast.pca = TRUE`` asks for the ``nb.pcs``
+leading triplets (:120-134); ``fast.pca = FALSE`` (:150-190, ``svd(scale(t(x)))``) for all min(samples, genes) of them.
+The centred matrix has rank <= samples - 1, so its last singular value is rounding noise and the vectors that go with it are
+as arbitrary here as they are in LAPACK.
 """
 from __future__ import annotations
 
@@ -25,8 +27,6 @@ def computePCA(se_obj, assay_names="All", apply_log=True, fast_pca=True, nb_pcs=
         raise ValueError("To perform fast PCA, the number of PCs (nb.pcs) must specified.")
     if assay_names is None:
         raise ValueError("Please provide at least an assay name.")
-    if not fast_pca:
-        raise NotImplementedError("fast.pca = FALSE (full svd of every assay, computePCA.R:150-190) is outside the CUDA path")
     if isinstance(assay_names, str):
         assay_names = list(se_obj.assays) if assay_names == "All" else [assay_names]
     assay_names = sorted(set(assay_names))                                                     # levels(as.factor(...)), :93-97
@@ -34,7 +34,8 @@ def computePCA(se_obj, assay_names="All", apply_log=True, fast_pca=True, nb_pcs=
     results = {}
     for name in assay_names:
         assay = np.asarray(se_obj.assay(name), dtype=np.float64)                               # genes x samples
-        res = eng.pca(assay.T, k=int(nb_pcs), apply_log=apply_log, pseudo_count=pseudo_count, center=center, scale=scale)
+        k = int(nb_pcs) if fast_pca else min(assay.shape)                                      # :150-190: svd() keeps every triplet
+        res = eng.pca(assay.T, k=k, apply_log=apply_log, pseudo_count=pseudo_count, center=center, scale=scale)
         sv = dict(u=res["u"], d=res["d"], v=res["v"])                                          # rownames: samples / genes
         out = dict(sing_val=sv)
         if return_pc_percentage:                                                               # :137-141
@@ -44,7 +45,8 @@ def computePCA(se_obj, assay_names="All", apply_log=True, fast_pca=True, nb_pcs=
     if not save_se_obj:
         return results
     for name in assay_names:                                                                   # :194-236
-        se_obj.metadata.setdefault("metric", {}).setdefault(name, {})["fastPCA"] = results[name]
-        _printColoredMessage("The PCA results are saved to metadata@metric$%s$fastPCA." % name, verbose)
+        key = "fastPCA" if fast_pca else "PCA"                                                 # :214-236
+        se_obj.metadata.setdefault("metric", {}).setdefault(name, {})[key] = results[name]
+        _printColoredMessage("The PCA results are saved to metadata@metric$%s$%s." % (name, key), verbose)
     _printColoredMessage("------------The computePCA function finished.", verbose)
     return se_obj

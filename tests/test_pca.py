@@ -65,3 +65,43 @@ def test_pca_on_resident_outputs_and_r_api(engine):
         ref = PCAO.fast_pca(se.assays[name], 5, apply_log=False)
         assert np.array_equal(got["variation"], ref["variation"])
         _check(got["sing_val"], ref, 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,k", [((150, 400), 40), ((150, 400), 97), ((120, 50), 50)])
+def test_pca_beyond_32_components(engine, shape, k):
+    """k > 32: library eigensolver for the k leading pairs, projection in chunks of 32 (one full chunk + a ragged one; k = n)."""
+    m1, n = shape
+    p = make_problem(m1=m1, n=n, groups=10, rep=3, n_ctl=20, k=3, seed=m1 + n + k)
+    res = engine.pca(p.assay.T, k=k, apply_log=False, center=True, scale=False)
+    ref = PCAO.fast_pca(p.assay, k, apply_log=False)
+    assert res["u"].shape == (m1, k) and res["v"].shape == (n, k)
+    assert np.allclose(res["d"], ref["d"], rtol=1e-9, atol=1e-9 * ref["d"][0])
+    assert O.rel_frob((res["u"] * res["d"]) @ res["v"].T, (ref["u"] * ref["d"]) @ ref["v"].T) < 1e-9
+    lead = 20                                                    # well-separated components: vectors agree one by one
+    u = O.align_rows_sign(res["u"][:, :lead].T, ref["u"][:, :lead].T).T
+    assert O.rel_frob(u, ref["u"][:, :lead]) < 1e-8
+    assert np.max(np.abs(res["u"].T @ res["u"] - np.eye(k))) < 1e-9                      # orthonormal columns throughout
+    with pytest.raises(rv.RuviiiError):
+        engine.pca(p.assay.T, k=min(m1, n) + 1)
+
+
+@pytest.mark.gpu
+def test_compute_pca_full_svd(engine):
+    """fast.pca = FALSE (computePCA.R:150-190): every singular triplet, saved under metadata$metric$<assay>$PCA.  The centred
+    matrix has rank m1 - 1: the last value is rounding noise in both implementations and is left out of the comparison."""
+    p = make_problem(m1=70, n=300, groups=6, rep=3, n_ctl=20, k=3, seed=5, counts=True)
+    se = rv.SummarizedExperiment(assays={"counts": p.assay}, col_names=p.sample_names)
+    api.set_engine(engine)
+    try:
+        se = computePCA(se, "counts", apply_log=True, fast_pca=False, nb_pcs=None, verbose=False)
+    finally:
+        api.set_engine(None)
+    got = se.metadata["metric"]["counts"]["PCA"]
+    ref = PCAO.fast_pca(p.assay, 70, apply_log=True)
+    d, dr = got["sing_val"]["d"], ref["d"]
+    assert d.shape == (70,) and got["sing_val"]["u"].shape == (70, 70) and got["sing_val"]["v"].shape == (300, 70)
+    assert np.allclose(d[:69], dr[:69], rtol=1e-9) and d[69] < 1e-6 * d[0]
+    assert np.array_equal(got["variation"], ref["variation"])
+    sv = got["sing_val"]
+    assert O.rel_frob((sv["u"][:, :69] * d[:69]) @ sv["v"][:, :69].T, (ref["u"][:, :69] * dr[:69]) @ ref["v"][:, :69].T) < 1e-9

@@ -35,7 +35,7 @@ def test_shim_compiles_and_registers_the_declared_boundary(driver):
     legacy = {"fastResidop": 2, "fastResidop2": 2, "matrixMult": 2, "matSubtraction": 2, "matTranspose": 1, "matInverse": 1}
     for name, nargs in legacy.items():
         assert reg.get("_RUVIIIPRPS_" + name) == nargs
-    for name, nargs in {"ruvIIICore": 9, "setEta": 1, "prpsMeans": 5, "fastPCA": 6, "geneStats": 5}.items():
+    for name, nargs in {"ruvIIICore": 9, "setEta": 1, "prpsMeans": 5, "fastPCA": 6, "geneStats": 5, "regressOut": 4}.items():
         assert reg.get("_RUVIIIPRPS_" + name) == nargs
     assert reg["dynamic_symbols"] == 0
 
