@@ -53,6 +53,7 @@ struct PersistArgs {
     int ldg;                      // row pitch of the shared-memory copy of this CTA's rows of G (GS kernels)
     double tol;
     int max_iter, first, period, cheb, jorder;
+    double skip_minp;             // an orthogonalisation whose smallest pivot was above this lets the next product go without one (0: never)
     unsigned* bar;                // [0] barrier counter, [1] exit counter
     int* state;                   // [0] converged, [1] G products, [2] Cholesky breakdown, [3] Jacobi sweeps, [4] RR count,
                                   // [5] second CholQR rounds, [6] Chebyshev products
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
 
     // One round of column-scaled Cholesky QR of the rows in `src` (partials -> reduce -> Cholesky -> substitution);
     // with `have_S` the reduced S is already in sm.S.  Leaves Q_blk in sm.Q; returns false on a Cholesky breakdown.
-    auto ortho = [&](const double (*src)[PS], bool have_S) -> bool {
+    double first_minp = 0.0;                                  // smallest pivot of the first round of the last ortho()
+    auto ortho = [&](const double (*src)[PS], bool have_S, bool accurate) -> bool {
         for (int round = 0; round < 2; ++round) {
             if (!(round == 0 && have_S)) {
                 partials_phase(a, round == 0 ? src : sm.Q, false, sm);
@@ -469,8 +471,10 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             apply_phase(a, round == 0 ? src : sm.Q, sm);
             trace_mark(a, ntrace, PH_APPLY);
             // kappa^2 of the scaled block ~ 1 / min pivot: below 1e-4 the orthogonality error of one round exceeds ~1e-12,
-            // so the block is orthogonalised once more (Cholesky QR 2); every CTA sees the same pivots and takes the same branch
-            if (sm.minp >= 1e-4) break;
+            // so the block is orthogonalised once more (Cholesky QR 2); every CTA sees the same pivots and takes the same branch.
+            // A block that only feeds the next product (not a Rayleigh-Ritz step) may be 1e-6 away from orthonormal.
+            if (round == 0) first_minp = sm.minp;
+            if (sm.minp >= (accurate ? 1e-4 : 1e-10)) break;
             if (round == 0 && cta == 0 && tid == 0) a.state[5] += 1;
         }
         return true;
@@ -498,7 +502,9 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
     }
     __syncthreads();
     bool ok = true;
-    int converged = 0, it = 0, n_rr = 0, n_cheb = 0;
+    int converged = 0, it = 0, n_rr = 0, n_cheb = 0, n_skip = 0;
+    bool skipped_last = true;                                 // the first pass always orthogonalises
+    double last_minp = 0.0;
     store_rows(a, Qbuf[cur], sm.Q, r0);
     gbar();
     int next_rr = a.first;
@@ -508,7 +514,22 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
         trace_mark(a, ntrace, PH_PRODUCT);
         const bool rr = it >= next_rr;
         if (!rr) {
-            ok = ortho(sm.Z, false);
+            // G (G Q) spans what G orth(G Q) spans: when the last Cholesky QR found the (column-scaled) block well conditioned
+            // -- the block is close to invariant, G Q ~ Q Lambda -- the next product starts from the unnormalised rows and
+            // the orthogonalisation (partials, two grid barriers, Cholesky, substitution: 23 k cycles at C3, more than the
+            // product itself) is done once for two products.  Never twice in a row, never right before a Rayleigh-Ritz step.
+            const bool skip = a.skip_minp > 0.0 && it >= 2 && !skipped_last && it + 1 < next_rr && last_minp >= a.skip_minp;
+            if (skip) {
+                store_rows(a, Qbuf[cur ^ 1], sm.Z, r0);
+                gbar();
+                cur ^= 1;
+                skipped_last = true;
+                ++n_skip;
+                continue;
+            }
+            ok = ortho(sm.Z, false, it + 1 >= next_rr);
+            last_minp = skipped_last ? sqrt(first_minp) : first_minp;      // per product
+            skipped_last = false;
             if (!ok) break;
             store_rows(a, Qbuf[cur ^ 1], sm.Q, r0);
             gbar();
@@ -637,7 +658,8 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
             __syncthreads();
             for (int e = tid; e < PB * PB; e += PT) sm.S[e / PB][e % PB] = sm.L[e / PB][e % PB];
             __syncthreads();
-            ok = ortho(sm.Z, true);
+            ok = ortho(sm.Z, true, true);
+            last_minp = first_minp; skipped_last = false;
             next_rr = it + a.period;
         } else {
             const double need = log(fmax(10.0 * worst / (a.tol * th0), 2.0));
@@ -680,9 +702,10 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
                 gain += log(cosh((double)d * ak));
                 for (int e = tid; e < RB * PB; e += PT) { const int r = e / PB, c = e - r * PB; sm.Z[r][c] = sm.Q[r][c]; }
                 __syncthreads();
-                ok = ortho(sm.Z, false);
+                ok = ortho(sm.Z, false, true);
                 if (!ok) break;
             }
+            skipped_last = true;                             // no skipping on what the filter rounds left
             next_rr = it + 1;                                // Rayleigh-Ritz right after the next product
         }
         if (!ok) break;
@@ -704,6 +727,7 @@ __global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
         a.state[2] = ok ? 0 : (sm.bad ? sm.bad : -1);
         a.state[4] = n_rr;
         a.state[6] = n_cheb;
+        a.state[7] = n_skip;
         if (a.flag_out) *a.flag_out = converged ? 0.0 : 1.0;
     }
     trace_mark(a, ntrace, PH_END);
@@ -776,6 +800,8 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
     a.cheb = cheb_env;
     static const int jorder_env = [] { const char* v = std::getenv("RUVIII_EIG_JORDER"); return v && *v ? std::atoi(v) : 0; }();
     a.jorder = jorder_env;
+    static const double skip_env = [] { const char* v = std::getenv("RUVIII_EIG_SKIP"); return v && *v ? std::atof(v) : 1e-3; }();
+    a.skip_minp = skip_env;
     a.bar = reinterpret_cast<unsigned*>(w.state + 8);
     a.state = w.state;
     // RB = 8: the CTA's 8 rows of G (8 R doubles, pitch = 4 mod 16 doubles so that the 8 x 4 fragment loads of a warp spread
@@ -809,8 +835,8 @@ TopkResult topk_eigen_persistent(const double* G, int R, int kk, int kp, int n_k
         const int n = (int)std::min<long long>(t[kMaxTrace], kMaxTrace);
         static const char* names[] = {"?", "start", "product", "partials", "bar", "reduce", "chol", "apply", "jacobi", "rotate", "check",
                                       "cheb", "end"};
-        fprintf(stderr, "[eig persist] R=%d RB=%d P=%d converged=%d products=%d rr=%d sweeps=%d chol2=%d cheb=%d; cycles:", R, rb, a.P,
-                h_state[0], h_state[1], h_state[4], h_state[3], h_state[5], h_state[6]);
+        fprintf(stderr, "[eig persist] R=%d RB=%d P=%d converged=%d products=%d rr=%d sweeps=%d chol2=%d cheb=%d skipped=%d; cycles:", R, rb, a.P,
+                h_state[0], h_state[1], h_state[4], h_state[3], h_state[5], h_state[6], h_state[7]);
         for (int i = 1; i < n; ++i)
             fprintf(stderr, " %s=%lld", names[std::min<long long>(t[i] >> 48, 12)], (t[i] & 0xFFFFFFFFFFFFll) - (t[i - 1] & 0xFFFFFFFFFFFFll));
         fprintf(stderr, " total=%lld\n", n > 1 ? (t[n - 1] & 0xFFFFFFFFFFFFll) - (t[0] & 0xFFFFFFFFFFFFll) : 0);

@@ -249,6 +249,9 @@ double* p2p_carve(ruviii_handle* h, size_t count) {
 bool p2p_allreduce(ruviii_handle* h, double* buf, size_t count) {
     P2PState* st = h->p2p;
     if (!st || !st->ready || !h->multi_process) return false;
+    // the same decision on every rank (it depends on the payload only): the inbox parity below counts calls
+    static const int64_t min_bytes = (int64_t)env_int("RUVIII_P2P_MIN_KB", 3072) * 1024;
+    if ((int64_t)count * 8 < min_bytes) return false;        // small payloads: NCCL's low-latency protocol wins (r2p2: 22 vs 38 us)
     const int W = h->world;
     const int64_t slice = round_up(ceil_div((int64_t)count, W), 2);
     if ((size_t)slice * W > st->cap_inbox) return false;
