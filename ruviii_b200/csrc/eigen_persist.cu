@@ -228,6 +228,10 @@ __device__ __forceinline__ void cholesky_phase(Smem& sm) {
         for (int c = 0; c < PB; ++c) a[c] = 0.5 * (sm.S[i][c] + sm.S[c][i]) * di * sm.dscale[c];
         int bad = 0;
         double minp = 1.0;
+        // column j of L goes through shared memory (one store per lane, then broadcast 16-byte loads): per trailing column
+        // one LDS.128 per two columns instead of two SHFL per column -- the step is bound by the issue rate of the
+        // shuffle / shared-memory queue, not by its ~130-cycle dependency chain
+        double* col = sm.part;                                // 16-byte aligned scratch, free between reduce and product
 #pragma unroll
         for (int j = 0; j < PB; ++j) {
             const double pj = __shfl_sync(full, a[j], j);
@@ -236,8 +240,18 @@ __device__ __forceinline__ void cholesky_phase(Smem& sm) {
             minp = fmin(minp, pj);
             const double lij = a[j] * rd;                    // L[i][j] for i >= j
             sm.L[i][j] = i > j ? lij : (i == j ? rd : 0.0);  // diagonal: 1 / L[j][j]
+            if (j + 1 < PB) {
+                col[(j & 1) * PB + i] = lij;
+                __syncwarp();
+                const double* cj = col + (j & 1) * PB;
+                if (((j + 1) & 1) != 0) a[j + 1] = fma(-lij, cj[j + 1], a[j + 1]);      // odd first column, then aligned pairs
 #pragma unroll
-            for (int c = j + 1; c < PB; ++c) a[c] = fma(-lij, __shfl_sync(full, lij, c), a[c]);
+                for (int c = (j + 2) & ~1; c < PB; c += 2) {
+                    const double2 l2 = *reinterpret_cast<const double2*>(cj + c);
+                    a[c] = fma(-lij, l2.x, a[c]);
+                    a[c + 1] = fma(-lij, l2.y, a[c + 1]);
+                }
+            }
         }
         if (i == 0) { sm.bad = bad; sm.minp = minp; }
     }
@@ -434,7 +448,7 @@ __device__ __forceinline__ void small_mm(double (*dst)[PS], const double (*lhs)[
 enum Phase { PH_START = 1, PH_PRODUCT, PH_PARTIALS, PH_BAR, PH_REDUCE, PH_CHOL, PH_APPLY, PH_JACOBI, PH_ROTATE, PH_CHECK, PH_CHEB, PH_END };
 
 template <int RT, bool GS>
-__global__ void __launch_bounds__(PT, 2) ek_persistent_kernel(PersistArgs a) {
+__global__ void __launch_bounds__(PT, 1) ek_persistent_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     double* gs = reinterpret_cast<double*>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));   // GS: RB x ldg doubles behind Smem
