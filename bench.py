@@ -74,42 +74,91 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the resident leg
+    is tens of milliseconds, shorter than one period of `nvidia-smi -lms`, so the samples come from NVML itself (the library
+    nvidia-smi reads), polled every ~2 ms by a thread between start and stop; `nvidia-smi -lms 100` is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []           # (time, sm_mhz, max_mhz, set of reasons)
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)          # fails here rather than in the thread
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _reasons_nvml(self):
+        nv = self.nvml
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        mask = int(get(self.handle))
+        names = {"hw_slowdown": ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": ("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": ("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": ("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        out = set()
+        for nm, (a, b, default) in names.items():
+            bit = getattr(nv, a, None) or getattr(nv, b, None) or default
+            if mask & int(bit):
+                out.add(nm)
+        return out
+
+    def _poll_nvml(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                self.rows.append((time.perf_counter(), mhz, self.max_mhz, self._reasons_nvml()))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                reasons = {nm for i, nm in enumerate(names) if len(r) > 5 + i and r[5 + i].lower().startswith("active")}
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), reasons))
+            except Exception:
+                pass
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows]
-        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"], "samples": 0}
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self._stop.set()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if not rows:                                   # nothing landed inside: the samples closest to it (the GPU was still loaded)
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+            window = "nearest to the timed region"
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
-            for i, nm in enumerate(names):
-                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+            reasons |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                "sm_max_mhz": max(r[2] for r in rows) if rows else None, "reasons": sorted(reasons), "samples": len(rows),
+                "source": "NVML" if self.nvml is not None else "nvidia-smi -lms 100", "window": window}
 
 
 def cpu_reference_run(sample, ks, threads_note=True):

@@ -24,5 +24,7 @@ PY
 timeout -s KILL 400 python bench.py --impl reference > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "reference arm exit $?"; cut -c1-600 $OUT/bench_reference.json
 RUVIII_EIG_TRACE=1 timeout -s KILL 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > $OUT/bench_trace.json 2> $OUT/bench_trace.err; echo "trace exit $?"
 timeout -s KILL 400 python scripts/bench_aux.py > $OUT/aux.json 2> $OUT/aux.err; echo "aux exit $?"; cut -c1-700 $OUT/aux.json
+if [ "$2" = "full-ref" ]; then
 ( time timeout -s KILL 1200 python bench.py --impl reference --ref-full --workload C3 --steps 1 --warmup 0 ) > $OUT/reference_full_C3.json 2> $OUT/reference_full_C3.err
 echo "ref full exit $?"; cut -c1-900 $OUT/reference_full_C3.json; tail -4 $OUT/reference_full_C3.err
+fi

@@ -4,8 +4,12 @@
 TAG=${1:-r2ncu}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout -s KILL 900 python -m pytest tests/test_prps.py tests/test_ncg.py tests/test_pca.py -m gpu -q -x --timeout 600 > $OUT/pytest_sel.log 2>&1; echo "pytest sel exit $?" | tee -a $OUT/pytest_sel.log
-tail -4 $OUT/pytest_sel.log
+timeout -s KILL 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "default bench exit $?"
+python -c "
+import json,sys
+d=json.loads(open('$OUT/bench.json').read().strip().splitlines()[-1])
+print('  ms/step %.3f e2e %.1f pageable %.1f clocks %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e_pageable']['ms_per_step'], d['clocks']))
+"
 CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-extra"
 timeout -s KILL 300 $CMD > $OUT/plain.log 2>&1 && \
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
