@@ -61,21 +61,30 @@ constexpr int kProjThreads = 128;
 constexpr int kProjRows = 32;                      // rows staged per step
 
 // KU <= KP: columns of U that are not padding (a multiple of 4): the others are neither accumulated nor read.
-// Eight rows are requested before any of them is used -- 8 x 16 B in flight per thread, four CTAs per SM: the kernel is a
-// stream over Y0 with 2 KU DFMA per 16 bytes, and with four rows in flight at three CTAs per SM it reached 2.0 TB/s.
+// The kernel is a stream over Y0 with 2 KU DFMA per 16 bytes.  Each thread keeps TWO batches of eight rows in registers:
+// the loads of the next batch are issued before the current one is used, so a warp always has 8 x 16 B per thread in
+// flight.  (Four rows in flight, three CTAs per SM: 2.0 TB/s.  Eight rows, four CTAs, but load -> wait -> compute in turn:
+// 3.4 TB/s -- the kernel lasted as long as one warp's chain of 16 exposed memory latencies.)
 template <int KP, int KU>
-__global__ void __launch_bounds__(kProjThreads, KU <= 16 ? 4 : (KU <= 24 ? 3 : 2))
+__global__ void __launch_bounds__(kProjThreads, KU <= 12 ? 4 : (KU <= 24 ? 3 : 2))
 project_kernel(const double* __restrict__ Y0, int64_t ldY0, int R, int n_pairs, const double* __restrict__ U,
                int rows_per_split, double* __restrict__ part, int64_t ld) {
     __shared__ __align__(16) double sU[kProjRows][KU];
     const int pair = blockIdx.x * kProjThreads + threadIdx.x;
     const bool active = pair < n_pairs;
-    const int64_t col = 2 * (int64_t)pair;
+    const int64_t col = 2 * (int64_t)(active ? pair : 0);
     const int r0 = blockIdx.y * rows_per_split;
     const int r1 = min(r0 + rows_per_split, R);
     double2 acc[KU];
 #pragma unroll
     for (int j = 0; j < KU; ++j) acc[j] = make_double2(0.0, 0.0);
+    double2 y[8], yn[8];
+    auto load8 = [&](double2 (&dst)[8], int row) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            dst[u] = (row + u < r1) ? ld_stream(Y0 + (int64_t)(row + u) * ldY0 + col) : make_double2(0.0, 0.0);
+    };
+    if (r0 < r1) load8(y, r0);
     for (int rb = r0; rb < r1; rb += kProjRows) {
         const int nr = min(kProjRows, r1 - rb);
         __syncthreads();
@@ -84,26 +93,22 @@ project_kernel(const double* __restrict__ Y0, int64_t ldY0, int R, int n_pairs, 
             sU[rr][j] = rr < nr ? U[(int64_t)(rb + rr) * KP + j] : 0.0;
         }
         __syncthreads();
-        if (active) {
 #pragma unroll 1
-            for (int rr = 0; rr < kProjRows; rr += 8) {
-                if (rr >= nr) break;
-                double2 y[8];
+        for (int rr = 0; rr < kProjRows; rr += 8) {
+            if (rr >= nr) break;
+            load8(yn, rb + rr + 8);                               // rows past r1 come back as zeros without a load
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    y[u] = (rr + u < nr) ? ld_stream(Y0 + (int64_t)(rb + rr + u) * ldY0 + col)
-                                         : make_double2(0.0, 0.0);
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int j = 0; j < KU; j += 2) {
+                    const double2 w = *reinterpret_cast<const double2*>(&sU[rr + u][j]);
+                    acc[j].x = fma(w.x, y[u].x, acc[j].x);
+                    acc[j].y = fma(w.x, y[u].y, acc[j].y);
+                    acc[j + 1].x = fma(w.y, y[u].x, acc[j + 1].x);
+                    acc[j + 1].y = fma(w.y, y[u].y, acc[j + 1].y);
+                }
 #pragma unroll
-                    for (int j = 0; j < KU; j += 2) {
-                        const double2 w = *reinterpret_cast<const double2*>(&sU[rr + u][j]);
-                        acc[j].x = fma(w.x, y[u].x, acc[j].x);
-                        acc[j].y = fma(w.x, y[u].y, acc[j].y);
-                        acc[j + 1].x = fma(w.y, y[u].x, acc[j + 1].x);
-                        acc[j + 1].y = fma(w.y, y[u].y, acc[j + 1].y);
-                    }
-            }
+            for (int u = 0; u < 8; ++u) y[u] = yn[u];
         }
     }
     if (active) {
@@ -359,41 +364,53 @@ ctl_products_mma_kernel(const double* __restrict__ Yc, int64_t ldc, int rows_w, 
     }
 }
 
-// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA: acT is streamed through shared memory in coalesced
-// chunks of 64 control genes; thread (pair e, quarter s) sums rows s, s+4, ... of every chunk and the four
-// quarters are added in a fixed order, so the result is bitwise reproducible.
-constexpr int kAcChunk = 64;
+// Gm[a][b] = sum_c acT[c][a] acT[c][b]   (kp x kp).  One CTA: acT (128 KB at C3) is brought into shared memory in as few
+// chunks as fit (every thread issues all its 16-byte loads before the first wait: one memory round trip per chunk, not one
+// per 64 control genes -- that version took 35 us and was the longest thing in the control-block stage); thread (pair e,
+// quarter s) sums rows s, s+4, ... and the four quarters are added in a fixed order, so the result is bitwise reproducible.
+constexpr int kAcSmemDoubles = 24 * 1024;            // 192 KB of acT per chunk
 __global__ void __launch_bounds__(1024)
-ac_gram_kernel(const double* __restrict__ acT, int n_ctl, int kp, double* __restrict__ Gm) {
-    __shared__ double sA[kAcChunk * kMaxK];
-    __shared__ double sP[4][kMaxK * kMaxK];
+ac_gram_kernel(const double* __restrict__ acT, int n_ctl, int kp, int chunk_rows, double* __restrict__ Gm) {
+    extern __shared__ __align__(16) double ac_smem[];
+    double* sA = ac_smem;                                  // chunk_rows x kp
+    double* sP = ac_smem + (size_t)chunk_rows * kp;        // 4 x kMaxK^2
     const int tid = threadIdx.x;
     const int npair = kp * kp;
     const int quarter = tid / 256, e = tid % 256;       // kp <= 16: one pair per thread; kp = 32: four pairs per thread
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c0 = 0; c0 < n_ctl; c0 += kAcChunk) {
-        const int nc = min(kAcChunk, n_ctl - c0);
+    for (int c0 = 0; c0 < n_ctl; c0 += chunk_rows) {
+        const int nc = min(chunk_rows, n_ctl - c0);
         __syncthreads();
-        for (int i = tid; i < nc * kp; i += 1024) sA[i] = acT[(int64_t)c0 * kp + i];
+        const double2* src = reinterpret_cast<const double2*>(acT + (int64_t)c0 * kp);      // kp is even, rows are contiguous
+        double2* dst = reinterpret_cast<double2*>(sA);
+        const int n2 = nc * kp / 2;
+#pragma unroll 8
+        for (int i = tid; i < n2; i += 1024) dst[i] = src[i];
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int pe = e + u * 256;
             if (pe < npair) {
                 const int a = pe / kp, b = pe - a * kp;
-                double s = acc[u];
-                for (int r = quarter; r < nc; r += 4) s = fma(sA[r * kp + a], sA[r * kp + b], s);
-                acc[u] = s;
+                double s0 = 0.0, s1 = 0.0;                    // two chains: the sum order is still fixed
+                int r = quarter;
+                for (; r + 4 < nc; r += 8) {
+                    s0 = fma(sA[r * kp + a], sA[r * kp + b], s0);
+                    s1 = fma(sA[(r + 4) * kp + a], sA[(r + 4) * kp + b], s1);
+                }
+                if (r < nc) s0 = fma(sA[r * kp + a], sA[r * kp + b], s0);
+                acc[u] += s0 + s1;
             }
         }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int pe = e + u * 256;
-        if (pe < npair) sP[quarter][pe] = acc[u];
+        if (pe < npair) sP[quarter * kMaxK * kMaxK + pe] = acc[u];
     }
     __syncthreads();
-    for (int pe = tid; pe < npair; pe += 1024) Gm[pe] = ((sP[0][pe] + sP[1][pe]) + sP[2][pe]) + sP[3][pe];
+    for (int pe = tid; pe < npair; pe += 1024)
+        Gm[pe] = ((sP[pe] + sP[kMaxK * kMaxK + pe]) + sP[2 * kMaxK * kMaxK + pe]) + sP[3 * kMaxK * kMaxK + pe];
 }
 
 // ---- K5c: column means of A, Cholesky of Gm[:kk,:kk], inverse of the factor -------------------------------
@@ -584,7 +601,10 @@ void launch_ctl_products(RowSrc src, int rows_w, const int* ctl_idx, int n_ctl, 
 }
 
 void launch_ac_gram(const double* acT, int n_ctl, int kp, double* Gm, cudaStream_t s) {
-    ac_gram_kernel<<<1, 1024, 0, s>>>(acT, n_ctl, kp, Gm);
+    const int chunk_rows = std::max(1, std::min(n_ctl, kAcSmemDoubles / kp));
+    const size_t smem = ((size_t)chunk_rows * kp + 4 * kMaxK * kMaxK) * sizeof(double);
+    RUVIII_CUDA_CHECK(cudaFuncSetAttribute(ac_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ac_gram_kernel<<<1, 1024, smem, s>>>(acT, n_ctl, kp, chunk_rows, Gm);
     RUVIII_LAUNCH_CHECK();
 }
 
