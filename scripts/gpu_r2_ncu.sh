@@ -4,6 +4,7 @@
 TAG=${1:-r2ncu}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
+timeout -s KILL 1500 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest gpu exit $?" | tee -a $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
 timeout -s KILL 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "default bench exit $?"
 python -c "
 import json,sys
