@@ -190,3 +190,54 @@ def test_supervised_find_ncg_regress_out(engine, which):
     # correlations are rounded to two decimals before ranking (:276-277): a residual that differs in the last bits can move
     # a gene across a rounding boundary, so allow a handful of swaps at the selection edge
     assert se.metadata["NCG"].sum() == ref.sum() and np.sum(se.metadata["NCG"] != ref) <= 4
+
+
+class _StubEngine:
+    """numpy stand-in for the engine's statistics entry points (tests only): lets the HOST flow of supervisedFindNCG -- which
+    data every test reads, the level filter, rounding, ranking, the rank product -- run without a GPU."""
+
+    def __init__(self):
+        self.reg = None
+
+    @staticmethod
+    def _expr(X, apply_log, pseudo_count):
+        X = np.asarray(X, dtype=np.float64)
+        return np.log2(X + pseudo_count) if apply_log else X
+
+    def regress_out(self, X, design, slot=-1, apply_log=False, pseudo_count=1.0, return_residuals=False):
+        E = self._expr(X, apply_log, pseudo_count)                       # samples x genes
+        self.reg = E - design @ np.linalg.lstsq(design, E, rcond=None)[0]
+        return dict(rank=int(np.linalg.matrix_rank(design)), ms=0.0)
+
+    def _data(self, X, slot, apply_log, pseudo_count):
+        return self.reg if slot == -2 else self._expr(X, apply_log, pseudo_count)
+
+    def gene_stats(self, X=None, groups=None, covariate=None, slot=-1, apply_log=False, pseudo_count=1.0):
+        E = self._data(X, slot, apply_log, pseudo_count)
+        out = dict(F=None, r=None, ms=0.0)
+        if groups is not None:
+            keep = np.asarray(groups) >= 0
+            out["F"] = NO.row_oneway_equalvar_statistic(E[keep].T, np.asarray(groups)[keep])
+        if covariate is not None:
+            out["r"] = NO.correls_pearson(covariate, E)
+        return out
+
+    def gene_spearman(self, X=None, covariate=None, slot=-1):
+        return dict(rho=NO.correls_spearman(covariate, self._data(X, slot, False, 1.0)), ms=0.0)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(corr_method="spearman"), dict(regress_out_uv_variables=True),
+                                  dict(regress_out_bio_variables=True)])
+def test_ncg_host_flow_with_a_stub_engine(opts):
+    counts, cd = _design(m1=120, n=301)
+    se = rv.SummarizedExperiment(assays={"counts": counts}, col_names=["s%d" % i for i in range(counts.shape[1])], col_data=cd)
+    api.set_engine(_StubEngine())
+    try:
+        got = supervisedFindNCG(se, "counts", ["subtype", "purity"], ["plate", "libsize"], no_ncg=40, apply_log=True, pseudo_count=1,
+                                save_se_obj=False, verbose=False, **opts)
+    finally:
+        api.set_engine(None)
+    ref = NO.supervised_find_ncg(counts, cd, ["subtype", "purity"], ["plate", "libsize"], 40, True, 1.0,
+                                 corr_method=opts.get("corr_method", "pearson"), regress_out_uv=opts.get("regress_out_uv_variables", False),
+                                 regress_out_bio=opts.get("regress_out_bio_variables", False))
+    assert got.dtype == bool and np.array_equal(got, ref)

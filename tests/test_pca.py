@@ -105,3 +105,33 @@ def test_compute_pca_full_svd(engine):
     assert np.array_equal(got["variation"], ref["variation"])
     sv = got["sing_val"]
     assert O.rel_frob((sv["u"][:, :69] * d[:69]) @ sv["v"][:, :69].T, (ref["u"][:, :69] * dr[:69]) @ ref["v"][:, :69].T) < 1e-9
+
+
+class _StubPcaEngine:
+    """numpy stand-in for ruviii_pca (tests only): the HOST flow of computePCA -- which k is asked for, where the result is
+    saved, the percentages -- without a GPU."""
+
+    def __init__(self):
+        self.calls = []
+
+    def pca(self, X, k=10, apply_log=False, pseudo_count=1.0, center=True, scale=False, **_):
+        self.calls.append(k)
+        ref = PCAO.fast_pca(np.asarray(X).T, k, apply_log, pseudo_count, center, scale)
+        return dict(u=ref["u"], d=ref["d"], v=ref["v"])
+
+
+def test_compute_pca_host_flow_with_a_stub_engine():
+    assay = np.random.default_rng(9).normal(8.0, 2.0, (90, 40))           # genes x samples
+    se = rv.SummarizedExperiment(assays={"a": assay, "b": assay * 2.0}, col_names=["s%d" % i for i in range(40)])
+    stub = _StubPcaEngine()
+    api.set_engine(stub)
+    try:
+        se = computePCA(se, "All", apply_log=False, fast_pca=True, nb_pcs=7, verbose=False)
+        se = computePCA(se, "b", apply_log=False, fast_pca=False, nb_pcs=None, verbose=False)
+    finally:
+        api.set_engine(None)
+    assert stub.calls == [7, 7, 40]                                         # svd() keeps min(samples, genes) triplets
+    assert set(se.metadata["metric"]["a"]) == {"fastPCA"} and set(se.metadata["metric"]["b"]) == {"fastPCA", "PCA"}
+    full = se.metadata["metric"]["b"]["PCA"]
+    assert full["sing_val"]["u"].shape == (40, 40) and full["sing_val"]["v"].shape == (90, 40)
+    assert abs(full["variation"].sum() - 100.0) < 2.0 and full["variation"][0] >= full["variation"][1]
