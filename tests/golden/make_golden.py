@@ -20,6 +20,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 
+from oracle import ncg_oracle as NO            # noqa: E402
+from oracle import pca_oracle as PCAO          # noqa: E402
 from oracle import ruviii_oracle as O          # noqa: E402
 from ruviii_b200.synth import make_problem     # noqa: E402
 
@@ -89,6 +91,25 @@ def main():
             Le = O.ruvIII_literal(c["assay"], c["sample_names"], c["replicate_data"], c["replicate_names"], c["ctl"],
                                   c["k"], apply_log=False, eta=eta, include_intercept=True)
             meta["dims"]["ruvIII.eta.newY"] = put(case, "ruvIII.eta.newY", Le["newY"])
+        # the steps either side of the path whose reference semantics are BASE R: lm residuals, one-way ANOVA F,
+        # Pearson / Spearman correlation, svd of the centred matrix -- replay.R checks these without any add-on package
+        if case == "mid":
+            m1 = c["assay"].shape[1]
+            batch = ["b%d" % ((i * 7 + i // 5) % 5) for i in range(m1)]
+            cov = np.sin(np.arange(m1) * 0.61) + 0.02 * np.arange(m1)
+            cov[::9] = cov[0]                                           # ties for Spearman
+            meta["side_batch"] = batch
+            meta["dims"]["side.covariate"] = put(case, "side.covariate", cov[:, None])
+            cd = {"batch": batch, "cov": list(cov)}
+            meta["dims"]["side.lm_residuals"] = put(case, "side.lm_residuals", NO.lm_residuals(c["assay"], cd, ["batch", "cov"]))
+            meta["dims"]["side.anovaF"] = put(case, "side.anovaF", NO.row_oneway_equalvar_statistic(c["assay"], np.asarray(batch))[:, None])
+            meta["dims"]["side.pearson"] = put(case, "side.pearson", NO.correls_pearson(cov, c["assay"].T)[:, None])
+            meta["dims"]["side.spearman"] = put(case, "side.spearman", NO.correls_spearman(cov, c["assay"].T)[:, None])
+            sv = PCAO.fast_pca(c["assay"], min(c["assay"].shape), apply_log=False)
+            meta["dims"]["side.svd_d"] = put(case, "side.svd_d", sv["d"][:, None])
+            meta["dims"]["side.svd_rank10"] = put(case, "side.svd_rank10", (sv["u"][:, :10] * sv["d"][:10]) @ sv["v"][:, :10].T)
+            with open(os.path.join(HERE, "%s.side_batch.txt" % case), "w") as f:
+                f.write("\n".join(batch) + "\n")
         with open(os.path.join(HERE, "%s.json" % case), "w") as f:
             json.dump(meta, f, indent=1)
         # base-R-readable sidecars for replay.R

@@ -15,6 +15,10 @@
 # is above tolerance, 0 otherwise.  The reference functions are taken from the installed package RUVIIIPRPS when there is
 # one, otherwise source()d from `reference.R.dir` (default: $RUVIIIPRPS_SRC or /root/reference/R).
 #
+# A first part needs BASE R ONLY and pins the statistics either side of the path (lm residuals of regress.out.*, the one-way
+# ANOVA F, Pearson / Spearman correlations, the full svd of computePCA) against stats::lm / oneway.test / cor / svd; it runs
+# even when the Bioconductor packages are missing (the RUV-III part is then skipped, and the script says so).
+#
 # COMPILE-/RUN-UNTESTED in the build container (no R there); base R only apart from the reference's own imports.
 
 args <- commandArgs(trailingOnly = TRUE)
@@ -24,12 +28,19 @@ ref.dir <- if (length(args) >= 2) args[2] else Sys.getenv("RUVIIIPRPS_SRC", "/ro
 tol.newY <- 1e-9
 tol.signed <- 1e-7
 
+have.pkgs <- all(vapply(c("SummarizedExperiment", "ruv", "BiocSingular"), requireNamespace, logical(1), quietly = TRUE))
+if (!have.pkgs) {
+    message("SummarizedExperiment / ruv / BiocSingular not installed: only the BASE-R part (lm residuals, ANOVA F, correlations, svd) runs")
+} else {
 suppressPackageStartupMessages({
     library(SummarizedExperiment)
     library(ruv)
     library(BiocSingular)
 })
-if (requireNamespace("RUVIIIPRPS", quietly = TRUE)) {
+}
+if (!have.pkgs) {
+    ruvIII <- fastruvIII <- ruvIIIMultipleK <- NULL
+} else if (requireNamespace("RUVIIIPRPS", quietly = TRUE)) {
     ruvIII <- RUVIIIPRPS::ruvIII
     fastruvIII <- RUVIIIPRPS::fastruvIII
     ruvIIIMultipleK <- RUVIIIPRPS::ruvIIIMultipleK
@@ -40,8 +51,8 @@ if (requireNamespace("RUVIIIPRPS", quietly = TRUE)) {
         source(file.path(ref.dir, f))
     message("reference: sourced from ", ref.dir)
 }
-message("ruv ", as.character(utils::packageVersion("ruv")), ", BiocSingular ", as.character(utils::packageVersion("BiocSingular")),
-        ", ", R.version.string)
+if (have.pkgs) message("ruv ", as.character(utils::packageVersion("ruv")), ", BiocSingular ", as.character(utils::packageVersion("BiocSingular")))
+message(R.version.string)
 
 read.mat <- function(case, name, dims) {
     d <- dims[dims$name == name, ]
@@ -61,7 +72,41 @@ check <- function(what, err, tol) {
     if (!ok) failures <<- failures + 1
 }
 
-for (case in c("tiny", "mid")) {
+# ---- BASE R ONLY: the statistics either side of the path (SURVEY.md 8f) -------------------------------------------------
+# supervisedFindNCG.R:111-121 lm(t(expr) ~ ...)$residuals; :179-191 row_oneway_equalvar(x, g)$statistic (the classical
+# equal-variance one-way F: stats::oneway.test(var.equal = TRUE)); :214-229 correls(y, x, type)[, "correlation"] (stats::cor);
+# computePCA.R:150-190 svd(scale(t(x), center, scale)).  matrixTests / Rfast are compared too when they happen to be installed.
+for (case in c("mid")) {
+    dims <- read.delim(file.path(golden.dir, paste0(case, ".manifest.tsv")), stringsAsFactors = FALSE)
+    if (!("side.covariate" %in% dims$name)) next
+    assay.mat <- read.mat(case, "assay", dims)                          # genes x samples
+    batch <- factor(readLines(file.path(golden.dir, paste0(case, ".side_batch.txt"))))
+    cov <- as.numeric(read.mat(case, "side.covariate", dims))
+    y <- lm(t(assay.mat) ~ batch + cov)
+    check(paste(case, "lm(t(expr) ~ batch + cov)$residuals"), rel.frob(t(unname(y$residuals)), read.mat(case, "side.lm_residuals", dims)), tol.newY)
+    Fstat <- apply(assay.mat, 1, function(v) unname(oneway.test(v ~ batch, var.equal = TRUE)$statistic))
+    F.ref <- as.numeric(read.mat(case, "side.anovaF", dims))
+    check(paste(case, "one-way ANOVA F (oneway.test, var.equal)"), rel.frob(Fstat, F.ref), tol.newY)
+    if (requireNamespace("matrixTests", quietly = TRUE))
+        check(paste(case, "matrixTests::row_oneway_equalvar statistic"),
+              rel.frob(matrixTests::row_oneway_equalvar(assay.mat, batch)$statistic, F.ref), tol.newY)
+    r.ref <- as.numeric(read.mat(case, "side.pearson", dims))
+    rho.ref <- as.numeric(read.mat(case, "side.spearman", dims))
+    check(paste(case, "Pearson r (stats::cor)"), max(abs(as.numeric(cor(t(assay.mat), cov)) - r.ref)), 1e-12)
+    check(paste(case, "Spearman rho (stats::cor, ties averaged)"), max(abs(as.numeric(cor(t(assay.mat), cov, method = "spearman")) - rho.ref)), 1e-12)
+    if (requireNamespace("Rfast", quietly = TRUE)) {
+        check(paste(case, "Rfast::correls pearson"), max(abs(Rfast::correls(cov, t(assay.mat), type = "pearson")[, "correlation"] - r.ref)), 1e-10)
+        check(paste(case, "Rfast::correls spearman"), max(abs(Rfast::correls(cov, t(assay.mat), type = "spearman")[, "correlation"] - rho.ref)), 1e-10)
+    }
+    sv <- svd(scale(t(assay.mat), center = TRUE, scale = FALSE))
+    d.ref <- as.numeric(read.mat(case, "side.svd_d", dims))
+    nz <- seq_len(length(d.ref) - 1)                                    # the centred matrix has rank m - 1: the last value is noise
+    check(paste(case, "svd(scale(t(x)))$d"), max(abs(sv$d[nz] - d.ref[nz]) / d.ref[1]), 1e-12)
+    check(paste(case, "svd rank-10 reconstruction"),
+          rel.frob(sv$u[, 1:10] %*% (sv$d[1:10] * t(sv$v[, 1:10])), read.mat(case, "side.svd_rank10", dims)), tol.newY)
+}
+
+for (case in if (have.pkgs) c("tiny", "mid") else character(0)) {
     dims <- read.delim(file.path(golden.dir, paste0(case, ".manifest.tsv")), stringsAsFactors = FALSE)
     k <- dims$nrow[dims$name == "k"]
     ks.multi <- dims$nrow[dims$name == "k_multi"]
@@ -124,6 +169,7 @@ for (case in c("tiny", "mid")) {
         check(paste(case, "ruvIII eta (RUV1) newY"), rel.frob(unname(o3$newY), read.mat(case, "ruvIII.eta.newY", dims)), tol.newY)
     }
 }
-cat(if (failures == 0) "PARITY PINNED: every fixture reproduces under the reference\n"
+if (!have.pkgs) cat("NOTE: the RUV-III fixtures were NOT replayed (Bioconductor packages missing); only the base-R statistics were checked\n")
+cat(if (failures == 0) "PARITY PINNED: every fixture that was replayed reproduces under R\n"
     else sprintf("%d comparison(s) above tolerance -- the numpy restatement and the reference disagree\n", failures))
 quit(status = if (failures == 0) 0 else 1)

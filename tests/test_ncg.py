@@ -241,3 +241,20 @@ def test_ncg_host_flow_with_a_stub_engine(opts):
                                  corr_method=opts.get("corr_method", "pearson"), regress_out_uv=opts.get("regress_out_uv_variables", False),
                                  regress_out_bio=opts.get("regress_out_bio_variables", False))
     assert got.dtype == bool and np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_engine_reproduces_the_base_r_side_fixtures(engine, golden_mid):
+    """The CUDA statistics against the golden files replay.R checks with base R (lm, oneway.test, cor, svd): engine -> golden
+    here, golden -> R in one command there."""
+    g = golden_mid
+    assay, batch, cov = g["assay"], np.asarray(g["meta"]["side_batch"]), g["side.covariate"][:, 0]
+    codes = np.unique(batch, return_inverse=True)[1].astype(np.int32)
+    st = engine.gene_stats(assay.T, groups=codes, covariate=cov)
+    assert O.rel_frob(st["F"], g["side.anovaF"][:, 0]) < 1e-10 and np.max(np.abs(st["r"] - g["side.pearson"][:, 0])) < 1e-12
+    assert np.max(np.abs(engine.gene_spearman(assay.T, covariate=cov)["rho"] - g["side.spearman"][:, 0])) < 1e-12
+    res = engine.regress_out(assay.T, model_matrix({"batch": list(batch), "cov": list(cov)}, ["batch", "cov"]), return_residuals=True)
+    assert res["rank"] == 6 and O.rel_frob(res["residuals"].T, g["side.lm_residuals"]) < 1e-11
+    pc = engine.pca(assay.T, k=60, apply_log=False)                        # the full svd of computePCA (fast.pca = FALSE)
+    assert np.allclose(pc["d"][:59], g["side.svd_d"][:59, 0], rtol=1e-9)
+    assert O.rel_frob((pc["u"][:, :10] * pc["d"][:10]) @ pc["v"][:, :10].T, g["side.svd_rank10"]) < 1e-9

@@ -243,3 +243,26 @@ def test_structural_rows_matches_full_structural(prob):
                                         apply_log=False)
     for k in (0, 1, 3, 5):
         assert O.rel_frob(sub[k], full[k]["newY"][rows]) < 1e-12
+
+
+def test_side_fixtures_reproduce_from_the_oracles(golden_mid):
+    """The base-R-checkable fixtures of the steps either side of the path (replay.R, first part): regenerated here from the
+    numpy restatements, and cross-checked by routes that share no code with them (scipy's F test, numpy's corrcoef)."""
+    from scipy import stats
+    from oracle import ncg_oracle as NO
+    from oracle import pca_oracle as PCAO
+    g = golden_mid
+    assay, batch, cov = g["assay"], np.asarray(g["meta"]["side_batch"]), g["side.covariate"][:, 0]
+    cd = {"batch": list(batch), "cov": list(cov)}
+    assert O.rel_frob(NO.lm_residuals(assay, cd, ["batch", "cov"]), g["side.lm_residuals"]) < 1e-12
+    F = np.array([stats.f_oneway(*[row[batch == b] for b in np.unique(batch)]).statistic for row in assay])
+    assert O.rel_frob(F, g["side.anovaF"][:, 0]) < 1e-10
+    r = np.array([np.corrcoef(row, cov)[0, 1] for row in assay])
+    assert np.max(np.abs(r - g["side.pearson"][:, 0])) < 1e-12
+    rho = np.array([stats.spearmanr(row, cov).statistic for row in assay])
+    assert np.max(np.abs(rho - g["side.spearman"][:, 0])) < 1e-12
+    sv = PCAO.fast_pca(assay, 60, apply_log=False)
+    assert np.allclose(sv["d"][:59], g["side.svd_d"][:59, 0], rtol=1e-12)
+    # residuals are orthogonal to the model matrix (intercept, batch dummies, covariate)
+    D = np.stack([np.ones(60)] + [(batch == b).astype(float) for b in np.unique(batch)[1:]] + [cov], axis=1)
+    assert np.max(np.abs(g["side.lm_residuals"] @ D)) < 1e-9
