@@ -7,7 +7,9 @@ choosing the constants without a GPU: prints products / Rayleigh-Ritz steps / fi
 import numpy as np
 
 
-def cholqr(Z, stats):
+def cholqr(Z, stats, accurate=True):
+    """Column-scaled Cholesky QR; a second round below a pivot of 1e-4 (accurate: the block enters a Rayleigh-Ritz step) or
+    1e-10 (the block only feeds the next product).  stats["minp"] = smallest pivot of the first round."""
     for rnd in range(2):
         S = Z.T @ Z
         d = 1.0 / np.sqrt(np.diag(S))
@@ -25,26 +27,39 @@ def cholqr(Z, stats):
             L[j:, j] = A[j:, j] / np.sqrt(pj)
             A[j + 1:, j + 1:] -= np.outer(L[j + 1:, j], L[j + 1:, j])
         Z = np.linalg.solve(L, (Z * d[None, :]).T).T
-        if minp >= 1e-4:
+        if rnd == 0:
+            stats["minp"] = minp
+        if minp >= (1e-4 if accurate else 1e-10):
             break
         if rnd == 0:
             stats["chol2"] += 1
     return Z
 
 
-def solve(G, kk, tol=1e-13, max_iter=150, first=6, period=3, cheb=True, B=32, seed=0):
+def solve(G, kk, tol=1e-13, max_iter=150, first=6, period=3, cheb=True, B=32, seed=0, skip_minp=1e-3):
     R = G.shape[0]
     rng = np.random.default_rng(seed)
-    stats = dict(products=0, rr=0, chol2=0, cheb=0, degs=[])
-    Q = cholqr(rng.uniform(-1, 1, (R, B)), stats)
+    stats = dict(products=0, rr=0, chol2=0, cheb=0, degs=[], qr=0, skipped=0)
+    Q = rng.uniform(-1, 1, (R, B))                  # the kernel's start block is not orthogonalised either
     it, next_rr = 0, first
+    skipped_last, last_minp = True, 0.0
     while it < max_iter:
         it += 1
         Z = G @ Q
         if it < next_rr:
-            Q = cholqr(Z, stats)
+            # one Cholesky QR for two products when the last factorisation found the block well conditioned; never twice
+            # in a row, never right before a Rayleigh-Ritz step (eigen_persist.cu)
+            if skip_minp > 0 and it >= 2 and not skipped_last and it + 1 < next_rr and last_minp >= skip_minp:
+                Q = Z
+                skipped_last = True
+                stats["skipped"] += 1
+                continue
+            Q = cholqr(Z, stats, accurate=it + 1 >= next_rr)
+            stats["qr"] += 1
             if Q is None:
                 return None, stats
+            last_minp = np.sqrt(stats["minp"]) if skipped_last and it > 1 else stats["minp"]
+            skipped_last = False
             continue
         stats["rr"] += 1
         H = Q.T @ Z
@@ -64,6 +79,9 @@ def solve(G, kk, tol=1e-13, max_iter=150, first=6, period=3, cheb=True, B=32, se
         plain = not cheb or not (tk > 1 + 1e-6)
         if plain:
             Q = cholqr(Z, stats)
+            stats["qr"] += 1
+            if Q is not None:
+                last_minp, skipped_last = stats["minp"], False
             next_rr = it + period
         else:
             need = np.log(max(10 * worst / (tol * th0), 2.0))
@@ -93,6 +111,7 @@ def solve(G, kk, tol=1e-13, max_iter=150, first=6, period=3, cheb=True, B=32, se
                 if Y0 is None:
                     return None, stats
             Q = Y0
+            skipped_last = True
             next_rr = it + 1
         if Q is None:
             return None, stats
@@ -110,8 +129,8 @@ def spectrum_case(name, lam, R=800, kk=10, **kw):
     err = None
     if ok:
         err = np.abs(out[0][:kk] - lam[:kk]).max() / lam[0]
-    print("%-28s converged=%s products=%d rr=%d cheb=%d degs=%s chol2=%d resid=%s eval_err=%s" % (
-        name, ok, st["products"], st["rr"], st["cheb"], st["degs"], st["chol2"], st.get("resid"), err))
+    print("%-28s converged=%s products=%d qr=%d skipped=%d rr=%d cheb=%d degs=%s chol2=%d resid=%s eval_err=%s" % (
+        name, ok, st["products"], st["qr"], st["skipped"], st["rr"], st["cheb"], st["degs"], st["chol2"], st.get("resid"), err))
 
 
 if __name__ == "__main__":
@@ -119,6 +138,7 @@ if __name__ == "__main__":
     j = np.arange(R)
     planted = np.where(j < 24, 2.25 * 0.7225 ** j * 3000, 1.0) * (1 + 0.3 * np.random.default_rng(2).random(R)) ** np.where(j < 24, 0, 1)
     spectrum_case("C3-like (planted 24)", np.sort(planted)[::-1])
+    spectrum_case("C3-like, QR after every product", np.sort(planted)[::-1], skip_minp=0.0)
     spectrum_case("C3-like, no chebyshev", np.sort(planted)[::-1], cheb=False)
     flat = np.where(j < 12, 100 * 0.8 ** j, 100 * 0.8 ** 11 * 0.5)
     spectrum_case("flat tail (ratio 0.5)", flat)
